@@ -1,0 +1,76 @@
+// extern "C" boundary of libcadre_sm100.so (declared in include/cadre_b200.h).
+#include "../../include/cadre_b200.h"
+
+#include "internal.h"
+
+namespace cadre {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace cadre
+
+#define CADRE_API_BEGIN try {
+#define CADRE_API_END                                    \
+  }                                                      \
+  catch (const cadre::Error& e) {                        \
+    cadre::set_last_error(e.what());                     \
+    return e.code;                                       \
+  }                                                      \
+  catch (const std::exception& e) {                      \
+    cadre::set_last_error(e.what());                     \
+    return 99;                                           \
+  }                                                      \
+  return 0;
+
+extern "C" {
+
+const char* cadre_last_error(void) { return cadre::g_last_error.c_str(); }
+const char* cadre_version(void) { return "cadre_b200 sm_100a " __DATE__; }
+
+int cadre_gemm(const cadre_gemm_args* s, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(s != nullptr, "args");
+  cadre::GemmArgs a;
+  a.kind = s->kind, a.a_mn = s->a_mn, a.b_mn = s->b_mn, a.batch = s->batch;
+  a.M = s->M, a.N = s->N, a.K = s->K, a.block_n = s->block_n;
+  a.A = s->A, a.B = s->B, a.lda = s->lda, a.a_bs = s->a_bs, a.ldb = s->ldb, a.b_bs = s->b_bs;
+  a.out = s->out, a.ldc = s->ldc, a.out_bs = s->out_bs, a.out_f32 = s->out_f32, a.act = s->act;
+  a.bias = s->bias, a.bias_bs = s->bias_bs;
+  a.res = s->res, a.ldr = s->ldr, a.res_bs = s->res_bs, a.res_after_act = s->res_after_act;
+  a.mask = s->mask, a.ldm = s->ldm, a.mask_bs = s->mask_bs;
+  a.batch_rows = s->batch_rows, a.rows_is_k = s->rows_is_k;
+  a.alpha = s->alpha, a.epi = s->epi;
+  a.xpart = s->xpart, a.c_prev = s->c_prev, a.c_out = s->c_out, a.h_out = s->h_out;
+  a.gates_out = s->gates_out, a.ldx = s->ldx, a.x_bs = s->x_bs, a.ldh = s->ldh, a.h_bs = s->h_bs;
+  cadre::launch_gemm(a, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const void* w, int Cout, int KH,
+                      int KW, int stride, int pad, const float* bias, const void* res, int res_after_act,
+                      int act, void* out, void* stream) {
+  CADRE_API_BEGIN
+  cadre::ConvArgs a;
+  a.in = static_cast<const __nv_bfloat16*>(in);
+  a.B = B, a.Hin = Hin, a.Win = Win, a.Cin = Cin;
+  a.w = static_cast<const __nv_bfloat16*>(w);
+  a.Cout = Cout, a.KH = KH, a.KW = KW, a.stride = stride, a.pad = pad;
+  a.bias = bias, a.res = static_cast<const __nv_bfloat16*>(res), a.res_after_act = res_after_act;
+  a.act = act, a.out = static_cast<__nv_bfloat16*>(out);
+  cadre::launch_conv(a, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+int cadre_stem_conv(const void* in_padded, int B, const void* w256, const float* bias, void* out,
+                    void* stream) {
+  CADRE_API_BEGIN
+  cadre::StemArgs a;
+  a.in = static_cast<const __nv_bfloat16*>(in_padded);
+  a.B = B;
+  a.w = static_cast<const __nv_bfloat16*>(w256);
+  a.bias = bias;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  cadre::launch_stem(a, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+}  // extern "C"

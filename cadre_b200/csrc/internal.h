@@ -1,0 +1,95 @@
+// Internal (C++) declarations shared between the translation units of libcadre_sm100.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace cadre {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define CADRE_CUDA_CHECK(expr)                                                                       \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      throw ::cadre::Error(2, std::string(#expr) + " -> " + cudaGetErrorString(e__) + " at " + __FILE__ + \
+                                  ":" + std::to_string(__LINE__));                                   \
+  } while (0)
+
+#define CADRE_REQUIRE(cond, msg)                                              \
+  do {                                                                        \
+    if (!(cond)) throw ::cadre::Error(1, std::string("invalid argument: ") + (msg)); \
+  } while (0)
+
+// ------------------------------------------------------------------ dense tile kernel (tc_gemm.cu)
+// D[M,N] = act(alpha * A*B^T + bias + res) ...; operands are either K-major ([rows=M|N][K], ld = row stride)
+// or MN-major ([rows=K][M|N], ld = row stride). kind 0 = bf16 operands, 1 = fp32 operands fed as TF32.
+struct GemmArgs {
+  int kind = 0, a_mn = 0, b_mn = 0;
+  const void* A = nullptr;
+  long long lda = 0, a_bs = 0;
+  const void* B = nullptr;
+  long long ldb = 0, b_bs = 0;
+  int M = 0, N = 0, K = 0, batch = 1;
+  void* out = nullptr;
+  int out_f32 = 0;
+  long long ldc = 0, out_bs = 0;
+  const float* bias = nullptr;
+  long long bias_bs = 0;
+  const void* res = nullptr;
+  long long ldr = 0, res_bs = 0;
+  int res_after_act = 0;
+  const void* mask = nullptr;
+  long long ldm = 0, mask_bs = 0;
+  int act = 0;
+  float alpha = 1.f;
+  const int* batch_rows = nullptr;
+  int rows_is_k = 0;
+  int block_n = 0;  // 0 = choose
+  // LSTM-cell epilogue (epi = 1)
+  int epi = 0;
+  const float* xpart = nullptr;
+  long long ldx = 0, x_bs = 0;
+  const float* c_prev = nullptr;
+  float* c_out = nullptr;
+  float* h_out = nullptr;
+  float* gates_out = nullptr;
+  long long ldh = 0, h_bs = 0;
+};
+void launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+// Implicit-GEMM convolution over NHWC bf16 activations; weights [Cout][KH][KW][Cin] bf16 (BN folded).
+struct ConvArgs {
+  const __nv_bfloat16* in = nullptr;  // [B][Hin][Win][Cin]
+  int B = 0, Hin = 0, Win = 0, Cin = 0;
+  const __nv_bfloat16* w = nullptr;  // [Cout][KH*KW*Cin]
+  int Cout = 0, KH = 1, KW = 1, stride = 1, pad = 0;
+  const float* bias = nullptr;        // [Cout]
+  const __nv_bfloat16* res = nullptr; // [B][Hout][Wout][Cout] or null
+  int res_after_act = 0;
+  int act = 0;
+  __nv_bfloat16* out = nullptr;  // [B][Hout][Wout][Cout]
+};
+void launch_conv(const ConvArgs& a, cudaStream_t stream);
+
+// 7x7/s2/p3 stem over the padded 4-channel bf16 image [B][150][262][4]; weights [64][256] (K = 4 row pairs x
+// 2 rows x 8 pixels x 4 ch, zero where kh==7 or kw==7); output [B][72][128][64].
+struct StemArgs {
+  const __nv_bfloat16* in = nullptr;
+  int B = 0;
+  const __nv_bfloat16* w = nullptr;
+  const float* bias = nullptr;
+  __nv_bfloat16* out = nullptr;
+};
+void launch_stem(const StemArgs& a, cudaStream_t stream);
+
+}  // namespace cadre

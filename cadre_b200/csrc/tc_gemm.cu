@@ -1,0 +1,227 @@
+// Host side of the tcgen05 tile kernel: TMA tensor-map construction and template dispatch.
+#include "internal.h"
+#include "tc_gemm.cuh"
+
+#include <mutex>
+
+namespace cadre {
+
+// ---------------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) throw Error(3, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+// dims/box innermost first; strides_bytes has rank-1 entries (dimension 0 is contiguous).
+static void make_map(CUtensorMap* m, int es, int rank, const void* base, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool atom32 = false) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CADRE_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "TMA base address must be 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    CADRE_REQUIRE(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA strides must be positive multiples of 16 bytes");
+  CUresult r = encode_fn()(m, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                           rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+}
+
+// matrix operand map: K-major -> dims {K, rows, batch}, box {BK, box_rows, 1};
+//                     MN-major -> dims {rows(MN), K, batch}, box {CHUNK, BK, 1}
+static void make_operand_map(CUtensorMap* m, int es, bool mn_major, const void* base, long long ld,
+                             long long bs, int mn, int k, int batch, int box_rows) {
+  const int bk = 128 / es;
+  uint64_t dims[3], str[2];
+  uint32_t box[3];
+  const long long rows_stored = mn_major ? k : mn;
+  str[0] = static_cast<uint64_t>(ld) * es;
+  str[1] = static_cast<uint64_t>(batch > 1 ? bs : ld * rows_stored) * es;
+  if (str[1] == 0 || str[1] % 16) str[1] = 16;  // batch == 1: never dereferenced beyond index 0
+  if (mn_major) {
+    dims[0] = mn, dims[1] = k, dims[2] = batch;
+    box[0] = bk, box[1] = bk, box[2] = 1;
+  } else {
+    dims[0] = k, dims[1] = mn, dims[2] = batch;
+    box[0] = bk, box[1] = box_rows, box[2] = 1;
+  }
+  // MN-major fp32 (TF32) operands only exist in the 128B swizzle with 32-byte atoms (UMMA layout type 1)
+  make_map(m, es, 3, base, dims, str, box, mn_major && es == 4);
+}
+
+template <int KIND, int A_MN, int B_MN, int BN, int STAGES, int MODE, int EPI, typename OutT>
+static void launch_inst(const TcGemmParams& p, dim3 grid, cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, STAGES, MODE, EPI, OutT>;
+  constexpr int smem = TcGemmSmem<KIND, BN, STAGES>::TOTAL;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, 192, smem, stream>>>(p);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
+  p.out = a.out, p.ldc = a.ldc, p.out_bs = a.out_bs;
+  p.bias = a.bias, p.bias_bs = a.bias_bs;
+  p.res = a.res, p.ldr = a.ldr, p.res_bs = a.res_bs, p.res_after_act = a.res_after_act;
+  p.mask = a.mask, p.ldm = a.ldm, p.mask_bs = a.mask_bs;
+  p.act = a.act, p.alpha = a.alpha;
+  p.batch_rows = a.batch_rows, p.rows_is_k = a.rows_is_k;
+  p.xpart = a.xpart, p.ldx = a.ldx, p.x_bs = a.x_bs;
+  p.c_prev = a.c_prev, p.c_out = a.c_out, p.h_out = a.h_out, p.gates_out = a.gates_out;
+  p.ldh = a.ldh, p.h_bs = a.h_bs;
+}
+
+void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  CADRE_REQUIRE(a.M > 0 && a.N > 0 && a.K >= 0 && a.batch > 0, "gemm dims");
+  CADRE_REQUIRE(a.A && a.B && (a.out || a.epi == EPI_LSTM), "gemm pointers");
+  const int es = a.kind ? 4 : 2;
+  const int bk = 128 / es;
+  int bn = a.block_n ? a.block_n : (a.N <= 64 ? 64 : 128);
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  make_operand_map(&p.tmA[0], es, a.a_mn, a.A, a.lda, a.a_bs, a.M, a.K, a.batch, 128);
+  make_operand_map(&p.tmB, es, a.b_mn, a.B, a.ldb, a.b_bs, a.N, a.K, a.batch, bn);
+  p.M = a.M, p.N = a.N, p.num_kb = (a.K + bk - 1) / bk;
+  fill_epilogue(p, a);
+  dim3 grid((a.M + 127) / 128, (a.N + bn - 1) / bn, a.batch);
+
+#define CADRE_GEMM_CASE(KIND, AMN, BMN, BN, ST, EPI, OUT_F32, OutT)                                   \
+  if (a.kind == KIND && a.a_mn == AMN && a.b_mn == BMN && bn == BN && a.epi == EPI && a.out_f32 == OUT_F32) { \
+    launch_inst<KIND, AMN, BMN, BN, ST, MODE_GEMM, EPI, OutT>(p, grid, stream);                       \
+    return;                                                                                           \
+  }
+  // bf16 operands (encoder linears)
+  CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 0, __nv_bfloat16)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 0, __nv_bfloat16)
+  CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 0, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 1, 1, 128, 3, EPI_LINEAR, 1, float)
+  // fp32 operands as TF32 (PPO update: forward, dgrad, wgrad, LSTM cell)
+  CADRE_GEMM_CASE(1, 0, 0, 64, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 1, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LSTM, 1, float)
+#undef CADRE_GEMM_CASE
+  throw Error(1, "launch_gemm: unsupported (kind, majors, block_n, epilogue, out dtype) combination");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  CADRE_REQUIRE(a.Cin % 64 == 0, "conv Cin must be a multiple of 64");
+  CADRE_REQUIRE(a.stride == 1 || a.stride == 2, "conv stride must be 1 or 2");
+  CADRE_REQUIRE(a.KH * a.KW <= 12, "conv filter too large for the tap table");
+  const int Hout = (a.Hin + 2 * a.pad - a.KH) / a.stride + 1;
+  const int Wout = (a.Win + 2 * a.pad - a.KW) / a.stride + 1;
+  CADRE_REQUIRE(Wout <= 128 && 128 % Wout == 0, "conv output width must divide 128");
+  const int rows_per_tile = 128 / Wout;
+  int TH = 1;
+  while (TH * 2 <= rows_per_tile && Hout % (TH * 2) == 0) TH *= 2;
+  const int TN = rows_per_tile / TH;
+  const int bn = a.Cout <= 64 ? 64 : 128;
+
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t es = 2;
+  const uint32_t box[4] = {64u, static_cast<uint32_t>(Wout), static_cast<uint32_t>(TH),
+                           static_cast<uint32_t>(TN)};
+  if (a.stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)a.B};
+    const uint64_t str[3] = {a.Cin * es, (uint64_t)a.Win * a.Cin * es, (uint64_t)a.Hin * a.Win * a.Cin * es};
+    make_map(&p.tmA[0], 2, 4, a.in, dims, str, box);
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int Hs = (a.Hin - ph + 1) / 2, Ws = (a.Win - pw + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)a.B};
+        const uint64_t str[3] = {2 * a.Cin * es, 2 * (uint64_t)a.Win * a.Cin * es,
+                                 (uint64_t)a.Hin * a.Win * a.Cin * es};
+        if (Hs > 0 && Ws > 0)
+          make_map(&p.tmA[ph * 2 + pw], 2, 4, a.in + ((long long)ph * a.Win + pw) * a.Cin, dims, str, box);
+      }
+  }
+  int nt = 0;
+  for (int kh = 0; kh < a.KH; ++kh)
+    for (int kw = 0; kw < a.KW; ++kw) {
+      ConvTap t;
+      const int oh = kh - a.pad, ow = kw - a.pad;
+      if (a.stride == 1) {
+        t.map = 0, t.dh = (short)oh, t.dw = (short)ow;
+      } else {
+        const int ph = oh & 1, pw = ow & 1;
+        t.map = (short)(ph * 2 + pw), t.dh = (short)((oh - ph) / 2), t.dw = (short)((ow - pw) / 2);
+      }
+      t.pad_ = 0;
+      p.taps[nt++] = t;
+    }
+  p.ntaps = nt, p.cin_chunks = a.Cin / 64;
+  p.num_kb = nt * p.cin_chunks;
+  p.Hout = Hout, p.Wout = Wout, p.TH = TH, p.TN = TN, p.Bimg = a.B;
+  // weights: [Cout][K] K-major
+  {
+    const int K = nt * a.Cin;
+    make_operand_map(&p.tmB, 2, false, a.w, K, 0, a.Cout, K, 1, bn);
+  }
+  p.M = 0, p.N = a.Cout;
+  p.out = a.out, p.ldc = a.Cout;
+  p.bias = a.bias;
+  p.res = a.res, p.ldr = a.Cout, p.res_after_act = a.res_after_act;
+  p.act = a.act, p.alpha = 1.f;
+  dim3 grid((Hout / TH) * ((a.B + TN - 1) / TN), (a.Cout + bn - 1) / bn, 1);
+  if (bn == 64)
+    launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+  else
+    launch_inst<0, 0, 0, 128, 3, MODE_CONV, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void launch_stem(const StemArgs& a, cudaStream_t stream) {
+  // Input layout (written by the preprocess kernel): row-pair interleaved, padded by 3 pixels on every side:
+  //   P[n][y2 = 0..74][x = 0..261][r = 0..1][c = 0..3]  (padded row 2*y2 + r), 16 bytes per (y2, x).
+  // Output pixel (oh, ow), filter-row pair j (kh = 2j, 2j+1) reads P[n][oh + j][2ow .. 2ow+7] = 128 contiguous
+  // bytes, so k-block j of the implicit GEMM is one 4-D TMA box whose ow-stride (32 B) overlaps its rows.
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t pitch = 262 * 16;  // bytes per row pair
+  const uint64_t dims[4] = {64, 128, 75, (uint64_t)a.B};
+  const uint64_t str[3] = {32, pitch, 75 * pitch};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  make_map(&p.tmA[0], 2, 4, a.in, dims, str, box);
+  make_operand_map(&p.tmB, 2, false, a.w, 256, 0, 64, 256, 1, 64);
+  p.num_kb = 4;
+  p.Hout = 72, p.Wout = 128, p.TH = 1, p.TN = 1, p.Bimg = a.B;
+  p.N = 64;
+  p.out = a.out, p.ldc = 64;
+  p.bias = a.bias;
+  p.act = ACT_RELU, p.alpha = 1.f;
+  dim3 grid(72 * a.B, 1, 1);
+  launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+}
+
+}  // namespace cadre

@@ -52,6 +52,12 @@ def lib():
     return _lib
 
 
+def enc_dtype():
+    """torch dtype of the encoder's 16-bit operands / activations as compiled into the library."""
+    import torch
+    return torch.float16 if lib().cadre_enc_dtype() == 1 else torch.bfloat16
+
+
 def check(rc):
     if rc != 0:
         raise CadreError(f"libcadre_sm100 error {rc}: {lib().cadre_last_error().decode()}")

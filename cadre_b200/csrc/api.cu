@@ -25,6 +25,13 @@ extern "C" {
 
 const char* cadre_last_error(void) { return cadre::g_last_error.c_str(); }
 const char* cadre_version(void) { return "cadre_b200 sm_100a " __DATE__; }
+int cadre_enc_dtype(void) { return CADRE_ENC_FP16 ? 1 : 0; }
+
+int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  CADRE_API_END
+}
 
 int cadre_gemm(const cadre_gemm_args* s, void* stream) {
   CADRE_API_BEGIN
@@ -50,12 +57,12 @@ int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const vo
                       int act, void* out, void* stream) {
   CADRE_API_BEGIN
   cadre::ConvArgs a;
-  a.in = static_cast<const __nv_bfloat16*>(in);
+  a.in = static_cast<const cadre::enc_t*>(in);
   a.B = B, a.Hin = Hin, a.Win = Win, a.Cin = Cin;
-  a.w = static_cast<const __nv_bfloat16*>(w);
+  a.w = static_cast<const cadre::enc_t*>(w);
   a.Cout = Cout, a.KH = KH, a.KW = KW, a.stride = stride, a.pad = pad;
-  a.bias = bias, a.res = static_cast<const __nv_bfloat16*>(res), a.res_after_act = res_after_act;
-  a.act = act, a.out = static_cast<__nv_bfloat16*>(out);
+  a.bias = bias, a.res = static_cast<const cadre::enc_t*>(res), a.res_after_act = res_after_act;
+  a.act = act, a.out = static_cast<cadre::enc_t*>(out);
   cadre::launch_conv(a, static_cast<cudaStream_t>(stream));
   CADRE_API_END
 }
@@ -64,11 +71,11 @@ int cadre_stem_conv(const void* in_padded, int B, const void* w256, const float*
                     void* stream) {
   CADRE_API_BEGIN
   cadre::StemArgs a;
-  a.in = static_cast<const __nv_bfloat16*>(in_padded);
+  a.in = static_cast<const cadre::enc_t*>(in_padded);
   a.B = B;
-  a.w = static_cast<const __nv_bfloat16*>(w256);
+  a.w = static_cast<const cadre::enc_t*>(w256);
   a.bias = bias;
-  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out = static_cast<cadre::enc_t*>(out);
   cadre::launch_stem(a, static_cast<cudaStream_t>(stream));
   CADRE_API_END
 }

@@ -1,0 +1,256 @@
+// Perception encoder forward plan: DANet.get_latent_feature (carla_perception/Networks/danet.py:216-238) as a
+// fixed sequence of kernel launches over NHWC bf16 activations held in library-owned HBM workspaces.
+//   ingest -> stem (tcgen05) -> maxpool -> 8 BasicBlocks (tcgen05 implicit GEMM, BN folded, residual + ReLU in
+//   the epilogue) -> conv5a|conv5c as one N=256 conv -> fused PAM / fused CAM -> conv51, conv52 (+sum) ->
+//   [conv8 o visual/bc 1x1 o Linear(20480,512)] folded into one [B,5120]x[5120,3072] GEMM + LeakyReLU ->
+//   six Linear(512,256) as one batched GEMM -> inter-task attention (+ measurement concat).
+#include "../../include/cadre_b200.h"
+#include "internal.h"
+
+#include <vector>
+
+namespace cadre {
+
+void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
+                       int B, cudaStream_t stream);
+void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
+void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C,
+                    cudaStream_t stream);
+void launch_pam(const enc_t* x, enc_t* out, const float* wqk, const float* bqk,
+                const float* wv, const float* bv, float gamma, int B, int ldin, int num_sms,
+                cudaStream_t stream);
+void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
+                cudaStream_t stream);
+void launch_intertask(const float* qkv, float* out, const double* meas, int B, int ld_out,
+                      cudaStream_t stream);
+
+struct Encoder {
+  cadre_encoder_weights w;
+  int max_batch = 0;
+  int num_sms = 148;
+  // workspaces (device)
+  enc_t* padded = nullptr;   // [Bmax][75][262][8]
+  enc_t* stem = nullptr;     // [Bmax][72][128][64]
+  enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
+  enc_t* head5 = nullptr;    // [Bmax][40][256]
+  enc_t* sa = nullptr;       // [Bmax][40][128]
+  enc_t* sc = nullptr;
+  enc_t* sa_conv = nullptr;
+  enc_t* feat_sum = nullptr;
+  enc_t* fc1 = nullptr;      // [Bmax][3072]
+  float* qkv = nullptr;              // [6][Bmax][256]
+  uint8_t* route_max = nullptr;      // [Bmax]
+  enc_t* l4 = nullptr;       // alias of the act buffer holding layer4's output after a forward
+  int launches_per_forward = 0;
+};
+
+template <typename T>
+static T* dev_alloc(size_t n, bool zero) {
+  T* p = nullptr;
+  CADRE_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+  if (zero) CADRE_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+  return p;
+}
+
+static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
+  CADRE_REQUIRE(w != nullptr && max_batch > 0, "encoder_create arguments");
+  Encoder* e = new Encoder();
+  e->w = *w;
+  e->max_batch = max_batch;
+  int dev = 0;
+  CADRE_CUDA_CHECK(cudaGetDevice(&dev));
+  CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t B = max_batch;
+  e->padded = dev_alloc<enc_t>(B * 75 * 262 * 8, true);  // zero borders = conv padding
+  e->stem = dev_alloc<enc_t>(B * 72 * 128 * 64, false);
+  for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
+  e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
+  e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
+  e->sc = dev_alloc<enc_t>(B * 40 * 128, false);
+  e->sa_conv = dev_alloc<enc_t>(B * 40 * 128, false);
+  e->feat_sum = dev_alloc<enc_t>(B * 40 * 128, false);
+  e->fc1 = dev_alloc<enc_t>(B * 3072, false);
+  e->qkv = dev_alloc<float>(6 * B * 256, false);
+  e->route_max = dev_alloc<uint8_t>(B, true);
+  return e;
+}
+
+static void encoder_destroy(Encoder* e) {
+  if (!e) return;
+  cudaFree(e->padded), cudaFree(e->stem);
+  for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
+  cudaFree(e->head5), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
+  cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max);
+  delete e;
+}
+
+static void conv(Encoder* e, int idx, const enc_t* in, int B, int H, int W, int Cin, int Cout, int k,
+                 int stride, int pad, const enc_t* res, int act, enc_t* out,
+                 cudaStream_t s) {
+  ConvArgs a;
+  a.in = in, a.B = B, a.Hin = H, a.Win = W, a.Cin = Cin;
+  a.w = static_cast<const enc_t*>(e->w.conv_w[idx]);
+  a.bias = e->w.conv_b[idx];
+  a.Cout = Cout, a.KH = k, a.KW = k, a.stride = stride, a.pad = pad;
+  a.res = res, a.act = act, a.out = out;
+  launch_conv(a, s);
+}
+
+// everything after the ingest kernel; `B` frames already sit in e->padded
+static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int ld_out, cudaStream_t s) {
+  int n = 0;
+  StemArgs st;
+  st.in = e->padded, st.B = B, st.w = static_cast<const enc_t*>(e->w.stem_w), st.bias = e->w.stem_b;
+  st.out = e->stem;
+  launch_stem(st, s), ++n;
+  launch_maxpool(e->stem, e->act[0], B, 72, 128, 64, s), ++n;
+
+  // ResNet-18 BasicBlocks (resnet.py:39-55, 116-119); conv indices follow execution order
+  int cur = 0, ci = 0, H = 36, W = 64, C = 64;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    for (int bi = 0; bi < 2; ++bi) {
+      const int stride = (li > 0 && bi == 0) ? 2 : 1;
+      const int Cout = planes[li];
+      const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+      enc_t* x = e->act[cur];
+      enc_t* t = e->act[(cur + 1) & 3];
+      enc_t* ds = e->act[(cur + 2) & 3];
+      enc_t* o = e->act[(cur + 3) & 3];
+      conv(e, ci++, x, B, H, W, C, Cout, 3, stride, 1, nullptr, 1, t, s), ++n;
+      const enc_t* idn = x;
+      const int conv2_idx = ci++;
+      if (stride == 2) {
+        conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s), ++n;
+        idn = ds;
+      }
+      conv(e, conv2_idx, t, B, Ho, Wo, Cout, Cout, 3, 1, 1, idn, 1, o, s), ++n;
+      cur = (cur + 3) & 3;
+      H = Ho, W = Wo, C = Cout;
+    }
+  }
+  e->l4 = e->act[cur];
+
+  // DANetHead (danet.py:43-69)
+  {
+    ConvArgs a;
+    a.in = e->l4, a.B = B, a.Hin = 5, a.Win = 8, a.Cin = 512;
+    a.w = static_cast<const enc_t*>(e->w.head5_w), a.bias = e->w.head5_b;
+    a.Cout = 256, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->head5;
+    launch_conv(a, s), ++n;
+  }
+  launch_pam(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_wv, e->w.pam_bv, e->w.pam_gamma, B, 256,
+             e->num_sms, s), ++n;
+  launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), ++n;
+  {
+    ConvArgs a;
+    a.in = e->sa, a.B = B, a.Hin = 5, a.Win = 8, a.Cin = 128;
+    a.w = static_cast<const enc_t*>(e->w.conv51_w), a.bias = e->w.conv51_b;
+    a.Cout = 128, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->sa_conv;
+    launch_conv(a, s), ++n;
+    a.in = e->sc;
+    a.w = static_cast<const enc_t*>(e->w.conv52_w), a.bias = e->w.conv52_b;
+    a.res = e->sa_conv, a.res_after_act = 1, a.out = e->feat_sum;  // feat_sum = relu(conv52) + sa_conv
+    launch_conv(a, s), ++n;
+  }
+  // conv8 -> {visual_conv, bc_conv} -> six Linear(20480,512): all linear, folded offline into fc1 (K = 40*128)
+  {
+    GemmArgs g;
+    g.kind = 0, g.A = e->feat_sum, g.lda = 5120, g.B = e->w.fc1_w, g.ldb = 5120;
+    g.M = B, g.N = 3072, g.K = 5120;
+    g.out = e->fc1, g.ldc = 3072, g.out_f32 = 0, g.bias = e->w.fc1_b, g.act = 2;
+    launch_gemm(g, s), ++n;
+  }
+  {
+    GemmArgs g;
+    g.kind = 0, g.batch = 6;
+    g.A = e->fc1, g.lda = 3072, g.a_bs = 512;
+    g.B = e->w.fc2_w, g.ldb = 512, g.b_bs = 256 * 512;
+    g.M = B, g.N = 256, g.K = 512;
+    g.out = e->qkv, g.ldc = 256, g.out_bs = static_cast<long long>(B) * 256, g.out_f32 = 1;
+    g.bias = e->w.fc2_b, g.bias_bs = 256;
+    launch_gemm(g, s), ++n;
+  }
+  launch_intertask(e->qkv, out, meas, B, ld_out, s), ++n;
+  e->launches_per_forward = n + 2;
+}
+
+}  // namespace cadre
+
+using cadre::Encoder;
+
+#define CADRE_API_BEGIN try {
+#define CADRE_API_END                \
+  }                                  \
+  catch (const cadre::Error& e) {    \
+    cadre::set_last_error(e.what()); \
+    return e.code;                   \
+  }                                  \
+  catch (const std::exception& e) {  \
+    cadre::set_last_error(e.what()); \
+    return 99;                       \
+  }                                  \
+  return 0;
+
+extern "C" {
+
+int cadre_encoder_create(void** handle, const cadre_encoder_weights* w, int max_batch) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle != nullptr, "handle");
+  *handle = cadre::encoder_create(w, max_batch);
+  CADRE_API_END
+}
+
+int cadre_encoder_destroy(void* handle) {
+  CADRE_API_BEGIN
+  cadre::encoder_destroy(static_cast<Encoder*>(handle));
+  CADRE_API_END
+}
+
+int cadre_encoder_forward_u8(void* handle, const uint8_t* rgb, const uint8_t* route_fig,
+                             const double* measurements, int B, float* out, int ld_out, void* stream) {
+  CADRE_API_BEGIN
+  Encoder* e = static_cast<Encoder*>(handle);
+  CADRE_REQUIRE(e && rgb && route_fig && out, "encoder_forward_u8 pointers");
+  CADRE_REQUIRE(B > 0 && B <= e->max_batch, "batch exceeds the encoder's max_batch");
+  CADRE_REQUIRE(ld_out >= (measurements ? 530 : 512), "ld_out too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cadre::launch_preprocess(rgb, route_fig, e->route_max, e->padded, B, s);
+  cadre::encoder_trunk(e, B, measurements, out, ld_out, s);
+  CADRE_API_END
+}
+
+int cadre_encoder_forward_f32(void* handle, const float* x_nchw, int B, float* out, int ld_out, void* stream) {
+  CADRE_API_BEGIN
+  Encoder* e = static_cast<Encoder*>(handle);
+  CADRE_REQUIRE(e && x_nchw && out, "encoder_forward_f32 pointers");
+  CADRE_REQUIRE(B > 0 && B <= e->max_batch, "batch exceeds the encoder's max_batch");
+  CADRE_REQUIRE(ld_out >= 512, "ld_out too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cadre::launch_pack_f32(x_nchw, e->padded, B, s);
+  cadre::encoder_trunk(e, B, nullptr, out, ld_out, s);
+  CADRE_API_END
+}
+
+int cadre_encoder_buffer(void* handle, int which, void** ptr, int64_t* elems_per_frame) {
+  CADRE_API_BEGIN
+  Encoder* e = static_cast<Encoder*>(handle);
+  CADRE_REQUIRE(e && ptr && elems_per_frame, "encoder_buffer pointers");
+  switch (which) {
+    case 0: *ptr = e->l4, *elems_per_frame = 40 * 512; break;          // layer4 output, NHWC bf16
+    case 1: *ptr = e->feat_sum, *elems_per_frame = 40 * 128; break;    // sa_conv + sc_conv, NHWC bf16
+    case 2: *ptr = e->head5, *elems_per_frame = 40 * 256; break;       // conv5a|conv5c output
+    case 3: *ptr = e->sa, *elems_per_frame = 40 * 128; break;          // PAM output
+    case 4: *ptr = e->sc, *elems_per_frame = 40 * 128; break;          // CAM output
+    case 5: *ptr = e->stem, *elems_per_frame = 72 * 128 * 64; break;   // stem output
+    default: throw cadre::Error(1, "encoder_buffer: unknown buffer id");
+  }
+  CADRE_API_END
+}
+
+int cadre_encoder_launches(void* handle) {
+  Encoder* e = static_cast<Encoder*>(handle);
+  return e ? e->launches_per_forward : 0;
+}
+
+}  // extern "C"

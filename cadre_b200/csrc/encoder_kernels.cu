@@ -1,0 +1,375 @@
+// Non-GEMM kernels of the perception encoder forward pass (HBM / latency bound, fp32 math on CUDA cores):
+// uint8 ingest, max-pool, fused position attention (PAM), fused channel attention (CAM), inter-task attention.
+#include "internal.h"
+
+namespace cadre {
+
+// ---------------------------------------------------------------------------------------------------------
+// pre_process (ppo_agent/agent.py:43-75): rgb u8 [B,144,256,3] / 255 -> channels 0..2; route_fig u8
+// [B,256,144], max-normalised per frame and truncated back to uint8 (so 1 where route == max > 0, else 0),
+// transposed -> channel 3. Output: the stem's row-pair interleaved, 3-pixel padded bf16 image
+// P[B][75][262][2][4] (borders stay zero from allocation time).
+__global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __restrict__ mx) {
+  const uint8_t* r = route + static_cast<long long>(blockIdx.x) * 256 * 144;
+  unsigned m = 0;
+  const uint4* r4 = reinterpret_cast<const uint4*>(r);
+  for (int i = threadIdx.x; i < 256 * 144 / 16; i += blockDim.x) {
+    uint4 v = r4[i];
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m = max(m, w[k] & 0xff);
+      m = max(m, (w[k] >> 8) & 0xff);
+      m = max(m, (w[k] >> 16) & 0xff);
+      m = max(m, w[k] >> 24);
+    }
+  }
+  __shared__ unsigned sm[32];
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) mx[blockIdx.x] = static_cast<uint8_t>(m);
+  }
+}
+
+__global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ route,
+                                  const uint8_t* __restrict__ route_max, enc_t* __restrict__ out,
+                                  int B) {
+  // one thread per (image, row pair y2 in 1..73, pixel x in 0..255): writes 16 bytes
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 73 * 256;
+  if (gid >= total) return;
+  const int x = static_cast<int>(gid % 256);
+  const int y2 = static_cast<int>((gid / 256) % 73) + 1;
+  const int n = static_cast<int>(gid / (256 * 73));
+  const uint8_t mx = route_max[n];
+  enc_t v[8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = 2 * y2 + r - 3;  // unpadded row
+    if (y >= 0 && y < 144) {
+      const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + y) * 256 + x) * 3;
+      // np.array(rgb / 255., dtype=float32): float64 division rounded to fp32, then to bf16 here
+      v[4 * r + 0] = enc_from_float(static_cast<float>(px[0] / 255.0));
+      v[4 * r + 1] = enc_from_float(static_cast<float>(px[1] / 255.0));
+      v[4 * r + 2] = enc_from_float(static_cast<float>(px[2] / 255.0));
+      const uint8_t rv = route[(static_cast<long long>(n) * 256 + x) * 144 + y];
+      v[4 * r + 3] = enc_from_float((mx > 0) ? ((rv == mx) ? 1.f : 0.f) : static_cast<float>(rv));
+    } else {
+      v[4 * r + 0] = v[4 * r + 1] = v[4 * r + 2] = v[4 * r + 3] = enc_from_float(0.f);
+    }
+  }
+  enc_t* dst = out + ((static_cast<long long>(n) * 75 + y2) * 262 + (x + 3)) * 8;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+}
+
+void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
+                       int B, cudaStream_t stream) {
+  route_max_kernel<<<B, 256, 0, stream>>>(route, route_max_ws);
+  const long long total = static_cast<long long>(B) * 73 * 256;
+  preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(rgb, route, route_max_ws,
+                                                                                     out, B);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+// same layout from an already-normalised fp32 NCHW tensor [B,4,144,256] (parity tests / encoder sweep input)
+__global__ void pack_f32_kernel(const float* __restrict__ x, enc_t* __restrict__ out, int B) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 73 * 256;
+  if (gid >= total) return;
+  const int xx = static_cast<int>(gid % 256);
+  const int y2 = static_cast<int>((gid / 256) % 73) + 1;
+  const int n = static_cast<int>(gid / (256 * 73));
+  enc_t v[8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = 2 * y2 + r - 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float f = 0.f;
+      if (y >= 0 && y < 144) f = x[((static_cast<long long>(n) * 4 + c) * 144 + y) * 256 + xx];
+      v[4 * r + c] = enc_from_float(f);
+    }
+  }
+  enc_t* dst = out + ((static_cast<long long>(n) * 75 + y2) * 262 + (xx + 3)) * 8;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+}
+
+void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * 73 * 256;
+  pack_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, out, B);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MaxPool2d(3, stride 2, padding 1) on NHWC bf16 (resnet.py:172): [B,72,128,64] -> [B,36,64,64].
+// One thread = one output pixel x 8 channels (16 B); inputs are post-ReLU so padding never wins.
+__global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__ out, int B,
+                               int Hin, int Win, int C) {
+  const int Hout = Hin / 2, Wout = Win / 2, CV = C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Hout * Wout * CV;
+  if (gid >= total) return;
+  const int cv = static_cast<int>(gid % CV);
+  const int ow = static_cast<int>((gid / CV) % Wout);
+  const int oh = static_cast<int>((gid / (CV * Wout)) % Hout);
+  const int n = static_cast<int>(gid / (static_cast<long long>(CV) * Wout * Hout));
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * oh + dy;
+    if (y < 0 || y >= Hin) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * ow + dx;
+      if (x < 0 || x >= Win) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * Hin + y) * Win + x) * C +
+                                                      cv * 8);
+      const enc_t* h = reinterpret_cast<const enc_t*>(&v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], enc_to_float(h[i]));
+    }
+  }
+  enc_t o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = enc_from_float(m[i]);
+  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Hout + oh) * Wout + ow) * C + cv * 8) =
+      *reinterpret_cast<const uint4*>(o);
+}
+
+void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C,
+                    cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2) * (C / 8);
+  maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, B, Hin, Win, C);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PAM_Module.forward (danet_blocks/da_att.py:32-51) fused per frame: q,k = 1x1 conv 128->16, v = 1x1 conv
+// 128->128, energy = q^T k [40x40] (no scale), softmax over keys, out = v att^T, gamma*out + x.
+// One CTA (256 threads) walks frames; weights live in shared memory for the CTA's lifetime; the 40x40 map
+// never leaves the SM. x / out: NHWC bf16 [B][40][128]. Weights fp32: wqk [32][128] (q rows then k rows),
+// bqk [32], wv [128][128], bv [128].
+constexpr int PAM_P = 40, PAM_C = 128;
+struct PamSmem {
+  float wv[PAM_C][PAM_C + 1];
+  float wqk[32][PAM_C + 1];
+  float bv[PAM_C];
+  float bqk[32];
+  float x[PAM_P][PAM_C + 1];
+  float v[PAM_P][PAM_C + 1];
+  float qk[PAM_P][33];
+  float att[PAM_P][PAM_P + 1];
+};
+
+__global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin,
+                                                  enc_t* __restrict__ out, const float* __restrict__ wqk,
+                                                  const float* __restrict__ bqk, const float* __restrict__ wv,
+                                                  const float* __restrict__ bv, float gamma, int B,
+                                                  int ldin) {
+  extern __shared__ uint8_t pam_raw[];
+  PamSmem& s = *reinterpret_cast<PamSmem*>(pam_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < PAM_C * PAM_C; i += 256) s.wv[i / PAM_C][i % PAM_C] = wv[i];
+  for (int i = tid; i < 32 * PAM_C; i += 256) s.wqk[i / PAM_C][i % PAM_C] = wqk[i];
+  if (tid < PAM_C) s.bv[tid] = bv[tid];
+  if (tid < 32) s.bqk[tid] = bqk[tid];
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    __syncthreads();
+    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
+    for (int i = tid; i < PAM_P * PAM_C; i += 256)
+      s.x[i / PAM_C][i % PAM_C] = enc_to_float(xf[(i / PAM_C) * ldin + (i % PAM_C)]);
+    __syncthreads();
+    // projections: v[p][c] (40x128 outputs) and qk[p][j] (40x32 outputs)
+    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
+      const int p = o / PAM_C, c = o % PAM_C;
+      float acc = s.bv[c];
+#pragma unroll 8
+      for (int k = 0; k < PAM_C; ++k) acc = fmaf(s.x[p][k], s.wv[c][k], acc);
+      s.v[p][c] = acc;
+    }
+    for (int o = tid; o < PAM_P * 32; o += 256) {
+      const int p = o / 32, j = o % 32;
+      float acc = s.bqk[j];
+#pragma unroll 8
+      for (int k = 0; k < PAM_C; ++k) acc = fmaf(s.x[p][k], s.wqk[j][k], acc);
+      s.qk[p][j] = acc;
+    }
+    __syncthreads();
+    // energy[i][j] = sum_d q[i][d] k[j][d]
+    for (int o = tid; o < PAM_P * PAM_P; o += 256) {
+      const int i = o / PAM_P, j = o % PAM_P;
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) acc = fmaf(s.qk[i][d], s.qk[j][16 + d], acc);
+      s.att[i][j] = acc;
+    }
+    __syncthreads();
+    // row softmax: one warp per row
+    for (int i = tid >> 5; i < PAM_P; i += 8) {
+      const int l = tid & 31;
+      const float e0 = s.att[i][l], e1 = (l + 32 < PAM_P) ? s.att[i][l + 32] : -INFINITY;
+      float m = fmaxf(e0, e1);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float p0 = expf(e0 - m), p1 = (l + 32 < PAM_P) ? expf(e1 - m) : 0.f;
+      float sum = p0 + p1;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      s.att[i][l] = p0 / sum;
+      if (l + 32 < PAM_P) s.att[i][l + 32] = p1 / sum;
+    }
+    __syncthreads();
+    // out[i][c] = gamma * sum_j v[j][c] att[i][j] + x[i][c]
+    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
+      const int i = o / PAM_C, c = o % PAM_C;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < PAM_P; ++j) acc = fmaf(s.v[j][c], s.att[i][j], acc);
+      of[o] = enc_from_float(gamma * acc + s.x[i][c]);
+    }
+  }
+}
+
+// CAM_Module.forward (da_att.py:63-83) fused per frame: energy = X X^T [128x128] over the 40 positions,
+// softmax(rowmax - energy), out = att X, gamma*out + x.
+struct CamSmem {
+  float x[PAM_P][PAM_C + 1];          // x[p][c]
+  float att[PAM_C][PAM_C + 1];
+};
+
+__global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
+                                                  enc_t* __restrict__ out, float gamma, int B,
+                                                  int ldin) {
+  extern __shared__ uint8_t cam_raw[];
+  CamSmem& s = *reinterpret_cast<CamSmem*>(cam_raw);
+  const int tid = threadIdx.x;
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    __syncthreads();
+    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
+    for (int i = tid; i < PAM_P * PAM_C; i += 256)
+      s.x[i / PAM_C][i % PAM_C] = enc_to_float(xf[(i / PAM_C) * ldin + (i % PAM_C)]);
+    __syncthreads();
+    for (int o = tid; o < PAM_C * PAM_C; o += 256) {
+      const int a = o / PAM_C, b = o % PAM_C;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < PAM_P; ++p) acc = fmaf(s.x[p][a], s.x[p][b], acc);
+      s.att[a][b] = acc;
+    }
+    __syncthreads();
+    // softmax(rowmax - e) == exp(rowmin - e) / sum: one warp per channel row, 4 values per lane
+    for (int a = tid >> 5; a < PAM_C; a += 8) {
+      const int l = tid & 31;
+      float e[4], mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[k] = s.att[a][l + 32 * k];
+        mx = fmaxf(mx, e[k]);
+      }
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float en[4], m2 = -INFINITY;  // energy_new = mx - e, then a regular stable softmax over energy_new
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        en[k] = mx - e[k];
+        m2 = fmaxf(m2, en[k]);
+      }
+      for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        en[k] = expf(en[k] - m2);
+        sum += en[k];
+      }
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s.att[a][l + 32 * k] = en[k] / sum;
+    }
+    __syncthreads();
+    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
+      const int p = o / PAM_C, a = o % PAM_C;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int b = 0; b < PAM_C; ++b) acc = fmaf(s.att[a][b], s.x[p][b], acc);
+      of[o] = enc_from_float(gamma * acc + s.x[p][a]);
+    }
+  }
+}
+
+void launch_pam(const enc_t* x, enc_t* out, const float* wqk, const float* bqk,
+                const float* wv, const float* bv, float gamma, int B, int ldin, int num_sms,
+                cudaStream_t stream) {
+  static bool cfg = false;
+  if (!cfg) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(pam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(PamSmem))));
+    cfg = true;
+  }
+  const int grid = B < num_sms ? B : num_sms;
+  pam_kernel<<<grid, 256, sizeof(PamSmem), stream>>>(x, out, wqk, bqk, wv, bv, gamma, B, ldin);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
+                cudaStream_t stream) {
+  static bool cfg = false;
+  if (!cfg) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(cam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(CamSmem))));
+    cfg = true;
+  }
+  const int grid = B < 2 * num_sms ? B : 2 * num_sms;
+  cam_kernel<<<grid, 256, sizeof(CamSmem), stream>>>(x, out, gamma, B, ldin);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// InterTaskAtt.forward, transformer branch (intertask_att.py:137-176): rank-1 energies
+//   att_bc[i]  = sum_j v_bc[j]  softmax_j((q_vis[i]/16) k_bc[j])  + v_bc[i]
+//   att_vis[i] = sum_j v_vis[j] softmax_j((q_bc[i]/16)  k_vis[j]) + v_vis[i]
+// qkv: fp32 [6][B][256] in the order (vis q, vis k, vis v, bc q, bc k, bc v). Output row: [att_vis | att_bc |
+// optional 18 measurement floats] fp32 with row stride ld_out (danet.py:233 + agent.py:106-111).
+__global__ void __launch_bounds__(256) intertask_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                        const double* __restrict__ meas, int B, int ld_out) {
+  __shared__ float sk[2][256], sv[2][256];
+  const int f = blockIdx.x, i = threadIdx.x;
+  const long long BS = static_cast<long long>(B) * 256;
+  const float* base = qkv + static_cast<long long>(f) * 256;
+  const float vq = base[0 * BS + i], vk = base[1 * BS + i], vv = base[2 * BS + i];
+  const float bq = base[3 * BS + i], bk = base[4 * BS + i], bv = base[5 * BS + i];
+  sk[0][i] = bk, sv[0][i] = bv;  // direction 0: visual query -> bc keys/values  => att_bc
+  sk[1][i] = vk, sv[1][i] = vv;  // direction 1: bc query -> visual keys/values  => att_vis
+  __syncthreads();
+  const float qs[2] = {vq / 16.0f, bq / 16.0f};
+  float res[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const float q = qs[d];
+    float m = -INFINITY;
+    for (int j = 0; j < 256; ++j) m = fmaxf(m, q * sk[d][j]);
+    float sum = 0.f, acc = 0.f;
+    for (int j = 0; j < 256; ++j) {
+      const float p = expf(q * sk[d][j] - m);
+      sum += p;
+      acc = fmaf(p, sv[d][j], acc);
+    }
+    res[d] = acc / sum + sv[d][i];
+  }
+  float* o = out + static_cast<long long>(f) * ld_out;
+  o[i] = res[1];         // att_visual first (danet.py:233 cat((att_visual, att_bc)))
+  o[256 + i] = res[0];
+  if (meas != nullptr && i < 18) o[512 + i] = static_cast<float>(meas[static_cast<long long>(f) * 3 + (i % 3)]);
+}
+
+void launch_intertask(const float* qkv, float* out, const double* meas, int B, int ld_out,
+                      cudaStream_t stream) {
+  intertask_kernel<<<B, 256, 0, stream>>>(qkv, out, meas, B, ld_out);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace cadre

@@ -2,13 +2,38 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <stdexcept>
 #include <string>
 
+// 16-bit storage / tensor-core operand type of the encoder path. fp16 (default) keeps the 20-layer encoder at
+// ~1.3e-3 relative error against the fp32 reference; bf16 sits at ~9e-3, on the edge of the 1e-2 budget
+// (measured). Both run at the same tcgen05 kind::f16 rate; stores saturate instead of overflowing.
+#ifndef CADRE_ENC_FP16
+#define CADRE_ENC_FP16 1
+#endif
+
 namespace cadre {
+
+#if CADRE_ENC_FP16
+using enc_t = __half;
+__device__ __forceinline__ enc_t enc_from_float(float f) {
+  return __float2half_rn(fminf(fmaxf(f, -65504.f), 65504.f));
+}
+__device__ __forceinline__ float enc_to_float(enc_t h) { return __half2float(h); }
+#else
+using enc_t = __nv_bfloat16;
+__device__ __forceinline__ enc_t enc_from_float(float f) { return __float2bfloat16_rn(f); }
+__device__ __forceinline__ float enc_to_float(enc_t h) { return __bfloat162float(h); }
+#endif
+__device__ __forceinline__ uint32_t enc_pack2(float a, float b) {
+  enc_t lo = enc_from_float(a), hi = enc_from_float(b);
+  return static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&lo)) |
+         (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hi)) << 16);
+}
 
 struct Error : public std::runtime_error {
   int code;
@@ -69,27 +94,41 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
 // Implicit-GEMM convolution over NHWC bf16 activations; weights [Cout][KH][KW][Cin] bf16 (BN folded).
 struct ConvArgs {
-  const __nv_bfloat16* in = nullptr;  // [B][Hin][Win][Cin]
+  const enc_t* in = nullptr;  // [B][Hin][Win][Cin]
   int B = 0, Hin = 0, Win = 0, Cin = 0;
-  const __nv_bfloat16* w = nullptr;  // [Cout][KH*KW*Cin]
+  const enc_t* w = nullptr;  // [Cout][KH*KW*Cin]
   int Cout = 0, KH = 1, KW = 1, stride = 1, pad = 0;
   const float* bias = nullptr;        // [Cout]
-  const __nv_bfloat16* res = nullptr; // [B][Hout][Wout][Cout] or null
+  const enc_t* res = nullptr; // [B][Hout][Wout][Cout] or null
   int res_after_act = 0;
   int act = 0;
-  __nv_bfloat16* out = nullptr;  // [B][Hout][Wout][Cout]
+  enc_t* out = nullptr;  // [B][Hout][Wout][Cout]
 };
 void launch_conv(const ConvArgs& a, cudaStream_t stream);
 
 // 7x7/s2/p3 stem over the padded 4-channel bf16 image [B][150][262][4]; weights [64][256] (K = 4 row pairs x
 // 2 rows x 8 pixels x 4 ch, zero where kh==7 or kw==7); output [B][72][128][64].
 struct StemArgs {
-  const __nv_bfloat16* in = nullptr;
+  const enc_t* in = nullptr;
   int B = 0;
-  const __nv_bfloat16* w = nullptr;
+  const enc_t* w = nullptr;
   const float* bias = nullptr;
-  __nv_bfloat16* out = nullptr;
+  enc_t* out = nullptr;
 };
 void launch_stem(const StemArgs& a, cudaStream_t stream);
+
+// Segmented (per-module) gradient norm + clip + Adam over flat buffers cut into chunks (rollout_optim_kernels.cu)
+struct OptTables {
+  int num_chunks = 0;
+  long long* chunk_off = nullptr;  // [num_chunks] element offset
+  int* chunk_len = nullptr;        // [num_chunks] multiple of 4
+  int* chunk_mod = nullptr;        // [num_chunks] module id 0..15, non-decreasing
+  int* mod_first = nullptr;        // [17] first chunk of each module
+  float* partial = nullptr;        // [num_chunks]
+  float* clip_coef = nullptr;      // [16]
+  float* norms = nullptr;          // [16]
+};
+void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
+                      float lr, float beta1, float beta2, float eps, int step, cudaStream_t s);
 
 }  // namespace cadre

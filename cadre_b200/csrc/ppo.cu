@@ -1,0 +1,765 @@
+// PPO minibatch update on one GPU: CadreAgent.update_policy (ppo_agent/agent.py:166-237) for W logical workers
+// at once, forward and hand-written backward, plus the chief's clip + Adam (ppo_agent/chief.py:13-21).
+//
+// The reference runs every row through all four command experts and masks (agent.py:170-182); here rows are
+// ROUTED: each row goes only through the LSTM + actor-critic of its own command (exactly the same function and
+// gradient, 4x less work). Rows of a head are stably sorted by command into per-expert slots
+// (expert e = head*4 + command); all eight experts run as one grid.z-batched tcgen05 GEMM per layer / step.
+//
+// Time-expanded buffers use 9 time slots per row ("x9" layout [E][cap][9][ld]): slot j<8 of X9 holds x_j, slot j
+// of H9 / C9 holds h_{j-1} / c_{j-1} (j = 0 is the stored recurrent state hn/cn), slot j<8 of G9 / dG9 holds the
+// gate activations / pre-activation gradients of step j and slot 8 of dG9 stays zero. With that layout the
+// weight gradients of all eight steps are single GEMMs over K = 9*rows: dW_ih = dG9^T X9, dW_hh = dG9^T H9.
+#include "../../include/cadre_b200.h"
+#include "internal.h"
+#include "ppo_layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace cadre {
+
+using namespace ppo;
+
+struct StorageRef {  // == cadre_storage_ref
+  const float* obs;
+  const long long* action;
+  const float* value_preds;
+  const float* returns;
+  const float* action_log_probs;
+  const float* adv;
+  const float* hn;
+  const float* cn;
+  const int* command;
+};
+
+// ------------------------------------------------------------------------------------------ routing
+// Stable counting sort of the R = W*mb rows of one head by command (one CTA per head).
+__global__ void __launch_bounds__(1024) route_kernel(const StorageRef* __restrict__ refs,
+                                                     const int* __restrict__ idx, int W, int mb,
+                                                     int* __restrict__ row_slot, int* __restrict__ row_expert,
+                                                     int* __restrict__ counts, int* __restrict__ counts9) {
+  __shared__ int base[4];
+  __shared__ int wcnt[32][4];
+  const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = W * mb;
+  if (tid < 4) base[tid] = 0;
+  __syncthreads();
+  for (int tile0 = 0; tile0 < R; tile0 += 1024) {
+    const int r = tile0 + tid;
+    int c = -1;
+    if (r < R) {
+      const int w = r / mb, i = r - w * mb;
+      const int t = idx[(w * 2 + h) * mb + i];
+      c = refs[w * 2 + h].command[t] & 3;
+    }
+    int my = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned bal = __ballot_sync(0xffffffffu, c == k);
+      if (c == k) my = __popc(bal & ((1u << lane) - 1));
+      if (lane == 0) wcnt[warp][k] = __popc(bal);
+    }
+    __syncthreads();
+    if (r < R) {
+      int off = 0;
+      for (int w2 = 0; w2 < warp; ++w2) off += wcnt[w2][c];
+      row_slot[h * R + r] = base[c] + off + my;
+      row_expert[h * R + r] = h * 4 + c;
+    }
+    __syncthreads();
+    if (tid < 4) {
+      int tot = 0;
+      for (int w2 = 0; w2 < 32; ++w2) tot += wcnt[w2][tid];
+      base[tid] += tot;
+    }
+    __syncthreads();
+  }
+  if (tid < 4) {
+    counts[h * 4 + tid] = base[tid];
+    counts9[h * 4 + tid] = 9 * base[tid];
+  }
+}
+
+// gather of one row: RolloutStorage.feed_forward_generator (storage.py:98-120) fused with the routing
+struct RowScalars {
+  int* action;
+  int* worker;
+  float* old_v;
+  float* ret;
+  float* old_lp;
+  float* adv;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict__ refs,
+                                                   const int* __restrict__ idx, int W, int mb, int cap,
+                                                   const int* __restrict__ row_slot,
+                                                   const int* __restrict__ row_expert, float* __restrict__ X9,
+                                                   float* __restrict__ H9, float* __restrict__ C9,
+                                                   RowScalars sc) {
+  const int r = blockIdx.x, h = blockIdx.y, R = W * mb;
+  const int w = r / mb, i = r - w * mb;
+  const StorageRef ref = refs[w * 2 + h];
+  const int t = idx[(w * 2 + h) * mb + i];
+  const int e = row_expert[h * R + r], slot = row_slot[h * R + r];
+  const long long row = static_cast<long long>(e) * cap + slot;
+  const float* obs = ref.obs + static_cast<long long>(t) * 8 * F;
+  float* x = X9 + row * 9 * LDF;
+  for (int k = threadIdx.x; k < 8 * F; k += 256) {
+    const int j = k / F, f = k - j * F;
+    x[j * LDF + f] = obs[k];
+  }
+  float* h0 = H9 + row * 9 * LDF;
+  float* c0 = C9 + row * 9 * LDF;
+  for (int f = threadIdx.x; f < F; f += 256) {
+    h0[f] = ref.hn[static_cast<long long>(t) * F + f];
+    c0[f] = ref.cn[static_cast<long long>(t) * F + f];
+  }
+  if (threadIdx.x == 0) {
+    sc.action[row] = static_cast<int>(ref.action[t]);
+    sc.worker[row] = w;
+    sc.old_v[row] = ref.value_preds[t];
+    sc.ret[row] = ref.returns[t];
+    sc.old_lp[row] = ref.action_log_probs[t];
+    sc.adv[row] = ref.adv[t];
+  }
+}
+
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                            int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
+// ------------------------------------------------------------------------------------------ heads + loss
+// Last actor / critic layers, Categorical log-prob + entropy (models.py:203-212, distributions.py:66-105),
+// the PPO objective (agent.py:184-229) and their backward down to the ReLU of the second hidden layer.
+struct HeadParams {
+  const float* Y2;      // [E][cap][256] post-ReLU hidden (actor | critic)
+  float* dZ2;           // [E][cap][256]
+  const float* params;  // flat parameters
+  float* grads;         // flat gradients (W3A/B3A/W3C/B3C accumulated with atomics)
+  const int* counts;
+  RowScalars sc;
+  float* losses;        // [W][2][3] value, action, entropy (un-scaled means)
+  int cap;
+  float inv_mb, clip, value_coeff, clip_coeff, ent_coeff;
+};
+
+constexpr int HEAD_ROWS_PER_CTA = 64;
+
+__global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  const int e = blockIdx.y, head = e >> 2;
+  const int A = head == 0 ? 33 : 3;
+  const int count = p.counts[e];
+  const int rows_pad = (count + 31) & ~31;
+  const int row0 = blockIdx.x * HEAD_ROWS_PER_CTA;
+  if (row0 >= rows_pad) return;
+  __shared__ float w3aT[HID][AMAX];      // [k][j]
+  __shared__ float b3a[AMAX + 3];
+  __shared__ float w3c[HID];
+  __shared__ float acc_w3a[AMAX * HID];  // [j][k]
+  __shared__ float acc_b3a[AMAX + 3];
+  __shared__ float acc_w3c[HID];
+  __shared__ float acc_b3c;
+  __shared__ float s_y[8][2 * HID];
+  __shared__ float s_dl[8][AMAX + 3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* W3A = p.params + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
+  for (int i = tid; i < AMAX * HID; i += 256) {
+    const int j = i / HID, k = i - j * HID;
+    w3aT[k][j] = W3A[i];
+    acc_w3a[i] = 0.f;
+  }
+  if (tid < AMAX) {
+    b3a[tid] = p.params[OFF_B3A + e * B3A_LD + tid];
+    acc_b3a[tid] = 0.f;
+  }
+  if (tid < HID) {
+    w3c[tid] = p.params[OFF_W3C + e * HID + tid];
+    acc_w3c[tid] = 0.f;
+  }
+  if (tid == 0) acc_b3c = 0.f;
+  const float b3c = p.params[OFF_B3C + e * 4];
+  __syncthreads();
+
+  const int row_end = min(row0 + HEAD_ROWS_PER_CTA, rows_pad);
+  for (int slot = row0 + warp; slot < row_end; slot += 8) {
+    const long long row = static_cast<long long>(e) * p.cap + slot;
+    float* dz = p.dZ2 + row * 2 * HID;
+    if (slot >= count) {  // K-padding rows of the weight-gradient GEMMs must be exact zeros
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dz[lane + 32 * q] = 0.f;
+      continue;
+    }
+    const float* y = p.Y2 + row * 2 * HID;
+    float ya[4], yc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ya[q] = y[lane + 32 * q];
+      yc[q] = y[HID + lane + 32 * q];
+      s_y[warp][lane + 32 * q] = ya[q];
+    }
+    __syncwarp();
+    // logits (lane j and, for A = 33, j = 32 on lane 0) and value
+    float l0 = -INFINITY, l1 = -INFINITY;
+    if (lane < A) {
+      float acc = b3a[lane];
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc = fmaf(s_y[warp][k], w3aT[k][lane], acc);
+      l0 = acc;
+    }
+    if (lane + 32 < A) {
+      float acc = b3a[lane + 32];
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc = fmaf(s_y[warp][k], w3aT[k][lane + 32], acc);
+      l1 = acc;
+    }
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v = fmaf(yc[q], w3c[lane + 32 * q], v);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    v += b3c;
+    // Categorical(logits): logits - logsumexp
+    float mx = fmaxf(l0, l1);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = (lane < A ? expf(l0 - mx) : 0.f) + (lane + 32 < A ? expf(l1 - mx) : 0.f);
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = mx + logf(se);
+    const float lp0 = l0 - lse, lp1 = l1 - lse;
+    const float p0 = lane < A ? expf(lp0) : 0.f, p1 = lane + 32 < A ? expf(lp1) : 0.f;
+    float ent = -((lane < A ? p0 * lp0 : 0.f) + (lane + 32 < A ? p1 * lp1 : 0.f));
+    for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    const int a = p.sc.action[row];
+    const float lpa_src = (a < 32) ? lp0 : lp1;
+    const float lp = __shfl_sync(0xffffffffu, lpa_src, a & 31);
+
+    const float old_lp = p.sc.old_lp[row], adv = p.sc.adv[row], old_v = p.sc.old_v[row], ret = p.sc.ret[row];
+    const float wgt = p.inv_mb;
+    // agent.py:184-193
+    const float ratio = expf(lp - old_lp);
+    const float lo = 1.f - p.clip, hi = 1.f + p.clip;
+    const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+    const float action_term = -fminf(s1, s2);
+    const float dvv = v - old_v;
+    const float v_clip = old_v + fminf(fmaxf(dvv, -p.clip), p.clip);
+    const float vl = (v - ret) * (v - ret), vlc = (v_clip - ret) * (v_clip - ret);
+    const float value_term = 0.5f * fmaxf(vl, vlc);
+    if (lane == 0) {
+      float* L = p.losses + (p.sc.worker[row] * 2 + head) * 3;
+      atomicAdd(L + 0, wgt * value_term);
+      atomicAdd(L + 1, wgt * action_term);
+      atomicAdd(L + 2, wgt * ent);
+    }
+    // backward seeds (autograd conventions of torch.min / torch.max / clamp: ties split evenly, clamp passes
+    // the gradient on the closed interval)
+    const float inside_r = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // weight of surr1 in min()
+    const float dmin_dlp = g1 * adv * ratio + (1.f - g1) * adv * ratio * inside_r;
+    const float dlp = -p.clip_coeff * wgt * dmin_dlp;
+    const float inside_v = (dvv >= -p.clip && dvv <= p.clip) ? 1.f : 0.f;
+    const float gv = vl > vlc ? 1.f : (vl < vlc ? 0.f : 0.5f);
+    const float dv = p.value_coeff * wgt * (gv * (v - ret) + (1.f - gv) * (v_clip - ret) * inside_v);
+    const float ew = p.ent_coeff * wgt;  // total = ... - ent_coeff * mean(entropy)
+    float dl0 = 0.f, dl1 = 0.f;
+    if (lane < A) dl0 = dlp * ((a == lane ? 1.f : 0.f) - p0) + ew * p0 * (lp0 + ent);
+    if (lane + 32 < A) dl1 = dlp * ((a == lane + 32 ? 1.f : 0.f) - p1) + ew * p1 * (lp1 + ent);
+    if (lane < A) s_dl[warp][lane] = dl0;
+    if (lane + 32 < A) s_dl[warp][lane + 32] = dl1;
+    __syncwarp();
+    // d hidden2 = dlogits W3a (actor), dv * w3c (critic), through the ReLU
+    float da[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < A; ++j) {
+      const float d = s_dl[warp][j];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        da[q] = fmaf(d, w3aT[lane + 32 * q][j], da[q]);
+        atomicAdd(&acc_w3a[j * HID + lane + 32 * q], d * ya[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dz[lane + 32 * q] = ya[q] > 0.f ? da[q] : 0.f;
+      dz[HID + lane + 32 * q] = yc[q] > 0.f ? dv * w3c[lane + 32 * q] : 0.f;
+      atomicAdd(&acc_w3c[lane + 32 * q], dv * yc[q]);
+    }
+    if (lane < A) atomicAdd(&acc_b3a[lane], dl0);
+    if (lane + 32 < A) atomicAdd(&acc_b3a[lane + 32], dl1);
+    if (lane == 0) atomicAdd(&acc_b3c, dv);
+    __syncwarp();
+  }
+  __syncthreads();
+  float* gW3A = p.grads + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
+  for (int i = tid; i < A * HID; i += 256) atomicAdd(gW3A + i, acc_w3a[i]);
+  if (tid < A) atomicAdd(p.grads + OFF_B3A + e * B3A_LD + tid, acc_b3a[tid]);
+  if (tid < HID) atomicAdd(p.grads + OFF_W3C + e * HID + tid, acc_w3c[tid]);
+  if (tid == 0) atomicAdd(p.grads + OFF_B3C + e * 4, acc_b3c);
+}
+
+// Forward-only variant for act() / get_value() / evaluate_actions (agent.py:114-164, models.py:184-212): writes,
+// per routed row, [value, log-prob(action), entropy, logits[0..32]] to row_out[((worker*2+head)*mb + i)*ROW_OUT].
+constexpr int ROW_OUT = 36;
+__global__ void __launch_bounds__(256) head_eval_kernel(const float* __restrict__ Y2,
+                                                        const float* __restrict__ params,
+                                                        const int* __restrict__ row_slot,
+                                                        const int* __restrict__ row_expert,
+                                                        const int* __restrict__ actions_by_row, int R, int cap,
+                                                        float* __restrict__ row_out) {
+  // one warp per (head, row r); r enumerates (worker, i) like the gather
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + warp;
+  if (g >= 2 * R) return;
+  const int head = g / R, r = g - head * R;
+  const int e = row_expert[head * R + r], slot = row_slot[head * R + r];
+  const int A = head == 0 ? 33 : 3;
+  const long long row = static_cast<long long>(e) * cap + slot;
+  const float* y = Y2 + row * 2 * HID;
+  const float* W3A = params + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
+  float l0 = -INFINITY, l1 = -INFINITY;
+  if (lane < A) {
+    float acc = params[OFF_B3A + e * B3A_LD + lane];
+    for (int k = 0; k < HID; ++k) acc = fmaf(y[k], W3A[lane * HID + k], acc);
+    l0 = acc;
+  }
+  if (lane + 32 < A) {
+    float acc = params[OFF_B3A + e * B3A_LD + lane + 32];
+    for (int k = 0; k < HID; ++k) acc = fmaf(y[k], W3A[(lane + 32) * HID + k], acc);
+    l1 = acc;
+  }
+  float v = 0.f;
+  for (int q = 0; q < 4; ++q) v = fmaf(y[HID + lane + 32 * q], params[OFF_W3C + e * HID + lane + 32 * q], v);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  v += params[OFF_B3C + e * 4];
+  float mx = fmaxf(l0, l1);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = (lane < A ? expf(l0 - mx) : 0.f) + (lane + 32 < A ? expf(l1 - mx) : 0.f);
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  const float lse = mx + logf(se);
+  const float lp0 = l0 - lse, lp1 = l1 - lse;
+  float ent = -((lane < A ? expf(lp0) * lp0 : 0.f) + (lane + 32 < A ? expf(lp1) * lp1 : 0.f));
+  for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+  const int a = actions_by_row[row];
+  const float lp = __shfl_sync(0xffffffffu, (a < 32) ? lp0 : lp1, a & 31);
+  float* o = row_out + static_cast<long long>(g) * ROW_OUT;
+  if (lane == 0) o[0] = v, o[1] = lp, o[2] = ent;
+  if (lane < A) o[3 + lane] = lp0;            // normalised logits (Categorical.logits)
+  if (lane + 32 < A) o[3 + lane + 32] = lp1;
+}
+
+// ------------------------------------------------------------------------------------------ LSTM backward
+// Pointwise part of BPTT for step t (inverse of the LSTM-cell epilogue in tc_gemm.cuh):
+//   dc  = dc_next + dh * o * (1 - tanh(c_t)^2)
+//   di = dc*g*i(1-i)   df = dc*c_{t-1}*f(1-f)   dg = dc*i*(1-g^2)   do = dh*tanh(c_t)*o(1-o)   dc_prev = dc*f
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__ dH, float* __restrict__ dC,
+                                                       const float* __restrict__ G9,
+                                                       const float* __restrict__ C9, float* __restrict__ dG9,
+                                                       const int* __restrict__ counts, int cap, int t,
+                                                       int first) {
+  const int e = blockIdx.y;
+  const int count = counts[e];
+  const int rows_pad = min(cap, (count + 31) & ~31);
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int slot = static_cast<int>(gid / F), u = static_cast<int>(gid - static_cast<long long>(slot) * F);
+  if (slot >= rows_pad) return;
+  const long long row = static_cast<long long>(e) * cap + slot;
+  float4* dg = reinterpret_cast<float4*>(dG9 + (row * 9 + t) * G) + u;
+  if (slot >= count) {
+    *dg = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4 g = *(reinterpret_cast<const float4*>(G9 + (row * 9 + t) * G) + u);  // i, f, g, o
+  const float c_prev = C9[(row * 9 + t) * LDF + u], c_t = C9[(row * 9 + t + 1) * LDF + u];
+  const float dh = dH[row * LDF + u];
+  const float tc = tanhf(c_t);
+  float dc = dh * g.w * (1.f - tc * tc);
+  if (!first) dc += dC[row * LDF + u];
+  *dg = make_float4(dc * g.z * g.x * (1.f - g.x), dc * c_prev * g.y * (1.f - g.y), dc * g.x * (1.f - g.z * g.z),
+                    dh * tc * g.w * (1.f - g.w));
+  dC[row * LDF + u] = dc * g.y;
+}
+
+// column sums over the valid rows of each expert (bias gradients); deterministic
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, long long ld,
+                                                     long long src_bs, const int* __restrict__ rows, int N,
+                                                     float* __restrict__ dst, long long dst_bs,
+                                                     float* __restrict__ dst2) {
+  __shared__ float sm[8][33];
+  const int e = blockIdx.y;
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int R = rows[e];
+  const float* s = src + e * src_bs;
+  float acc = 0.f;
+  if (n < N)
+    for (int r = ry; r < R; r += 8) acc += s[r * ld + n];
+  sm[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x & 31];
+    dst[e * dst_bs + n] = t;
+    if (dst2) dst2[e * dst_bs + n] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ plan
+struct PpoPlan {
+  cadre_ppo_config cfg;
+  int cap = 0, R = 0;
+  // device buffers
+  float *X9 = nullptr, *XP9 = nullptr, *G9 = nullptr, *dG9 = nullptr, *H9 = nullptr, *C9 = nullptr;
+  float *Y1 = nullptr, *Y2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dH = nullptr, *dC = nullptr;
+  float* bsum = nullptr;
+  RowScalars sc{};
+  int *row_slot = nullptr, *row_expert = nullptr, *counts = nullptr, *counts9 = nullptr;
+  int* idx_dev = nullptr;
+  StorageRef* refs_dev = nullptr;
+  OptTables opt;
+  int launches = 0;
+};
+
+template <typename T>
+static T* dalloc(size_t n) {
+  T* p = nullptr;
+  CADRE_CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+  CADRE_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+  return p;
+}
+
+static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
+  CADRE_REQUIRE(cfg && cfg->workers > 0 && cfg->mini_batch > 0, "ppo config");
+  PpoPlan* P = new PpoPlan();
+  P->cfg = *cfg;
+  P->R = cfg->workers * cfg->mini_batch;
+  P->cap = (P->R + 127) / 128 * 128;  // worst case: every row of a head carries the same command
+  const size_t rows = static_cast<size_t>(E) * P->cap;
+  P->X9 = dalloc<float>(rows * 9 * LDF);
+  P->XP9 = dalloc<float>(rows * 9 * G);
+  P->G9 = dalloc<float>(rows * 9 * G);
+  P->dG9 = dalloc<float>(rows * 9 * G);
+  P->H9 = dalloc<float>(rows * 9 * LDF);
+  P->C9 = dalloc<float>(rows * 9 * LDF);
+  P->Y1 = dalloc<float>(rows * 2 * HID);
+  P->Y2 = dalloc<float>(rows * 2 * HID);
+  P->dZ1 = dalloc<float>(rows * 2 * HID);
+  P->dZ2 = dalloc<float>(rows * 2 * HID);
+  P->dH = dalloc<float>(rows * LDF);
+  P->dC = dalloc<float>(rows * LDF);
+  P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
+  P->sc.action = dalloc<int>(rows);
+  P->sc.worker = dalloc<int>(rows);
+  P->sc.old_v = dalloc<float>(rows);
+  P->sc.ret = dalloc<float>(rows);
+  P->sc.old_lp = dalloc<float>(rows);
+  P->sc.adv = dalloc<float>(rows);
+  P->row_slot = dalloc<int>(2 * static_cast<size_t>(P->R));
+  P->row_expert = dalloc<int>(2 * static_cast<size_t>(P->R));
+  P->counts = dalloc<int>(E);
+  P->counts9 = dalloc<int>(E);
+  P->idx_dev = dalloc<int>(2 * static_cast<size_t>(P->R));
+  P->refs_dev = dalloc<StorageRef>(2 * static_cast<size_t>(cfg->workers));
+
+  // optimizer chunk table, grouped by module: module e = LSTM of expert e, module 8+e = actor-critic of expert e
+  struct Piece {
+    long long off, len;
+    int mod;
+  };
+  std::vector<Piece> pieces;
+  for (int e = 0; e < E; ++e) {
+    pieces.push_back({OFF_WIH + (long long)e * G * LDF, (long long)G * LDF, e});
+    pieces.push_back({OFF_WHH + (long long)e * G * LDF, (long long)G * LDF, e});
+    pieces.push_back({OFF_BIH + (long long)e * G, G, e});
+    pieces.push_back({OFF_BHH + (long long)e * G, G, e});
+  }
+  for (int e = 0; e < E; ++e) {
+    pieces.push_back({OFF_W1 + (long long)e * 2 * HID * LDF, 2LL * HID * LDF, 8 + e});
+    pieces.push_back({OFF_B1 + (long long)e * 2 * HID, 2 * HID, 8 + e});
+    pieces.push_back({OFF_W2 + (long long)e * 2 * HID * HID, 2LL * HID * HID, 8 + e});
+    pieces.push_back({OFF_B2 + (long long)e * 2 * HID, 2 * HID, 8 + e});
+    pieces.push_back({OFF_W3A + (long long)e * AMAX * HID, (long long)AMAX * HID, 8 + e});
+    pieces.push_back({OFF_B3A + (long long)e * B3A_LD, B3A_LD, 8 + e});
+    pieces.push_back({OFF_W3C + (long long)e * HID, HID, 8 + e});
+    pieces.push_back({OFF_B3C + (long long)e * 4, 4, 8 + e});
+  }
+  std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.mod < b.mod; });
+  std::vector<long long> coff;
+  std::vector<int> clen, cmod, mfirst(17, 0);
+  const int CH = 8192;
+  for (const Piece& pc : pieces)
+    for (long long o = 0; o < pc.len; o += CH) {
+      coff.push_back(pc.off + o);
+      clen.push_back(static_cast<int>(std::min<long long>(CH, pc.len - o)));
+      cmod.push_back(pc.mod);
+    }
+  for (size_t i = 0; i < cmod.size(); ++i) mfirst[cmod[i] + 1] = static_cast<int>(i) + 1;
+  for (int m = 1; m <= 16; ++m) mfirst[m] = std::max(mfirst[m], mfirst[m - 1]);
+  OptTables& T = P->opt;
+  T.num_chunks = static_cast<int>(coff.size());
+  T.chunk_off = dalloc<long long>(coff.size());
+  T.chunk_len = dalloc<int>(coff.size());
+  T.chunk_mod = dalloc<int>(coff.size());
+  T.mod_first = dalloc<int>(17);
+  T.partial = dalloc<float>(coff.size());
+  T.clip_coef = dalloc<float>(16);
+  T.norms = dalloc<float>(16);
+  CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_off, coff.data(), coff.size() * 8, cudaMemcpyHostToDevice));
+  CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_len, clen.data(), clen.size() * 4, cudaMemcpyHostToDevice));
+  CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_mod, cmod.data(), cmod.size() * 4, cudaMemcpyHostToDevice));
+  CADRE_CUDA_CHECK(cudaMemcpy(T.mod_first, mfirst.data(), 17 * 4, cudaMemcpyHostToDevice));
+  return P;
+}
+
+static void ppo_destroy(PpoPlan* P) {
+  if (!P) return;
+  void* ptrs[] = {P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
+                  P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
+                  P->row_expert, P->counts, P->counts9, P->idx_dev, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
+                  P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
+  for (void* p : ptrs) cudaFree(p);
+  delete P;
+}
+
+static GemmArgs tf32_gemm(int a_mn, int b_mn) {
+  GemmArgs g;
+  g.kind = 1, g.a_mn = a_mn, g.b_mn = b_mn, g.batch = E, g.out_f32 = 1, g.block_n = 128;
+  return g;
+}
+
+// routing + gather + forward through the second hidden layer (Y2); returns the number of kernels launched
+static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host,
+                       const float* params, cudaStream_t s) {
+  const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap, R = P->R;
+  const long long rs9F = static_cast<long long>(cap) * 9 * LDF, rs9G = static_cast<long long>(cap) * 9 * G;
+  int n = 0;
+  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, idx_host, sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s));
+  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, refs_host, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
+  route_kernel<<<2, 1024, 0, s>>>(P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
+                                  P->counts9), ++n;
+  pack_kernel<<<dim3(R, 2), 256, 0, s>>>(P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
+                                         P->X9, P->H9, P->C9, P->sc), ++n;
+  add2_kernel<<<(E * G + 255) / 256, 256, 0, s>>>(params + OFF_BIH, params + OFF_BHH, P->bsum, E * G), ++n;
+  CADRE_CUDA_CHECK(cudaGetLastError());
+
+  // ---- forward
+  {  // x-part of all 8 (+1 dummy) time slots: XP9 = X9 W_ih^T + (b_ih + b_hh)
+    GemmArgs g = tf32_gemm(0, 0);
+    g.A = P->X9, g.lda = LDF, g.a_bs = rs9F;
+    g.B = params + OFF_WIH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
+    g.M = 9 * cap, g.N = G, g.K = F;
+    g.out = P->XP9, g.ldc = G, g.out_bs = rs9G;
+    g.bias = P->bsum, g.bias_bs = G;
+    g.batch_rows = P->counts9;
+    launch_gemm(g, s), ++n;
+  }
+  for (int t = 0; t < 8; ++t) {  // models.py:146-151: 8 sequential LSTMCell steps
+    GemmArgs g = tf32_gemm(0, 0);
+    g.epi = 1;
+    g.A = P->H9 + t * LDF, g.lda = 9 * LDF, g.a_bs = rs9F;
+    g.B = params + OFF_WHH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
+    g.M = cap, g.N = G, g.K = F;
+    g.xpart = P->XP9 + t * G, g.gates_out = P->G9 + t * G, g.ldx = 9 * G, g.x_bs = rs9G;
+    g.c_prev = P->C9 + t * LDF, g.c_out = P->C9 + (t + 1) * LDF, g.h_out = P->H9 + (t + 1) * LDF;
+    g.ldh = 9 * LDF, g.h_bs = rs9F;
+    g.batch_rows = P->counts;
+    launch_gemm(g, s), ++n;
+  }
+  {  // first actor + critic layers share the input h_8: one N = 256 GEMM
+    GemmArgs g = tf32_gemm(0, 0);
+    g.A = P->H9 + 8 * LDF, g.lda = 9 * LDF, g.a_bs = rs9F;
+    g.B = params + OFF_W1, g.ldb = LDF, g.b_bs = 2LL * HID * LDF;
+    g.M = cap, g.N = 2 * HID, g.K = F;
+    g.out = P->Y1, g.ldc = 2 * HID, g.out_bs = static_cast<long long>(cap) * 2 * HID;
+    g.bias = params + OFF_B1, g.bias_bs = 2 * HID, g.act = 1;
+    g.batch_rows = P->counts;
+    launch_gemm(g, s), ++n;
+  }
+  for (int br = 0; br < 2; ++br) {
+    GemmArgs g = tf32_gemm(0, 0);
+    g.A = P->Y1 + br * HID, g.lda = 2 * HID, g.a_bs = static_cast<long long>(cap) * 2 * HID;
+    g.B = params + OFF_W2 + br * HID * HID, g.ldb = HID, g.b_bs = 2LL * HID * HID;
+    g.M = cap, g.N = HID, g.K = HID;
+    g.out = P->Y2 + br * HID, g.ldc = 2 * HID, g.out_bs = static_cast<long long>(cap) * 2 * HID;
+    g.bias = params + OFF_B2 + br * HID, g.bias_bs = 2 * HID, g.act = 1;
+    g.batch_rows = P->counts;
+    launch_gemm(g, s), ++n;
+  }
+  return n;
+}
+
+static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host, float* params,
+                       float* grads, float* losses, cudaStream_t s) {
+  const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap;
+  const long long rs9F = static_cast<long long>(cap) * 9 * LDF, rs9G = static_cast<long long>(cap) * 9 * G;
+  CADRE_CUDA_CHECK(cudaMemsetAsync(losses, 0, sizeof(float) * W * 2 * 3, s));
+  CADRE_CUDA_CHECK(cudaMemsetAsync(grads + OFF_W3A, 0, sizeof(float) * (TOTAL - OFF_W3A), s));
+  int n = ppo_forward(P, refs_host, idx_host, params, s);
+  {
+    HeadParams hp;
+    hp.Y2 = P->Y2, hp.dZ2 = P->dZ2, hp.params = params, hp.grads = grads, hp.counts = P->counts, hp.sc = P->sc;
+    hp.losses = losses, hp.cap = cap, hp.inv_mb = 1.f / static_cast<float>(mb);
+    hp.clip = P->cfg.clip, hp.value_coeff = P->cfg.value_coeff, hp.clip_coeff = P->cfg.clip_coeff;
+    hp.ent_coeff = P->cfg.ent_coeff;
+    head_kernel<<<dim3(cap / HEAD_ROWS_PER_CTA, E), 256, 0, s>>>(hp), ++n;
+    CADRE_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // ---- backward
+  const long long bs256 = static_cast<long long>(cap) * 2 * HID;
+  for (int br = 0; br < 2; ++br) {
+    {  // dW2 = dZ2^T Y1
+      GemmArgs g = tf32_gemm(1, 1);
+      g.A = P->dZ2 + br * HID, g.lda = 2 * HID, g.a_bs = bs256;
+      g.B = P->Y1 + br * HID, g.ldb = 2 * HID, g.b_bs = bs256;
+      g.M = HID, g.N = HID, g.K = cap;
+      g.out = grads + OFF_W2 + br * HID * HID, g.ldc = HID, g.out_bs = 2LL * HID * HID;
+      g.batch_rows = P->counts, g.rows_is_k = 1;
+      launch_gemm(g, s), ++n;
+    }
+    {  // dZ1 = (dZ2 W2) * relu'(Y1)
+      GemmArgs g = tf32_gemm(0, 1);
+      g.A = P->dZ2 + br * HID, g.lda = 2 * HID, g.a_bs = bs256;
+      g.B = params + OFF_W2 + br * HID * HID, g.ldb = HID, g.b_bs = 2LL * HID * HID;
+      g.M = cap, g.N = HID, g.K = HID;
+      g.out = P->dZ1 + br * HID, g.ldc = 2 * HID, g.out_bs = bs256;
+      g.mask = P->Y1 + br * HID, g.ldm = 2 * HID, g.mask_bs = bs256;
+      g.batch_rows = P->counts;
+      launch_gemm(g, s), ++n;
+    }
+  }
+  colsum_kernel<<<dim3(8, E), 256, 0, s>>>(P->dZ2, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B2, 2 * HID,
+                                           nullptr), ++n;
+  colsum_kernel<<<dim3(8, E), 256, 0, s>>>(P->dZ1, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B1, 2 * HID,
+                                           nullptr), ++n;
+  {  // dW1 = dZ1^T h_8
+    GemmArgs g = tf32_gemm(1, 1);
+    g.A = P->dZ1, g.lda = 2 * HID, g.a_bs = bs256;
+    g.B = P->H9 + 8 * LDF, g.ldb = 9 * LDF, g.b_bs = rs9F;
+    g.M = 2 * HID, g.N = F, g.K = cap;
+    g.out = grads + OFF_W1, g.ldc = LDF, g.out_bs = 2LL * HID * LDF;
+    g.batch_rows = P->counts, g.rows_is_k = 1;
+    launch_gemm(g, s), ++n;
+  }
+  {  // dh_8 = dZ1 W1
+    GemmArgs g = tf32_gemm(0, 1);
+    g.A = P->dZ1, g.lda = 2 * HID, g.a_bs = bs256;
+    g.B = params + OFF_W1, g.ldb = LDF, g.b_bs = 2LL * HID * LDF;
+    g.M = cap, g.N = F, g.K = 2 * HID;
+    g.out = P->dH, g.ldc = LDF, g.out_bs = static_cast<long long>(cap) * LDF;
+    g.batch_rows = P->counts;
+    launch_gemm(g, s), ++n;
+  }
+  const unsigned bwd_blocks = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
+  for (int t = 7; t >= 0; --t) {
+    lstm_bwd_kernel<<<dim3(bwd_blocks, E), 256, 0, s>>>(P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
+                                                        t == 7),
+        ++n;
+    if (t > 0) {  // dh_{t-1} = dG_t W_hh
+      GemmArgs g = tf32_gemm(0, 1);
+      g.A = P->dG9 + t * G, g.lda = 9 * G, g.a_bs = rs9G;
+      g.B = params + OFF_WHH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
+      g.M = cap, g.N = F, g.K = G;
+      g.out = P->dH, g.ldc = LDF, g.out_bs = static_cast<long long>(cap) * LDF;
+      g.batch_rows = P->counts;
+      launch_gemm(g, s), ++n;
+    }
+  }
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  for (int which = 0; which < 2; ++which) {  // dW_ih = dG9^T X9, dW_hh = dG9^T H9 (K = 9 * rows)
+    GemmArgs g = tf32_gemm(1, 1);
+    g.A = P->dG9, g.lda = G, g.a_bs = rs9G;
+    g.B = which ? P->H9 : P->X9, g.ldb = LDF, g.b_bs = rs9F;
+    g.M = G, g.N = F, g.K = 9 * cap;
+    g.out = grads + (which ? OFF_WHH : OFF_WIH), g.ldc = LDF, g.out_bs = static_cast<long long>(G) * LDF;
+    g.batch_rows = P->counts9, g.rows_is_k = 1;
+    launch_gemm(g, s), ++n;
+  }
+  colsum_kernel<<<dim3((G + 31) / 32, E), 256, 0, s>>>(P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
+                                                       grads + OFF_BHH), ++n;
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  P->launches = n;
+}
+
+}  // namespace cadre
+
+using cadre::PpoPlan;
+
+#define CADRE_API_BEGIN try {
+#define CADRE_API_END                \
+  }                                  \
+  catch (const cadre::Error& e) {    \
+    cadre::set_last_error(e.what()); \
+    return e.code;                   \
+  }                                  \
+  catch (const std::exception& e) {  \
+    cadre::set_last_error(e.what()); \
+    return 99;                       \
+  }                                  \
+  return 0;
+
+extern "C" {
+
+int64_t cadre_ppo_param_count(void) { return cadre::ppo::TOTAL; }
+
+int cadre_ppo_create(void** handle, const cadre_ppo_config* cfg) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle != nullptr, "handle");
+  static_assert(sizeof(cadre_storage_ref) == sizeof(cadre::StorageRef), "storage ref layout");
+  *handle = cadre::ppo_create(cfg);
+  CADRE_API_END
+}
+
+int cadre_ppo_destroy(void* handle) {
+  CADRE_API_BEGIN
+  cadre::ppo_destroy(static_cast<PpoPlan*>(handle));
+  CADRE_API_END
+}
+
+int cadre_ppo_update(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
+                     float* params, float* grads, float* losses, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle && storages_host && indices_host && params && grads && losses, "ppo_update pointers");
+  cadre::ppo_update(static_cast<PpoPlan*>(handle), storages_host, indices_host, params, grads, losses,
+                    static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+int cadre_ppo_evaluate(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
+                       const float* params, float* row_out, void* stream) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && storages_host && indices_host && params && row_out, "ppo_evaluate pointers");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int n = cadre::ppo_forward(P, storages_host, indices_host, params, s);
+  cadre::head_eval_kernel<<<(2 * P->R + 7) / 8, 256, 0, s>>>(P->Y2, params, P->row_slot, P->row_expert,
+                                                             P->sc.action, P->R, P->cap, row_out);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  P->launches = n + 1;
+  CADRE_API_END
+}
+
+int cadre_ppo_adam_step(void* handle, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
+                        void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle && params && grads && exp_avg && exp_avg_sq && step >= 1, "adam_step arguments");
+  cadre::launch_clip_adam(static_cast<PpoPlan*>(handle)->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm,
+                          lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+int cadre_ppo_module_norms(void* handle, float* norms16_host) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && norms16_host, "module_norms arguments");
+  CADRE_CUDA_CHECK(cudaMemcpy(norms16_host, P->opt.norms, 16 * sizeof(float), cudaMemcpyDeviceToHost));
+  CADRE_API_END
+}
+
+int cadre_ppo_launches(void* handle) {
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  return P ? P->launches : 0;
+}
+
+}  // extern "C"

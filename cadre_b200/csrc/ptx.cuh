@@ -158,7 +158,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // Instruction descriptor (InstrDescriptor): c_format F32 (1) at [4,6); a/b format [7,10)/[10,13)
-// (1 = BF16, 2 = TF32); a/b major bits 15/16 (1 = MN-major); N>>3 at [17,23); M>>4 at [24,29).
+// (0 = F16, 1 = BF16, 2 = TF32); a/b major bits 15/16 (1 = MN-major); N>>3 at [17,23); M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t a_mn_major,
                                                   uint32_t b_mn_major, uint32_t M, uint32_t N) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (a_mn_major << 15) | (b_mn_major << 16) |

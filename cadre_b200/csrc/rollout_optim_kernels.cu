@@ -1,0 +1,223 @@
+// HBM-bound kernels around the PPO update: GAE / returns scan + advantage normalisation, segmented gradient
+// norm + fused clip + Adam over the flat parameter buffer.
+#include "../../include/cadre_b200.h"
+#include "internal.h"
+
+namespace cadre {
+
+// ---------------------------------------------------------------------------------------------------------
+// RolloutStorage.compute_returns (ppo_agent/storage.py:68-76, GAE branch) + advantage normalisation
+// (ppo_agent/train.py:82-88). One warp per (env, head) sequence; the reverse-time recurrence
+//   A_t = (r_t + g V_{t+1} m_t - V_t) + g*tau*m_t * A_{t+1}
+// is an affine scan: each lane composes its chunk's affine map, the 32 maps are suffix-scanned with shuffles,
+// then every lane replays its chunk. Sequences are staged in shared memory with coalesced loads/stores.
+__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
+
+__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+                                                  const float* __restrict__ masks,
+                                                  const float* __restrict__ next_value,
+                                                  float* __restrict__ returns, float* __restrict__ adv, int E,
+                                                  int T, float gamma, float tau, int normalize) {
+  extern __shared__ float gsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (e >= E) return;
+  const int L = skew(T + 1) + 1;
+  float* sr = gsm + warp * 3 * L;
+  float* sv = sr + L;
+  float* sm = sv + L;
+  const long long base = static_cast<long long>(e) * (T + 1);
+  for (int i = lane; i <= T; i += 32) {
+    sr[skew(i)] = rewards[base + i];
+    sv[skew(i)] = (i == T) ? next_value[e] : values[base + i];
+    sm[skew(i)] = masks[base + i];
+  }
+  if (lane == 0) values[base + T] = next_value[e];  // storage.py:70 value_preds[-1] = next_value
+  __syncwarp();
+  const int cs = (T + 31) / 32;
+  const int t0 = lane * cs, t1 = min(T, t0 + cs);
+  // chunk map x -> a*x + b (x = gae entering the chunk from later time steps)
+  float a = 1.f, b = 0.f;
+  for (int t = t1 - 1; t >= t0; --t) {
+    const float m = sm[skew(t)];
+    const float delta = sr[skew(t)] + gamma * sv[skew(t + 1)] * m - sv[skew(t)];
+    const float at = gamma * tau * m;
+    // F_t o F_chunk_so_far : later steps were composed first
+    b = at * b + delta;
+    a = at * a;
+  }
+  // inclusive suffix composition S_l = F_l o F_{l+1} o ... o F_31
+  float sa = a, sb = b;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float oa = __shfl_down_sync(0xffffffffu, sa, off);
+    const float ob = __shfl_down_sync(0xffffffffu, sb, off);
+    if (lane + off < 32) {
+      sb = sa * ob + sb;
+      sa = sa * oa;
+    }
+  }
+  float gae = __shfl_down_sync(0xffffffffu, sb, 1);  // S_{l+1}(0)
+  if (lane == 31) gae = 0.f;
+  // replay the chunk; returns_t = gae + V_t, advantage = returns_t - V_t (train.py:82)
+  float lsum = 0.f;
+  for (int t = t1 - 1; t >= t0; --t) {
+    const float m = sm[skew(t)];
+    const float v = sv[skew(t)];
+    const float delta = sr[skew(t)] + gamma * sv[skew(t + 1)] * m - v;
+    gae = delta + gamma * tau * m * gae;
+    const float ret = gae + v;
+    const float ad = ret - v;
+    sr[skew(t)] = ret;  // r_t is dead from here on
+    sm[skew(t)] = ad;   // m_t too
+    lsum += ad;
+  }
+  __syncwarp();
+  float mean = 0.f, denom = 1.f;
+  if (normalize) {
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    mean = lsum / static_cast<float>(T);
+    float lsq = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const float d = sm[skew(t)] - mean;
+      lsq += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) lsq += __shfl_xor_sync(0xffffffffu, lsq, o);
+    denom = sqrtf(lsq / static_cast<float>(T - 1)) + 1e-8f;  // torch.std is unbiased; train.py:86
+  }
+  for (int i = lane; i < T; i += 32) {
+    returns[base + i] = sr[skew(i)];
+    const float ad = sm[skew(i)];
+    adv[static_cast<long long>(e) * T + i] = normalize ? (ad - mean) / denom : ad;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// chief.py:13-21: per-module clip_grad_norm_(max_norm) on the summed gradient, then one Adam step
+// (torch.optim.Adam defaults, main.py:55). The flat buffers are cut into fixed chunks; every chunk belongs to
+// exactly one of the 16 modules. Pass 1 writes one partial sum of squares per chunk (deterministic), pass 2
+// (one warp per module) reduces them in a fixed order, pass 3 applies clip + Adam elementwise.
+
+__global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g,
+                                                             const long long* __restrict__ chunk_off,
+                                                             const int* __restrict__ chunk_len,
+                                                             float* __restrict__ partial) {
+  const long long off = chunk_off[blockIdx.x];
+  const int len = chunk_len[blockIdx.x];
+  const float4* g4 = reinterpret_cast<const float4*>(g + off);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < (len >> 2); i += 256) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float sm[8];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void sqnorm_final_kernel(const float* __restrict__ partial, const int* __restrict__ mod_first,
+                                    float max_norm, float* __restrict__ clip_coef, float* __restrict__ norms) {
+  // one warp per module; chunks of a module are contiguous in the chunk table
+  const int m = blockIdx.x, lane = threadIdx.x;
+  double s = 0.0;
+  for (int i = mod_first[m] + lane; i < mod_first[m + 1]; i += 32) s += static_cast<double>(partial[i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const float total = static_cast<float>(sqrt(s));
+    norms[m] = total;
+    clip_coef[m] = fminf(max_norm / (total + 1e-6f), 1.0f);  // torch.nn.utils.clip_grad_norm_
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   const long long* __restrict__ chunk_off,
+                                                   const int* __restrict__ chunk_len,
+                                                   const int* __restrict__ chunk_mod,
+                                                   const float* __restrict__ clip_coef, float beta1,
+                                                   float beta2, float eps, float step_size,
+                                                   float bc2_sqrt) {
+  const long long off = chunk_off[blockIdx.x];
+  const int len = chunk_len[blockIdx.x];
+  const float coef = clip_coef[chunk_mod[blockIdx.x]];
+  float4* p4 = reinterpret_cast<float4*>(p + off);
+  const float4* g4 = reinterpret_cast<const float4*>(g + off);
+  float4* m4 = reinterpret_cast<float4*>(m + off);
+  float4* v4 = reinterpret_cast<float4*>(v + off);
+  for (int i = threadIdx.x; i < (len >> 2); i += 256) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float* pe = &pp.x;
+    float* ge = &gg.x;
+    float* me = &mm.x;
+    float* ve = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = ge[k] * coef;
+      me[k] = me[k] + (gr - me[k]) * (1.f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+      ve[k] = ve[k] * beta2 + (1.f - beta2) * gr * gr;       // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(ve[k]) / bc2_sqrt + eps;
+      pe[k] = pe[k] - step_size * (me[k] / denom);           // addcdiv_(exp_avg, denom, value=-step_size)
+    }
+    p4[i] = pp, m4[i] = mm, v4[i] = vv;
+  }
+}
+
+void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
+                      float lr, float beta1, float beta2, float eps, int step, cudaStream_t s) {
+  sqnorm_partial_kernel<<<t.num_chunks, 256, 0, s>>>(grads, t.chunk_off, t.chunk_len, t.partial);
+  sqnorm_final_kernel<<<16, 32, 0, s>>>(t.partial, t.mod_first, max_norm, t.clip_coef, t.norms);
+  // torch.optim.Adam: step_size = lr / (1 - beta1^step); denom = sqrt(v) / sqrt(1 - beta2^step) + eps
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adam_kernel<<<t.num_chunks, 256, 0, s>>>(params, grads, m, v, t.chunk_off, t.chunk_len, t.chunk_mod,
+                                           t.clip_coef, beta1, beta2, eps, static_cast<float>(lr / bc1),
+                                           static_cast<float>(sqrt(bc2)));
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace cadre
+
+#define CADRE_API_BEGIN try {
+#define CADRE_API_END                \
+  }                                  \
+  catch (const cadre::Error& e) {    \
+    cadre::set_last_error(e.what()); \
+    return e.code;                   \
+  }                                  \
+  catch (const std::exception& e) {  \
+    cadre::set_last_error(e.what()); \
+    return 99;                       \
+  }                                  \
+  return 0;
+
+extern "C" {
+
+int cadre_gae(const float* rewards, float* values, const float* masks, const float* next_value, float* returns,
+              float* adv, int E, int T, float gamma, float tau, int normalize, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(rewards && values && masks && next_value && returns && adv, "gae pointers");
+  CADRE_REQUIRE(E > 0 && T > 1 && T <= 16384, "gae sizes (1 < T <= 16384)");
+  const int L = (T + 1) + ((T + 1) >> 5) + 1;
+  const size_t per_warp = 3 * static_cast<size_t>(L) * sizeof(float);
+  int warps = 4;
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  const size_t smem = warps * per_warp;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(cadre::gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+    configured = smem;
+  }
+  cadre::gae_kernel<<<(E + warps - 1) / warps, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  CADRE_API_END
+}
+
+}  // extern "C"

@@ -40,7 +40,7 @@ static void make_map(CUtensorMap* m, int es, int rank, const void* base, const u
   CADRE_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "TMA base address must be 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i)
     CADRE_REQUIRE(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA strides must be positive multiples of 16 bytes");
-  CUresult r = encode_fn()(m, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+  CUresult r = encode_fn()(m, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (CADRE_ENC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
                            rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -115,8 +115,8 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     return;                                                                                           \
   }
   // bf16 operands (encoder linears)
-  CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 0, __nv_bfloat16)
-  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 0, __nv_bfloat16)
+  CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 0, enc_t)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 0, enc_t)
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(0, 0, 1, 128, 3, EPI_LINEAR, 1, float)
@@ -195,9 +195,9 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.act = a.act, p.alpha = 1.f;
   dim3 grid((Hout / TH) * ((a.B + TN - 1) / TN), (a.Cout + bn - 1) / bn, 1);
   if (bn == 64)
-    launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+    launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
   else
-    launch_inst<0, 0, 0, 128, 3, MODE_CONV, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+    launch_inst<0, 0, 0, 128, 3, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -221,7 +221,7 @@ void launch_stem(const StemArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.act = ACT_RELU, p.alpha = 1.f;
   dim3 grid(72 * a.B, 1, 1);
-  launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, __nv_bfloat16>(p, grid, stream);
+  launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, enc_t>(p, grid, stream);
 }
 
 }  // namespace cadre

@@ -7,8 +7,7 @@
 // One CTA = one 128 x BLOCK_N output tile. Warp 0 lane 0 issues TMA, warp 1 lane 0 issues tcgen05.mma into a
 // TMEM accumulator, warps 2..5 drain TMEM (tcgen05.ld) and run the fused epilogue.
 #pragma once
-#include <cuda_bf16.h>
-
+#include "internal.h"
 #include "ptx.cuh"
 
 namespace cadre {
@@ -65,7 +64,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 template <typename OutT>
 __device__ __forceinline__ float load_as_float(const void* base, long long idx) {
   if constexpr (sizeof(OutT) == 2)
-    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+    return enc_to_float(reinterpret_cast<const enc_t*>(base)[idx]);
   else
     return reinterpret_cast<const float*>(base)[idx];
 }
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc(KIND ? 2u : 1u, A_MN, B_MN, 128, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc(KIND ? 2u : (CADRE_ENC_FP16 ? 0u : 1u), A_MN, B_MN, 128, BLOCK_N);
     constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : 32;
     constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : 32;
     constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16;
@@ -257,15 +256,11 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 h0_ = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-              __nv_bfloat162 h1_ = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 h2_ = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              __nv_bfloat162 h3_ = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
               uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0_);
-              u.y = *reinterpret_cast<uint32_t*>(&h1_);
-              u.z = *reinterpret_cast<uint32_t*>(&h2_);
-              u.w = *reinterpret_cast<uint32_t*>(&h3_);
+              u.x = enc_pack2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = enc_pack2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = enc_pack2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = enc_pack2(v[8 * i + 6], v[8 * i + 7]);
               reinterpret_cast<uint4*>(dst)[i] = u;
             }
           } else {
@@ -278,7 +273,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           for (int i = 0; i < 32; ++i)
             if (nb + i < p.N) {
               if constexpr (sizeof(OutT) == 2)
-                dst[i] = __float2bfloat16_rn(v[i]);
+                dst[i] = enc_from_float(v[i]);
               else
                 dst[i] = v[i];
             }

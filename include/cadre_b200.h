@@ -23,12 +23,17 @@ extern "C" {
 const char* cadre_last_error(void);
 /* library / build identification: "cadre_b200 sm_100a <date>" */
 const char* cadre_version(void);
+/* 16-bit storage / tensor-core operand type of the encoder path: 1 = IEEE fp16 (default build), 0 = bf16.
+ * Every "enc16" buffer below (activations, conv / linear weights) uses this type. */
+int cadre_enc_dtype(void);
+/* stream-ordered device-to-device copy (test / debug helper) */
+int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Dense tile operator (tcgen05 + TMEM + TMA). Replaces the cuBLAS/cuDNN calls PyTorch dispatches for
  * nn.Linear / nn.LSTMCell / F.conv2d on the path (ppo_agent/models.py:139-152,165-212;
  * carla_perception/Networks/danet_blocks/resnet.py:39-55,168-183; intertask_att.py:39-80).
- * out[M,N] = epilogue(alpha * A * B^T); kind 0: bf16 operands, kind 1: fp32 operands consumed as TF32.
+ * out[M,N] = epilogue(alpha * A * B^T); kind 0: enc16 operands, kind 1: fp32 operands consumed as TF32.
  * a_mn / b_mn = 0: operand stored [M|N][K] (K contiguous); 1: stored [K][M|N] (M|N contiguous).
  * All leading dimensions / batch strides are in elements. */
 typedef struct cadre_gemm_args {
@@ -59,7 +64,7 @@ typedef struct cadre_gemm_args {
 } cadre_gemm_args;
 int cadre_gemm(const cadre_gemm_args* args, void* stream);
 
-/* NHWC bf16 implicit-GEMM convolution with folded BatchNorm bias, optional residual and ReLU
+/* NHWC enc16 implicit-GEMM convolution with folded BatchNorm bias, optional residual and ReLU
  * (resnet.py:39-55 BasicBlock, danet.py:21-36 conv5a/5c/51/52, danet.py:41 conv8). */
 int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const void* w, int Cout, int KH,
                       int KW, int stride, int pad, const float* bias, const void* res, int res_after_act,
@@ -69,6 +74,103 @@ int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const vo
  * cadre_preprocess (resnet.py:169-171). */
 int cadre_stem_conv(const void* in_padded, int B, const void* w256, const float* bias, void* out,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Perception encoder forward = DANet.get_latent_feature(x, "concate")
+ * (carla_perception/Networks/danet.py:216-238) + CadreAgent.pre_process / get_latent_feature
+ * (ppo_agent/agent.py:43-75, 97-112). Weights are prepared once by the host (BatchNorm folded into the
+ * preceding conv, NHWC / K-major bf16 layouts, linear chains folded) — see cadre_b200/encoder.py. */
+typedef struct cadre_encoder_weights {
+  const void* stem_w;   /* enc16 [64][256]: [cout][row pair 4][kw 8][row 2][c 4], zero where kh==7 or kw==7 */
+  const float* stem_b;  /* [64] conv bias and BN folded */
+  const void* conv_w[19]; /* backbone convs in execution order (per block: conv1, conv2, [downsample]);
+                             enc16 [Cout][KH][KW][Cin], BN folded */
+  const float* conv_b[19];
+  const void* head5_w;  /* conv5a | conv5c stacked on Cout: enc16 [256][3][3][512] */
+  const float* head5_b; /* [256] */
+  const float* pam_wqk; /* fp32 [32][128]: query_conv rows 0..15, key_conv rows 16..31 */
+  const float* pam_bqk; /* [32] */
+  const float* pam_wv;  /* fp32 [128][128] */
+  const float* pam_bv;  /* [128] */
+  const void* conv51_w; /* enc16 [128][3][3][128] */
+  const float* conv51_b;
+  const void* conv52_w;
+  const float* conv52_b;
+  const void* fc1_w;    /* enc16 [3072][5120]: Linear(20480,512) x6 o {visual,bc}_conv o conv8, K = (h*8+w)*128+c */
+  const float* fc1_b;   /* [3072] */
+  const void* fc2_w;    /* enc16 [6][256][512], order vis q,k,v, bc q,k,v */
+  const float* fc2_b;   /* [6][256] */
+  float pam_gamma, cam_gamma;
+} cadre_encoder_weights;
+
+int cadre_encoder_create(void** handle, const cadre_encoder_weights* w, int max_batch);
+int cadre_encoder_destroy(void* handle);
+/* rgb u8 [B][144][256][3], route_fig u8 [B][256][144], measurements f64 [B][3] or NULL;
+ * out fp32 [B][ld_out]: 512 latent floats (+ 18 measurement floats when measurements != NULL). */
+int cadre_encoder_forward_u8(void* handle, const uint8_t* rgb, const uint8_t* route_fig,
+                             const double* measurements, int B, float* out, int ld_out, void* stream);
+/* x fp32 NCHW [B][4][144][256] already pre-processed (BASELINE config 2, encoder sweep). */
+int cadre_encoder_forward_f32(void* handle, const float* x_nchw, int B, float* out, int ld_out, void* stream);
+/* internal activation buffers for parity tests: 0 layer4 out, 1 feat_sum, 2 conv5a|5c, 3 PAM, 4 CAM, 5 stem */
+int cadre_encoder_buffer(void* handle, int which, void** ptr, int64_t* elems_per_frame);
+/* kernels launched by the last forward call */
+int cadre_encoder_launches(void* handle);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Rollout: RolloutStorage.compute_returns GAE branch (ppo_agent/storage.py:68-76) + advantage
+ * normalisation with unbiased std (ppo_agent/train.py:82-88), one sequence per (env, head).
+ * rewards / values / masks / returns: fp32 [E][T+1]; next_value fp32 [E]; adv fp32 [E][T].
+ * values[e][T] is overwritten with next_value[e] exactly as the reference does. */
+int cadre_gae(const float* rewards, float* values, const float* masks, const float* next_value, float* returns,
+              float* adv, int E, int T, float gamma, float tau, int normalize, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * PPO update = CadreAgent.update_policy (ppo_agent/agent.py:166-237) for `workers` logical workers at once
+ * (forward + hand-written backward; gradients are the SUM over workers, like Shared_grad_buffers.add_gradient,
+ * ppo_agent/models.py:231-239), then the chief's per-module clip + Adam (ppo_agent/chief.py:13-21).
+ * Parameters / gradients / Adam moments are flat fp32 buffers of cadre_ppo_param_count() elements in the
+ * layout of cadre_b200/csrc/ppo_layout.h (converted from / to reference state dicts by
+ * cadre_b200/ppo_params.py). Between cadre_ppo_update and cadre_ppo_adam_step the host all-reduces (sum) the
+ * gradient buffer across ranks (NCCL), which replaces the shared-memory aggregation of the reference. */
+typedef struct cadre_ppo_config {
+  int32_t workers;    /* logical workers (envs) whose minibatches are processed per update on this GPU */
+  int32_t mini_batch; /* rows per worker per head = num_steps / mini_batch_num (storage.py:94) */
+  float clip, value_coeff, clip_coeff, ent_coeff; /* agent_config.py:43-46 */
+} cadre_ppo_config;
+
+/* device pointers into one RolloutStorage (ppo_agent/storage.py:8-26) + its advantage vector */
+typedef struct cadre_storage_ref {
+  const float* obs;              /* [T+1][8][530] */
+  const int64_t* action;         /* [T+1][1] */
+  const float* value_preds;      /* [T+1][1] */
+  const float* returns;          /* [T+1][1] */
+  const float* action_log_probs; /* [T+1][1] */
+  const float* adv;              /* [T][1] normalised advantages */
+  const float* hn;               /* [T+1][530] */
+  const float* cn;               /* [T+1][530] */
+  const int32_t* command;        /* [T+1][1] */
+} cadre_storage_ref;
+
+int64_t cadre_ppo_param_count(void);
+int cadre_ppo_create(void** handle, const cadre_ppo_config* cfg);
+int cadre_ppo_destroy(void* handle);
+/* storages_host: [workers][2] (steer, throttle); indices_host: int32 [workers][2][mini_batch] minibatch row
+ * indices (host-generated, bit-exact torch.randperm chunks); losses: device fp32 [workers][2][3] =
+ * per-worker, per-head UN-scaled (value, action, entropy) losses. grads is overwritten. */
+int cadre_ppo_update(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
+                     float* params, float* grads, float* losses, void* stream);
+/* Forward only (CadreAgent.act / get_value, Model.evaluate_actions; agent.py:114-164, models.py:184-212):
+ * row_out fp32 [2 heads][workers*mini_batch][36] = value, log-prob(stored action), entropy, 33 normalised
+ * logits (first 3 valid for the throttle head); row order = (worker, minibatch position). */
+int cadre_ppo_evaluate(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
+                       const float* params, float* row_out, void* stream);
+int cadre_ppo_adam_step(void* handle, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
+                        void* stream);
+/* gradient norms of the 16 modules seen by the last adam_step: [0..7] LSTM of expert e, [8..15] actor-critic
+ * of expert e (expert = head*4 + command); synchronises */
+int cadre_ppo_module_norms(void* handle, float* norms16_host);
+int cadre_ppo_launches(void* handle);
 
 #ifdef __cplusplus
 }

@@ -99,7 +99,7 @@ def danet_fixture_state(seed=0, peaky=False):
     for nm, cin in (("conv5a", 512), ("conv5c", 512), ("conv51", 128), ("conv52", 128)):
         _conv_w(sd, f"da_head.{nm}.0.weight", 128, cin, 3, seed)
         _bn(sd, f"da_head.{nm}.1", 128, seed)
-    qk_gain = 6.0 if peaky else 1.0
+    qk_gain = 1.5 if peaky else 1.0
     for nm, co in (("query_conv", 16), ("key_conv", 16), ("value_conv", 128)):
         g = qk_gain if nm != "value_conv" else 1.0
         sd[f"da_head.sa.{nm}.weight"] = fixture_tensor(f"da_head.sa.{nm}.weight", (co, 128, 1, 1), seed,
@@ -113,7 +113,7 @@ def danet_fixture_state(seed=0, peaky=False):
     for nm in ("visual_conv", "bc_conv"):
         sd[nm + ".weight"] = fixture_tensor(nm + ".weight", (512, 512, 1, 1), seed, std=1.0 / math.sqrt(512))
         sd[nm + ".bias"] = fixture_tensor(nm + ".bias", (512,), seed, std=0.05)
-    it_gain = 40.0 if peaky else 1.0
+    it_gain = 2.0 if peaky else 1.0
     for task in ("visual", "bc"):
         for role in ("query", "key", "value"):
             p = f"inter_task_att.{task}_{role}_layer"

@@ -13,6 +13,7 @@ from cadre_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 dev = torch.device("cuda:0")
+ENC16 = _lib.enc_dtype()
 torch.manual_seed(0)
 
 
@@ -29,7 +30,7 @@ def report(name, got, ref, tol):
 
 def run_gemm(kind, a_mn, b_mn, M, N, K, batch=1, out_f32=1, act=0, bias=False, res=False, block_n=0,
              rows=None, name=""):
-    dt = torch.float32 if kind else torch.bfloat16
+    dt = torch.float32 if kind else ENC16
     es = 4 if kind else 2
     al = 16 // es
 
@@ -58,7 +59,7 @@ def run_gemm(kind, a_mn, b_mn, M, N, K, batch=1, out_f32=1, act=0, bias=False, r
         Bs = torch.zeros(batch, N, ldb, device=dev, dtype=dt)
         Bs[:, :, :K] = Bm
         b_bs = N * ldb
-    odt = torch.float32 if out_f32 else torch.bfloat16
+    odt = torch.float32 if out_f32 else ENC16
     ldc = (N + 7) // 8 * 8
     out = torch.full((batch, M, ldc), 7.0, device=dev, dtype=odt)
     bias_t = torch.randn(batch, N, device=dev) if bias else None
@@ -105,15 +106,15 @@ def run_gemm(kind, a_mn, b_mn, M, N, K, batch=1, out_f32=1, act=0, bias=False, r
 
 
 def run_conv(B, H, W, Cin, Cout, k, stride, pad, act=1, res=False, name=""):
-    x = torch.randn(B, Cin, H, W, device=dev).to(torch.bfloat16)
-    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    x = torch.randn(B, Cin, H, W, device=dev).to(ENC16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(ENC16)
     bias = torch.randn(Cout, device=dev)
     Ho = (H + 2 * pad - k) // stride + 1
     Wo = (W + 2 * pad - k) // stride + 1
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     w_k = w.permute(0, 2, 3, 1).contiguous().view(Cout, -1)
-    r = torch.randn(B, Ho, Wo, Cout, device=dev).to(torch.bfloat16) if res else None
-    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=torch.bfloat16)
+    r = torch.randn(B, Ho, Wo, Cout, device=dev).to(ENC16) if res else None
+    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=ENC16)
     rc = L.cadre_conv2d_nhwc(_lib.ptr(x_nhwc), B, H, W, Cin, _lib.ptr(w_k), Cout, k, k, stride, pad,
                              _lib.ptr(bias), _lib.ptr(r), 0, act, _lib.ptr(out), _lib.stream_ptr())
     if rc != 0:
@@ -129,18 +130,18 @@ def run_conv(B, H, W, Cin, Cout, k, stride, pad, act=1, res=False, name=""):
 
 
 def run_stem(B, name="stem"):
-    x = torch.randn(B, 4, 144, 256, device=dev).to(torch.bfloat16)
-    w = (torch.randn(64, 4, 7, 7, device=dev) / 14.0).to(torch.bfloat16)
+    x = torch.randn(B, 4, 144, 256, device=dev).to(ENC16)
+    w = (torch.randn(64, 4, 7, 7, device=dev) / 14.0).to(ENC16)
     bias = torch.randn(64, device=dev)
-    xp = torch.zeros(B, 150, 262, 4, device=dev, dtype=torch.bfloat16)
+    xp = torch.zeros(B, 150, 262, 4, device=dev, dtype=ENC16)
     xp[:, 3:147, 3:259, :] = x.permute(0, 2, 3, 1)
     # row-pair interleaved: [B][75][262][2][4]
     xp = xp.view(B, 75, 2, 262, 4).permute(0, 1, 3, 2, 4).contiguous()
     # weights [64][j 4][kw 8][r 2][c 4], zero for kh==7 / kw==7
-    wk = torch.zeros(64, 8, 8, 4, device=dev, dtype=torch.bfloat16)   # [o][kh][kw][c]
+    wk = torch.zeros(64, 8, 8, 4, device=dev, dtype=ENC16)   # [o][kh][kw][c]
     wk[:, :7, :7, :] = w.permute(0, 2, 3, 1)
     wk = wk.view(64, 4, 2, 8, 4).permute(0, 1, 3, 2, 4).contiguous().view(64, 256)
-    out = torch.full((B, 72, 128, 64), 7.0, device=dev, dtype=torch.bfloat16)
+    out = torch.full((B, 72, 128, 64), 7.0, device=dev, dtype=ENC16)
     rc = L.cadre_stem_conv(_lib.ptr(xp), B, _lib.ptr(wk), _lib.ptr(bias), _lib.ptr(out), _lib.stream_ptr())
     if rc != 0:
         print(f"FAIL {name}: rc={rc} {L.cadre_last_error().decode()}", flush=True)
@@ -209,9 +210,9 @@ def conv_cases():
 def perf_cases():
     # throughput probes (kernel only)
     for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 8192)]:
-        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
-        Bm = torch.randn(N, K, device=dev).to(torch.bfloat16)
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        A = torch.randn(M, K, device=dev).to(ENC16)
+        Bm = torch.randn(N, K, device=dev).to(ENC16)
+        out = torch.empty(M, N, device=dev, dtype=ENC16)
         g = _lib.GemmArgs()
         g.kind, g.batch, g.M, g.N, g.K = 0, 1, M, N, K
         g.A, g.B, g.lda, g.ldb = A.data_ptr(), Bm.data_ptr(), K, K
@@ -222,19 +223,19 @@ def perf_cases():
         print(f"perf bf16 gemm {M}x{N}x{K}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s (torch {ms_t:.3f} ms = "
               f"{2*M*N*K/ms_t/1e9:.1f})", flush=True)
     B = 256
-    x = torch.randn(B, 36, 64, 64, device=dev).to(torch.bfloat16)
-    w = torch.randn(64, 576, device=dev).to(torch.bfloat16)
+    x = torch.randn(B, 36, 64, 64, device=dev).to(ENC16)
+    w = torch.randn(64, 576, device=dev).to(ENC16)
     bias = torch.randn(64, device=dev)
-    out = torch.empty(B, 36, 64, 64, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(B, 36, 64, 64, device=dev, dtype=ENC16)
     sp = _lib.stream_ptr()
     ms = timed(lambda: L.cadre_conv2d_nhwc(_lib.ptr(x), B, 36, 64, 64, _lib.ptr(w), 64, 3, 3, 1, 1, _lib.ptr(bias),
                                            None, 0, 1, _lib.ptr(out), sp))
     fl = 2 * B * 36 * 64 * 64 * 576
     print(f"perf conv3x3 layer1 B={B}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
-    x4 = torch.randn(B, 5, 8, 512, device=dev).to(torch.bfloat16)
-    w4 = torch.randn(512, 4608, device=dev).to(torch.bfloat16)
+    x4 = torch.randn(B, 5, 8, 512, device=dev).to(ENC16)
+    w4 = torch.randn(512, 4608, device=dev).to(ENC16)
     b4 = torch.randn(512, device=dev)
-    o4 = torch.empty(B, 5, 8, 512, device=dev, dtype=torch.bfloat16)
+    o4 = torch.empty(B, 5, 8, 512, device=dev, dtype=ENC16)
     ms = timed(lambda: L.cadre_conv2d_nhwc(_lib.ptr(x4), B, 5, 8, 512, _lib.ptr(w4), 512, 3, 3, 1, 1, _lib.ptr(b4),
                                            None, 0, 1, _lib.ptr(o4), sp))
     fl = 2 * B * 40 * 512 * 4608

@@ -7,6 +7,8 @@
 #include "../../include/cadre_b200.h"
 #include "internal.h"
 
+#include <cstring>
+#include <string>
 #include <vector>
 
 namespace cadre {
@@ -42,7 +44,19 @@ struct Encoder {
   uint8_t* route_max = nullptr;      // [Bmax]
   enc_t* l4 = nullptr;       // alias of the act buffer holding layer4's output after a forward
   int launches_per_forward = 0;
+  // optional per-launch timing (cadre_encoder_profile)
+  bool prof = false;
+  cudaEvent_t ev[64];
+  std::vector<std::string> names;
 };
+
+static inline void step(Encoder* e, cudaStream_t s, int& n, const char* name) {
+  ++n;
+  if (e->prof) {
+    cudaEventRecord(e->ev[n], s);
+    e->names.push_back(name);
+  }
+}
 
 template <typename T>
 static T* dev_alloc(size_t n, bool zero) {
@@ -99,11 +113,15 @@ static void conv(Encoder* e, int idx, const enc_t* in, int B, int H, int W, int 
 // everything after the ingest kernel; `B` frames already sit in e->padded
 static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int ld_out, cudaStream_t s) {
   int n = 0;
+  if (e->prof) {
+    e->names.clear();
+    cudaEventRecord(e->ev[0], s);
+  }
   StemArgs st;
   st.in = e->padded, st.B = B, st.w = static_cast<const enc_t*>(e->w.stem_w), st.bias = e->w.stem_b;
   st.out = e->stem;
-  launch_stem(st, s), ++n;
-  launch_maxpool(e->stem, e->act[0], B, 72, 128, 64, s), ++n;
+  launch_stem(st, s), step(e, s, n, "stem");
+  launch_maxpool(e->stem, e->act[0], B, 72, 128, 64, s), step(e, s, n, "maxpool");
 
   // ResNet-18 BasicBlocks (resnet.py:39-55, 116-119); conv indices follow execution order
   int cur = 0, ci = 0, H = 36, W = 64, C = 64;
@@ -117,14 +135,17 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
       enc_t* t = e->act[(cur + 1) & 3];
       enc_t* ds = e->act[(cur + 2) & 3];
       enc_t* o = e->act[(cur + 3) & 3];
-      conv(e, ci++, x, B, H, W, C, Cout, 3, stride, 1, nullptr, 1, t, s), ++n;
+      conv(e, ci++, x, B, H, W, C, Cout, 3, stride, 1, nullptr, 1, t, s);
+      step(e, s, n, (std::string("layer") + std::to_string(li + 1) + "." + std::to_string(bi) + ".conv1").c_str());
       const enc_t* idn = x;
       const int conv2_idx = ci++;
       if (stride == 2) {
-        conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s), ++n;
+        conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s);
+        step(e, s, n, (std::string("layer") + std::to_string(li + 1) + ".0.downsample").c_str());
         idn = ds;
       }
-      conv(e, conv2_idx, t, B, Ho, Wo, Cout, Cout, 3, 1, 1, idn, 1, o, s), ++n;
+      conv(e, conv2_idx, t, B, Ho, Wo, Cout, Cout, 3, 1, 1, idn, 1, o, s);
+      step(e, s, n, (std::string("layer") + std::to_string(li + 1) + "." + std::to_string(bi) + ".conv2").c_str());
       cur = (cur + 3) & 3;
       H = Ho, W = Wo, C = Cout;
     }
@@ -137,21 +158,21 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     a.in = e->l4, a.B = B, a.Hin = 5, a.Win = 8, a.Cin = 512;
     a.w = static_cast<const enc_t*>(e->w.head5_w), a.bias = e->w.head5_b;
     a.Cout = 256, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->head5;
-    launch_conv(a, s), ++n;
+    launch_conv(a, s), step(e, s, n, "conv5a|conv5c");
   }
   launch_pam(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_wv, e->w.pam_bv, e->w.pam_gamma, B, 256,
-             e->num_sms, s), ++n;
-  launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), ++n;
+             e->num_sms, s), step(e, s, n, "pam");
+  launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), step(e, s, n, "cam");
   {
     ConvArgs a;
     a.in = e->sa, a.B = B, a.Hin = 5, a.Win = 8, a.Cin = 128;
     a.w = static_cast<const enc_t*>(e->w.conv51_w), a.bias = e->w.conv51_b;
     a.Cout = 128, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->sa_conv;
-    launch_conv(a, s), ++n;
+    launch_conv(a, s), step(e, s, n, "conv51");
     a.in = e->sc;
     a.w = static_cast<const enc_t*>(e->w.conv52_w), a.bias = e->w.conv52_b;
     a.res = e->sa_conv, a.res_after_act = 1, a.out = e->feat_sum;  // feat_sum = relu(conv52) + sa_conv
-    launch_conv(a, s), ++n;
+    launch_conv(a, s), step(e, s, n, "conv52+sum");
   }
   // conv8 -> {visual_conv, bc_conv} -> six Linear(20480,512): all linear, folded offline into fc1 (K = 40*128)
   {
@@ -159,7 +180,7 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     g.kind = 0, g.A = e->feat_sum, g.lda = 5120, g.B = e->w.fc1_w, g.ldb = 5120;
     g.M = B, g.N = 3072, g.K = 5120;
     g.out = e->fc1, g.ldc = 3072, g.out_f32 = 0, g.bias = e->w.fc1_b, g.act = 2;
-    launch_gemm(g, s), ++n;
+    launch_gemm(g, s), step(e, s, n, "fc1(folded)");
   }
   {
     GemmArgs g;
@@ -169,9 +190,9 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     g.M = B, g.N = 256, g.K = 512;
     g.out = e->qkv, g.ldc = 256, g.out_bs = static_cast<long long>(B) * 256, g.out_f32 = 1;
     g.bias = e->w.fc2_b, g.bias_bs = 256;
-    launch_gemm(g, s), ++n;
+    launch_gemm(g, s), step(e, s, n, "fc2");
   }
-  launch_intertask(e->qkv, out, meas, B, ld_out, s), ++n;
+  launch_intertask(e->qkv, out, meas, B, ld_out, s), step(e, s, n, "intertask");
   e->launches_per_forward = n + 2;
 }
 
@@ -245,6 +266,31 @@ int cadre_encoder_buffer(void* handle, int which, void** ptr, int64_t* elems_per
     case 5: *ptr = e->stem, *elems_per_frame = 72 * 128 * 64; break;   // stem output
     default: throw cadre::Error(1, "encoder_buffer: unknown buffer id");
   }
+  CADRE_API_END
+}
+
+int cadre_encoder_profile(void* handle, int B, float* out, int ld_out, float* ms_out, char* names_out,
+                          int names_cap, int* n_out, void* stream) {
+  CADRE_API_BEGIN
+  Encoder* e = static_cast<Encoder*>(handle);
+  CADRE_REQUIRE(e && out && ms_out && names_out && n_out, "encoder_profile pointers");
+  CADRE_REQUIRE(B > 0 && B <= e->max_batch, "batch exceeds the encoder's max_batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 64; ++i) CADRE_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
+  e->prof = true;
+  cadre::encoder_trunk(e, B, nullptr, out, ld_out, s);   // re-runs the trunk on the frames already ingested
+  e->prof = false;
+  CADRE_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int n = static_cast<int>(e->names.size());
+  std::string joined;
+  for (int i = 0; i < n; ++i) {
+    CADRE_CUDA_CHECK(cudaEventElapsedTime(&ms_out[i], e->ev[i], e->ev[i + 1]));
+    joined += e->names[i] + (i + 1 < n ? ";" : "");
+  }
+  for (int i = 0; i < 64; ++i) cudaEventDestroy(e->ev[i]);
+  CADRE_REQUIRE(static_cast<int>(joined.size()) < names_cap, "names buffer too small");
+  memcpy(names_out, joined.c_str(), joined.size() + 1);
+  *n_out = n;
   CADRE_API_END
 }
 

@@ -2,6 +2,7 @@
 #include "internal.h"
 #include "tc_gemm.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace cadre {
@@ -26,6 +27,11 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// fp32 operands are loaded as CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 so that TMA rounds them to TF32 (round to
+// nearest) on the way to shared memory; plain FLOAT32 would leave the truncation to the tensor core, which
+// biases every product towards zero (measured: 7.7e-4 -> see DESIGN.md). CADRE_TF32_TRUNCATE=1 restores that.
+static const bool g_tf32_rn = getenv("CADRE_TF32_TRUNCATE") == nullptr;
+
 // dims/box innermost first; strides_bytes has rank-1 entries (dimension 0 is contiguous).
 static void make_map(CUtensorMap* m, int es, int rank, const void* base, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool atom32 = false) {
@@ -40,7 +46,7 @@ static void make_map(CUtensorMap* m, int es, int rank, const void* base, const u
   CADRE_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "TMA base address must be 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i)
     CADRE_REQUIRE(gstr[i] % 16 == 0 && gstr[i] > 0, "TMA strides must be positive multiples of 16 bytes");
-  CUresult r = encode_fn()(m, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (CADRE_ENC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
+  CUresult r = encode_fn()(m, es == 4 ? (g_tf32_rn ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32) : (CADRE_ENC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
                            rank, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

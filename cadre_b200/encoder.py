@@ -186,6 +186,16 @@ class Encoder:
         _lib.check(self._lib.cadre_memcpy_d2d(_lib.ptr(t), p, ctypes.c_int64(B * n.value * 2), _lib.stream_ptr()))
         return t
 
+    def profile(self, B):
+        """[(launch name, ms)] for the trunk re-run on the B frames ingested by the previous forward call."""
+        out = torch.empty(B, 512, device=self.device, dtype=torch.float32)
+        ms = (ctypes.c_float * 64)()
+        names = ctypes.create_string_buffer(4096)
+        n = ctypes.c_int()
+        _lib.check(self._lib.cadre_encoder_profile(self._h, B, _lib.ptr(out), 512, ms, names, 4096, ctypes.byref(n),
+                                                   _lib.stream_ptr()))
+        return list(zip(names.value.decode().split(";"), [ms[i] for i in range(n.value)]))
+
     @property
     def launches_per_forward(self):
         return int(self._lib.cadre_encoder_launches(self._h))

@@ -1,0 +1,142 @@
+"""Data-parallel learner: the B200 replacement of the worker/chief handshake
+(ppo_agent/train.py:76-110, ppo_agent/chief.py:8-27, ppo_agent/models.py:219-258).
+
+Contract kept from the reference: every logical worker contributes exactly one gradient per update step;
+the step applied is Adam on the SUM of the workers' gradients with a per-module clip at max_grad_norm; all
+replicas hold identical parameters afterwards. How it is done here:
+  * the W_local workers of a rank are processed by ONE batched cadre_ppo_update call (their gradients are
+    summed on the device by construction);
+  * across ranks the flat fp32 gradient (77.9 MB) is summed with one NCCL all-reduce over NVLink
+    (`torch.distributed.all_reduce`), which replaces Shared_grad_buffers + the 1 Hz polling chief;
+  * every rank then runs the same deterministic clip + Adam kernel, so no parameter broadcast
+    (agent.py:239-243) is needed and replicas stay bit-identical.
+"""
+import numpy as np
+import torch
+
+from . import ppo as _ppo
+from . import ppo_params
+from .storage import RolloutStorage
+
+
+class RolloutPool:
+    """W x 2 RolloutStorage objects (steer, throttle per worker; train.py:44-48) whose tensors are views of
+    batched device tensors, so that one GAE launch covers all 2W sequences."""
+
+    def __init__(self, workers, rollout_cfg, device):
+        self.workers, self.device = workers, torch.device(device)
+        cfg = dict(rollout_cfg)
+        cfg.setdefault("hidden_size", cfg["feature_dims"])
+        T, S, Fd, Hd = cfg["num_steps"], cfg["seq_length"], cfg["feature_dims"], cfg["hidden_size"]
+        n = workers * 2
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=self.device)  # noqa: E731
+        self.batched = dict(
+            command=z(n, T + 1, 1, dtype=torch.int32), obs=z(n, T + 1, S, Fd), rewards=z(n, T + 1, 1),
+            value_preds=z(n, T + 1, 1), returns=z(n, T + 1, 1), action_log_probs=z(n, T + 1, 1),
+            action=z(n, T + 1, 1, dtype=torch.int64), masks=z(n, T + 1, 1), hn=z(n, T + 1, Hd), cn=z(n, T + 1, Hd),
+            advantages=z(n, T, 1))
+        self.next_value = z(n)
+        self.storages = []
+        for w in range(workers):
+            pair = []
+            for h in range(2):
+                st = RolloutStorage(**cfg)
+                for name, t in self.batched.items():
+                    setattr(st, name, t[w * 2 + h])
+                pair.append(st)
+            self.storages.append(tuple(pair))
+        self.num_steps, self.gamma, self.tau = T, cfg["gamma"], cfg["tau"]
+
+    def compute_returns(self, next_values=None, normalize=True):
+        """All 2W sequences in one launch (storage.py:68-76 + train.py:82-88). next_values: [W,2] or None to use
+        self.next_value."""
+        if next_values is not None:
+            self.next_value.copy_(torch.as_tensor(next_values, dtype=torch.float32).reshape(-1))
+        b, T = self.batched, self.num_steps
+        n = self.workers * 2
+        _ppo.gae(b["rewards"].view(n, T + 1), b["value_preds"].view(n, T + 1), b["masks"].view(n, T + 1),
+                 self.next_value, b["returns"].view(n, T + 1), b["advantages"].view(n, T), self.gamma, self.tau,
+                 normalize)
+
+
+class Learner:
+    def __init__(self, workers, mini_batch, ppo_state, device="cuda:0", clip=0.1, value_coeff=0.1, clip_coeff=1.0,
+                 ent_coeff=0.01, lr=3e-4, max_grad_norm=250.0, process_group=None, seeds=None):
+        self.device = torch.device(device)
+        self.workers, self.mini_batch = workers, mini_batch
+        self.value_coeff, self.clip_coeff, self.ent_coeff = value_coeff, clip_coeff, ent_coeff
+        self.lr, self.max_grad_norm = lr, max_grad_norm
+        self.engine = _ppo.PpoEngine(workers, mini_batch, clip, value_coeff, clip_coeff, ent_coeff, self.device)
+        self.params = ppo_params.pack_state(ppo_state, self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.losses = torch.zeros(workers, 2, 3, device=self.device)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        # one CPU RNG stream per logical worker (each reference worker is its own process with its own global RNG)
+        self._rng_states = []
+        if seeds is not None:
+            keep = torch.get_rng_state()
+            for s in seeds:
+                torch.manual_seed(int(s))
+                self._rng_states.append(torch.get_rng_state())
+            torch.set_rng_state(keep)
+
+    # ---------------------------------------------------------------- index sampling (bit-exact, host side)
+    def sample_epoch_indices(self, storages):
+        """One PPO epoch of minibatch indices for every worker: [n_minibatches][W][2][mb] (train.py:94-96: the
+        steer generator draws its permutation first, then the throttle generator)."""
+        per_worker = []
+        keep = torch.get_rng_state() if self._rng_states else None
+        for w, (st_s, st_t) in enumerate(storages):
+            if self._rng_states:
+                torch.set_rng_state(self._rng_states[w])
+            s_chunks = st_s.sample_indices()
+            t_chunks = st_t.sample_indices()
+            if self._rng_states:
+                self._rng_states[w] = torch.get_rng_state()
+            per_worker.append((s_chunks, t_chunks))
+        if keep is not None:
+            torch.set_rng_state(keep)
+        n_mb = min(len(per_worker[0][0]), len(per_worker[0][1]))
+        out = np.empty((n_mb, len(storages), 2, self.mini_batch), dtype=np.int32)
+        for w, (s_chunks, t_chunks) in enumerate(per_worker):
+            for k in range(n_mb):
+                out[k, w, 0] = s_chunks[k]
+                out[k, w, 1] = t_chunks[k]
+        return out
+
+    # ---------------------------------------------------------------- one synchronous update step
+    def update_step(self, storages, indices, async_losses=True):
+        """update_policy for all local workers -> all-reduce(sum) -> per-module clip + Adam.
+        storages[w] = (steer, throttle) RolloutStorage with `.advantages`; indices int32 [W,2,mb]."""
+        advs = [(s.advantages, t.advantages) for s, t in storages]
+        self.engine.update(storages, advs, indices, self.params, self.grads, self.losses)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
+                              self.max_grad_norm, self.lr)
+        return self.losses if async_losses else self.scaled_losses()
+
+    def scaled_losses(self):
+        """[W,3] = (value_loss*coeff, action_loss*coeff, entropy*coeff) per worker, like update_policy's return."""
+        L = self.losses.sum(1).cpu()
+        return L * torch.tensor([self.value_coeff, self.clip_coeff, self.ent_coeff])
+
+    def learn(self, pool_or_storages, ppo_epoch=4):
+        """ppo_epoch x minibatches of update_step over already computed returns/advantages (train.py:93-110)."""
+        storages = pool_or_storages.storages if hasattr(pool_or_storages, "storages") else pool_or_storages
+        n = 0
+        for _ in range(ppo_epoch):
+            for idx in self.sample_epoch_indices(storages):
+                self.update_step(storages, idx)
+                n += 1
+        return n
+
+    def state(self):
+        return ppo_params.unpack_state(self.params)

@@ -113,6 +113,11 @@ int cadre_encoder_forward_u8(void* handle, const uint8_t* rgb, const uint8_t* ro
 int cadre_encoder_forward_f32(void* handle, const float* x_nchw, int B, float* out, int ld_out, void* stream);
 /* internal activation buffers for parity tests: 0 layer4 out, 1 feat_sum, 2 conv5a|5c, 3 PAM, 4 CAM, 5 stem */
 int cadre_encoder_buffer(void* handle, int which, void** ptr, int64_t* elems_per_frame);
+/* Re-runs the trunk on the frames ingested by the previous forward call with a CUDA event between launches:
+ * ms_out[i] = device time of launch i (<= 64), names_out = ';'-joined launch names. Measurement helper for
+ * bench.py's roofline object; synchronises the stream. */
+int cadre_encoder_profile(void* handle, int B, float* out, int ld_out, float* ms_out, char* names_out,
+                          int names_cap, int* n_out, void* stream);
 /* kernels launched by the last forward call */
 int cadre_encoder_launches(void* handle);
 

@@ -3,6 +3,8 @@
 
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace cadre {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
@@ -46,6 +48,8 @@ int cadre_gemm(const cadre_gemm_args* s, void* stream) {
   a.mask = s->mask, a.ldm = s->ldm, a.mask_bs = s->mask_bs;
   a.batch_rows = s->batch_rows, a.rows_is_k = s->rows_is_k;
   a.alpha = s->alpha, a.epi = s->epi;
+  if (getenv("CADRE_DBG_A_SHIFT")) a.dbg_a_shift = atoi(getenv("CADRE_DBG_A_SHIFT"));
+  if (getenv("CADRE_DBG_BASE_OFFSET")) a.dbg_base_offset = atoi(getenv("CADRE_DBG_BASE_OFFSET"));
   a.xpart = s->xpart, a.c_prev = s->c_prev, a.c_out = s->c_out, a.h_out = s->h_out;
   a.gates_out = s->gates_out, a.ldx = s->ldx, a.x_bs = s->x_bs, a.ldh = s->ldh, a.h_bs = s->h_bs;
   cadre::launch_gemm(a, static_cast<cudaStream_t>(stream));

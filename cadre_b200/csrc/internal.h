@@ -80,6 +80,7 @@ struct GemmArgs {
   const int* batch_rows = nullptr;
   int rows_is_k = 0;
   int block_n = 0;  // 0 = choose
+  int dbg_a_shift = 0, dbg_base_offset = 0;
   // LSTM-cell epilogue (epi = 1)
   int epi = 0;
   const float* xpart = nullptr;

@@ -96,6 +96,7 @@ static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
   p.mask = a.mask, p.ldm = a.ldm, p.mask_bs = a.mask_bs;
   p.act = a.act, p.alpha = a.alpha;
   p.batch_rows = a.batch_rows, p.rows_is_k = a.rows_is_k;
+  p.dbg_a_shift = a.dbg_a_shift, p.dbg_base_offset = a.dbg_base_offset;
   p.xpart = a.xpart, p.ldx = a.ldx, p.x_bs = a.x_bs;
   p.c_prev = a.c_prev, p.c_out = a.c_out, p.h_out = a.h_out, p.gates_out = a.gates_out;
   p.ldh = a.ldh, p.h_bs = a.h_bs;

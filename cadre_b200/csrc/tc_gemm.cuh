@@ -39,6 +39,7 @@ struct TcGemmParams {
   long long ldm, mask_bs;
   int act;
   float alpha;
+  int dbg_a_shift, dbg_base_offset;  // experiment: A descriptor start shifted by rows (128 B each)
   const int* batch_rows;  // optional [gridDim.z]: valid rows (M) per batch, or valid K when rows_is_k
   int rows_is_k;
   // EPI_LSTM: acc = h_{t-1} W_hh^T (gate-interleaved columns 4*u+g); xpart holds x_t W_ih^T + b_ih + b_hh
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       const uint32_t b_addr = a_addr + S::A_BYTES;
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
-        const uint64_t da = umma_smem_desc(a_addr + k * A_KSTEP, A_LBO, A_SBO, A_LAYOUT);
+        uint64_t da = umma_smem_desc(a_addr + k * A_KSTEP + p.dbg_a_shift * 128, A_LBO, A_SBO, A_LAYOUT);
+        da |= static_cast<uint64_t>(p.dbg_base_offset & 7) << 49;
         const uint64_t db = umma_smem_desc(b_addr + k * B_KSTEP, B_LBO, B_SBO, B_LAYOUT);
         if constexpr (KIND)
           tc_mma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);

@@ -312,8 +312,25 @@ def run_cadre(args):
     value = total_frames / (ms_step * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
 
+    # ---- phase split of one resident step (every rank runs it: update_step contains the all-reduce)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    for s in range(0, n, ENC_CHUNK):
+        enc.forward_u8(rgb[s:s + ENC_CHUNK], route[s:s + ENC_CHUNK], meas[s:s + ENC_CHUNK], feats[s:s + ENC_CHUNK])
+    ev[1].record()
+    scatter_features()
+    pool.compute_returns(next_values)
+    ev[2].record()
+    n_upd = learner.learn(pool, PPO_EPOCH)
+    ev[3].record()
+    torch.cuda.synchronize()
+    phase = {"encoder_ms": round(ev[0].elapsed_time(ev[1]), 3), "scatter_gae_ms": round(ev[1].elapsed_time(ev[2]), 3),
+             "ppo_update_ms": round(ev[2].elapsed_time(ev[3]), 3), "update_steps": n_upd,
+             "encoder_frames_per_s": round(n / (ev[0].elapsed_time(ev[1]) * 1e-3)),
+             "ppo_samples_per_s": round(WORKERS * T * PPO_EPOCH / (ev[2].elapsed_time(ev[3]) * 1e-3))}
+
     # ---- per-kernel view (rank 0): encoder launches timed with CUDA events inside the library
-    roofline, kernels, phase = None, None, None
+    roofline, kernels = None, None
     if rank == 0:
         tf_peak, hbm_peak, peak_src = measured_peaks()
         enc.forward_u8(rgb[:ENC_CHUNK], route[:ENC_CHUNK], meas[:ENC_CHUNK], feats[:ENC_CHUNK])
@@ -331,27 +348,11 @@ def run_cadre(args):
         tot_ms = sum(k["ms"] for k in conv)
         tot_fl = sum(fl[k["name"]] for k in conv) * ENC_CHUNK
         ach = tot_fl / (tot_ms * 1e-3) / 1e12
-        roofline = {"kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv / linear launches of one encoder forward, "
+        roofline = {"kernel": "tcgen05 tile kernels (implicit-GEMM conv / linear launches of one encoder forward, "
                               f"{len(conv)} launches, batch {ENC_CHUNK})",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": round(ach / tf_peak, 4), "traffic": None, "peak_source": peak_src + " (sustained bf16)",
                     "share_of_encoder_ms": round(tot_ms / sum(k["ms"] for k in kernels), 3)}
-        # phase split of one resident step
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        for s in range(0, n, ENC_CHUNK):
-            enc.forward_u8(rgb[s:s + ENC_CHUNK], route[s:s + ENC_CHUNK], meas[s:s + ENC_CHUNK], feats[s:s + ENC_CHUNK])
-        ev[1].record()
-        scatter_features()
-        pool.compute_returns(next_values)
-        ev[2].record()
-        n_upd = learner.learn(pool, PPO_EPOCH)
-        ev[3].record()
-        torch.cuda.synchronize()
-        phase = {"encoder_ms": round(ev[0].elapsed_time(ev[1]), 3), "scatter_gae_ms": round(ev[1].elapsed_time(ev[2]), 3),
-                 "ppo_update_ms": round(ev[2].elapsed_time(ev[3]), 3), "update_steps": n_upd,
-                 "encoder_frames_per_s": round(n / (ev[0].elapsed_time(ev[1]) * 1e-3)),
-                 "ppo_samples_per_s": round(WORKERS * T * PPO_EPOCH / (ev[2].elapsed_time(ev[3]) * 1e-3))}
         launches = (n // ENC_CHUNK) * enc.launches_per_forward + 1 + n_upd * (learner.engine.launches + 3)
         cpu_val, cpu_detail = cpu_reference_rate(64, 64, os.cpu_count() or 1)
         line = {

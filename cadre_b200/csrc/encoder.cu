@@ -7,6 +7,7 @@
 #include "../../include/cadre_b200.h"
 #include "internal.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,7 +17,7 @@ namespace cadre {
 void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
                        int B, cudaStream_t stream);
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
-void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C,
+void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
                     cudaStream_t stream);
 void launch_pam(const enc_t* x, enc_t* out, const float* wqk, const float* bqk,
                 const float* wv, const float* bv, float gamma, int B, int ldin, int num_sms,
@@ -34,6 +35,8 @@ struct Encoder {
   enc_t* padded = nullptr;   // [Bmax][75][262][8]
   enc_t* stem = nullptr;     // [Bmax][72][128][64]
   enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
+  enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
+  bool use_flat = true;
   enc_t* head5 = nullptr;    // [Bmax][40][256]
   enc_t* sa = nullptr;       // [Bmax][40][128]
   enc_t* sc = nullptr;
@@ -78,6 +81,8 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   e->padded = dev_alloc<enc_t>(B * 75 * 262 * 8, true);  // zero borders = conv padding
   e->stem = dev_alloc<enc_t>(B * 72 * 128 * 64, false);
   for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
+  for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
+  e->use_flat = getenv("CADRE_NO_FLAT") == nullptr;
   e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
   e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sc = dev_alloc<enc_t>(B * 40 * 128, false);
@@ -93,6 +98,7 @@ static void encoder_destroy(Encoder* e) {
   if (!e) return;
   cudaFree(e->padded), cudaFree(e->stem);
   for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
   cudaFree(e->head5), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
   cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max);
   delete e;
@@ -100,8 +106,9 @@ static void encoder_destroy(Encoder* e) {
 
 static void conv(Encoder* e, int idx, const enc_t* in, int B, int H, int W, int Cin, int Cout, int k,
                  int stride, int pad, const enc_t* res, int act, enc_t* out,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool in_pad = false) {
   ConvArgs a;
+  a.in_pad = in_pad ? 1 : 0;
   a.in = in, a.B = B, a.Hin = H, a.Win = W, a.Cin = Cin;
   a.w = static_cast<const enc_t*>(e->w.conv_w[idx]);
   a.bias = e->w.conv_b[idx];
@@ -121,26 +128,48 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
   st.in = e->padded, st.B = B, st.w = static_cast<const enc_t*>(e->w.stem_w), st.bias = e->w.stem_b;
   st.out = e->stem;
   launch_stem(st, s), step(e, s, n, "stem");
-  launch_maxpool(e->stem, e->act[0], B, 72, 128, 64, s), step(e, s, n, "maxpool");
+  launch_maxpool(e->stem, e->use_flat ? e->padact[0] : e->act[0], B, 72, 128, 64, e->use_flat ? 1 : 0, s);
+  step(e, s, n, "maxpool");
 
   // ResNet-18 BasicBlocks (resnet.py:39-55, 116-119); conv indices follow execution order
   int cur = 0, ci = 0, H = 36, W = 64, C = 64;
   const int planes[4] = {64, 128, 256, 512};
-  for (int li = 0; li < 4; ++li) {
+  const enc_t* padded_in = nullptr;  // layer1 output in zero-bordered layout (input of layer2.0)
+  if (e->use_flat) {
+    // layer1 (4 convs 64->64, 3x3/s1) through the halo-reuse kernel on zero-bordered buffers
+    enc_t* x = e->padact[0];
+    enc_t* t = e->padact[1];
+    enc_t* o = e->padact[2];
+    for (int bi = 0; bi < 2; ++bi) {
+      FlatArgs f;
+      f.B = B, f.H = 36, f.W = 64, f.act = 1;
+      f.in = x, f.w = static_cast<const enc_t*>(e->w.conv_w[ci]), f.bias = e->w.conv_b[ci], f.out = t;
+      launch_flat3x3(f, s), ++ci;
+      step(e, s, n, (std::string("layer1.") + std::to_string(bi) + ".conv1").c_str());
+      f.in = t, f.w = static_cast<const enc_t*>(e->w.conv_w[ci]), f.bias = e->w.conv_b[ci], f.out = o, f.res = x;
+      launch_flat3x3(f, s), ++ci;
+      step(e, s, n, (std::string("layer1.") + std::to_string(bi) + ".conv2").c_str());
+      enc_t* tmp = x;
+      x = o, o = tmp;
+    }
+    padded_in = x;
+  }
+  for (int li = e->use_flat ? 1 : 0; li < 4; ++li) {
     for (int bi = 0; bi < 2; ++bi) {
       const int stride = (li > 0 && bi == 0) ? 2 : 1;
       const int Cout = planes[li];
       const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-      enc_t* x = e->act[cur];
+      const bool from_pad = (padded_in != nullptr && li == 1 && bi == 0);
+      const enc_t* x = from_pad ? padded_in : e->act[cur];
       enc_t* t = e->act[(cur + 1) & 3];
       enc_t* ds = e->act[(cur + 2) & 3];
       enc_t* o = e->act[(cur + 3) & 3];
-      conv(e, ci++, x, B, H, W, C, Cout, 3, stride, 1, nullptr, 1, t, s);
+      conv(e, ci++, x, B, H, W, C, Cout, 3, stride, 1, nullptr, 1, t, s, from_pad);
       step(e, s, n, (std::string("layer") + std::to_string(li + 1) + "." + std::to_string(bi) + ".conv1").c_str());
       const enc_t* idn = x;
       const int conv2_idx = ci++;
       if (stride == 2) {
-        conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s);
+        conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s, from_pad);
         step(e, s, n, (std::string("layer") + std::to_string(li + 1) + ".0.downsample").c_str());
         idn = ds;
       }

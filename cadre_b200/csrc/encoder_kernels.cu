@@ -108,7 +108,7 @@ void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream) {
 // MaxPool2d(3, stride 2, padding 1) on NHWC bf16 (resnet.py:172): [B,72,128,64] -> [B,36,64,64].
 // One thread = one output pixel x 8 channels (16 B); inputs are post-ReLU so padding never wins.
 __global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__ out, int B,
-                               int Hin, int Win, int C) {
+                               int Hin, int Win, int C, int out_pad) {
   const int Hout = Hin / 2, Wout = Win / 2, CV = C / 8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Hout * Wout * CV;
@@ -138,14 +138,16 @@ __global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__
   enc_t o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = enc_from_float(m[i]);
-  *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Hout + oh) * Wout + ow) * C + cv * 8) =
-      *reinterpret_cast<const uint4*>(o);
+  // out_pad: the output carries a 1-pixel zero border ([B][Hout+2][Wout+2][C]) for the halo-reuse convs
+  const long long opix = (static_cast<long long>(n) * (Hout + 2 * out_pad) + oh + out_pad) * (Wout + 2 * out_pad) +
+                         ow + out_pad;
+  *reinterpret_cast<uint4*>(out + opix * C + cv * 8) = *reinterpret_cast<const uint4*>(o);
 }
 
-void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C,
+void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
                     cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2) * (C / 8);
-  maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, B, Hin, Win, C);
+  maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, B, Hin, Win, C, out_pad);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -104,8 +104,21 @@ struct ConvArgs {
   int res_after_act = 0;
   int act = 0;
   enc_t* out = nullptr;  // [B][Hout][Wout][Cout]
+  int in_pad = 0;        // input tensor is [B][Hin+2][Win+2][Cin] with a zero border (Hin/Win stay logical)
 };
 void launch_conv(const ConvArgs& a, cudaStream_t stream);
+
+// Halo-reuse 3x3/s1/p1 64->64 convolution on zero-bordered activations [B][H+2][W+2][64] (tc_flat3x3.cuh)
+struct FlatArgs {
+  const enc_t* in = nullptr;
+  int B = 0, H = 0, W = 0;
+  const enc_t* w = nullptr;   // [64][3][3][64]
+  const float* bias = nullptr;
+  const enc_t* res = nullptr; // zero-bordered, same shape as out
+  int act = 0;
+  enc_t* out = nullptr;
+};
+void launch_flat3x3(const FlatArgs& a, cudaStream_t stream);
 
 // 7x7/s2/p3 stem over the padded 4-channel bf16 image [B][150][262][4]; weights [64][256] (K = 4 row pairs x
 // 2 rows x 8 pixels x 4 ch, zero where kh==7 or kw==7); output [B][72][128][64].

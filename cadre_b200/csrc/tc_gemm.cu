@@ -1,6 +1,8 @@
 // Host side of the tcgen05 tile kernel: TMA tensor-map construction and template dispatch.
 #include "internal.h"
 #include "tc_gemm.cuh"
+#include "tc_flat3x3.cuh"
+#include "tc_persist.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -89,6 +91,32 @@ static void launch_inst(const TcGemmParams& p, dim3 grid, cudaStream_t stream) {
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    CADRE_CUDA_CHECK(cudaGetDevice(&dev));
+    CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+static const bool g_use_v1 = getenv("CADRE_CONV_V1") != nullptr;  // A/B switch: non-persistent encoder kernels
+
+template <int BN, int STAGES, int MODE>
+static void launch_persist(const PersistParams& p, cudaStream_t stream) {
+  auto kern = tc_persist_kernel<BN, STAGES, MODE>;
+  constexpr int smem = PersistSmem<BN, STAGES>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 192, smem, stream>>>(p);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
 static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
   p.out = a.out, p.ldc = a.ldc, p.out_bs = a.out_bs;
   p.bias = a.bias, p.bias_bs = a.bias_bs;
@@ -108,6 +136,31 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const int es = a.kind ? 4 : 2;
   const int bk = 128 / es;
   int bn = a.block_n ? a.block_n : (a.N <= 64 ? 64 : 128);
+  if (!g_use_v1 && a.kind == 0 && !a.a_mn && !a.b_mn && a.batch == 1 && !a.out_f32 && a.epi == 0 && !a.mask &&
+      !a.batch_rows && a.alpha == 1.f && a.N % 8 == 0) {
+    PersistParams q;
+    memset(&q, 0, sizeof(q));
+    bn = a.N <= 64 ? 64 : 128;
+    make_operand_map(&q.tmA[0], 2, false, a.A, a.lda, 0, a.M, a.K, 1, 128);
+    make_operand_map(&q.tmB, 2, false, a.B, a.ldb, 0, a.N, a.K, 1, bn);
+    {
+      const uint64_t dims[3] = {(uint64_t)a.N, (uint64_t)a.M, 1};
+      const uint64_t str[2] = {(uint64_t)a.ldc * 2, (uint64_t)a.ldc * 2 * a.M};
+      const uint32_t box[3] = {64, 128, 1};
+      make_map(&q.tmOut, 2, 3, a.out, dims, str, box);
+    }
+    q.num_kb = (a.K + 63) / 64;
+    q.tiles_m = (a.M + 127) / 128, q.tiles_n = (a.N + bn - 1) / bn;
+    q.M = a.M, q.N = a.N;
+    q.bias = a.bias, q.res = static_cast<const enc_t*>(a.res), q.ldr = a.ldr;
+    q.res_after_act = a.res_after_act, q.act = a.act;
+    CADRE_REQUIRE(a.bias != nullptr, "persistent gemm needs a bias vector");
+    if (bn == 64)
+      launch_persist<64, 6, MODE_GEMM>(q, stream);
+    else
+      launch_persist<128, 5, MODE_GEMM>(q, stream);
+    return;
+  }
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
   make_operand_map(&p.tmA[0], es, a.a_mn, a.A, a.lda, a.a_bs, a.M, a.K, a.batch, 128);
@@ -146,6 +199,8 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   const int Hout = (a.Hin + 2 * a.pad - a.KH) / a.stride + 1;
   const int Wout = (a.Win + 2 * a.pad - a.KW) / a.stride + 1;
   CADRE_REQUIRE(Wout <= 128 && 128 % Wout == 0, "conv output width must divide 128");
+  // zero-bordered input: same taps, shifted by one pixel, on a (Hin+2) x (Win+2) tensor
+  const int Hs = a.Hin + 2 * a.in_pad, Ws = a.Win + 2 * a.in_pad, pad_eff = a.pad - a.in_pad;
   const int rows_per_tile = 128 / Wout;
   int TH = 1;
   while (TH * 2 <= rows_per_tile && Hout % (TH * 2) == 0) TH *= 2;
@@ -158,26 +213,25 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   const uint32_t box[4] = {64u, static_cast<uint32_t>(Wout), static_cast<uint32_t>(TH),
                            static_cast<uint32_t>(TN)};
   if (a.stride == 1) {
-    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.Win, (uint64_t)a.Hin, (uint64_t)a.B};
-    const uint64_t str[3] = {a.Cin * es, (uint64_t)a.Win * a.Cin * es, (uint64_t)a.Hin * a.Win * a.Cin * es};
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)a.B};
+    const uint64_t str[3] = {a.Cin * es, (uint64_t)Ws * a.Cin * es, (uint64_t)Hs * Ws * a.Cin * es};
     make_map(&p.tmA[0], 2, 4, a.in, dims, str, box);
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
-        const int Hs = (a.Hin - ph + 1) / 2, Ws = (a.Win - pw + 1) / 2;
-        const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)a.B};
-        const uint64_t str[3] = {2 * a.Cin * es, 2 * (uint64_t)a.Win * a.Cin * es,
-                                 (uint64_t)a.Hin * a.Win * a.Cin * es};
-        if (Hs > 0 && Ws > 0)
-          make_map(&p.tmA[ph * 2 + pw], 2, 4, a.in + ((long long)ph * a.Win + pw) * a.Cin, dims, str, box);
+        const int Hq = (Hs - ph + 1) / 2, Wq = (Ws - pw + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)a.B};
+        const uint64_t str[3] = {2 * a.Cin * es, 2 * (uint64_t)Ws * a.Cin * es, (uint64_t)Hs * Ws * a.Cin * es};
+        if (Hq > 0 && Wq > 0)
+          make_map(&p.tmA[ph * 2 + pw], 2, 4, a.in + ((long long)ph * Ws + pw) * a.Cin, dims, str, box);
       }
   }
   int nt = 0;
   for (int kh = 0; kh < a.KH; ++kh)
     for (int kw = 0; kw < a.KW; ++kw) {
       ConvTap t;
-      const int oh = kh - a.pad, ow = kw - a.pad;
+      const int oh = kh - pad_eff, ow = kw - pad_eff;
       if (a.stride == 1) {
         t.map = 0, t.dh = (short)oh, t.dw = (short)ow;
       } else {
@@ -201,10 +255,64 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.res = a.res, p.ldr = a.Cout, p.res_after_act = a.res_after_act;
   p.act = a.act, p.alpha = 1.f;
   dim3 grid((Hout / TH) * ((a.B + TN - 1) / TN), (a.Cout + bn - 1) / bn, 1);
+  if (!g_use_v1) {
+    PersistParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < 4; ++i) q.tmA[i] = p.tmA[i];
+    q.tmB = p.tmB;
+    {
+      const uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)a.B};
+      const uint64_t str[3] = {(uint64_t)a.Cout * es, (uint64_t)Wout * a.Cout * es,
+                               (uint64_t)Hout * Wout * a.Cout * es};
+      make_map(&q.tmOut, 2, 4, a.out, dims, str, box);
+    }
+    q.num_kb = p.num_kb, q.ntaps = p.ntaps, q.cin_chunks = p.cin_chunks;
+    q.Hout = Hout, q.Wout = Wout, q.TH = TH, q.TN = TN, q.Bimg = a.B;
+    for (int i = 0; i < 12; ++i) q.taps[i] = p.taps[i];
+    q.tiles_m = grid.x, q.tiles_n = grid.y;
+    q.N = a.Cout;
+    q.bias = a.bias, q.res = a.res, q.ldr = a.Cout, q.res_after_act = a.res_after_act, q.act = a.act;
+    if (bn == 64)
+      launch_persist<64, 6, MODE_CONV>(q, stream);
+    else
+      launch_persist<128, 5, MODE_CONV>(q, stream);
+    return;
+  }
   if (bn == 64)
     launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
   else
     launch_inst<0, 0, 0, 128, 3, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
+  CADRE_REQUIRE(a.W + 2 <= 67, "flat3x3 window is sized for W <= 65");
+  FlatParams p;
+  memset(&p, 0, sizeof(p));
+  const int PW = a.W + 2;
+  const long long P = static_cast<long long>(a.B) * (a.H + 2) * PW;
+  CADRE_REQUIRE(P < (1LL << 31) - 1024, "flat3x3: too many pixels");
+  const uint64_t dims[2] = {64, (uint64_t)P};
+  const uint64_t str[1] = {128};
+  const uint32_t box_a[2] = {64, (uint32_t)FLAT_WIN_A}, box_b[2] = {64, 128};
+  make_map(&p.tmX, 2, 2, a.in, dims, str, box_a);
+  make_map(&p.tmX2, 2, 2, a.in, dims, str, box_b);
+  make_map(&p.tmY, 2, 2, a.out, dims, str, box_b);
+  const uint64_t wdims[2] = {576, 64};
+  const uint64_t wstr[1] = {576 * 2};
+  const uint32_t wbox[2] = {64, 64};
+  make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox);
+  p.P = static_cast<int>(P), p.H = a.H, p.W = a.W, p.PW = PW;
+  p.num_tiles = static_cast<int>((P + 127) / 128);
+  p.bias = a.bias, p.res = a.res, p.act = a.act;
+  static bool configured = false;
+  if (!configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  tc_flat3x3_kernel<<<grid, 192, FLAT_SMEM, stream>>>(p);
+  CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -228,6 +336,22 @@ void launch_stem(const StemArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.act = ACT_RELU, p.alpha = 1.f;
   dim3 grid(72 * a.B, 1, 1);
+  if (!g_use_v1) {
+    PersistParams q;
+    memset(&q, 0, sizeof(q));
+    q.tmA[0] = p.tmA[0], q.tmB = p.tmB;
+    {
+      const uint64_t odims[4] = {64, 128, 72, (uint64_t)a.B};
+      const uint64_t ostr[3] = {64 * 2, 128 * 64 * 2, 72 * 128 * 64 * 2};
+      const uint32_t obox[4] = {64, 128, 1, 1};
+      make_map(&q.tmOut, 2, 4, a.out, odims, ostr, obox);
+    }
+    q.num_kb = 4, q.Hout = 72, q.Wout = 128, q.TH = 1, q.TN = 1, q.Bimg = a.B;
+    q.tiles_m = grid.x, q.tiles_n = 1, q.N = 64;
+    q.bias = a.bias, q.act = ACT_RELU;
+    launch_persist<64, 6, MODE_STEM>(q, stream);
+    return;
+  }
   launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, enc_t>(p, grid, stream);
 }
 

@@ -1,0 +1,285 @@
+// Persistent, software-pipelined variant of the tcgen05 tile kernel for the encoder (fp16 in / fp16 out):
+//   * one CTA per SM walks output tiles (m fastest, so a weight tile stays hot in L2);
+//   * warp 0 = TMA producer running up to STAGES k-blocks ahead ACROSS tiles,
+//     warp 1 = tcgen05.mma issuer alternating between two TMEM accumulators,
+//     warps 2..5 = epilogue: residual row prefetched before the accumulator is ready, tcgen05.ld, bias /
+//     residual / activation, fp16 pack into a 128B-swizzled staging tile, one TMA store per 64 channels;
+//   * the epilogue of tile i overlaps the main loop of tile i+1 (double-buffered TMEM, mbarrier hand-off).
+// Modes as in tc_gemm.cuh (GEMM / implicit-GEMM conv / stem).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace cadre {
+
+struct PersistParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  CUtensorMap tmOut;
+  int num_kb;
+  int ntaps, cin_chunks, Hout, Wout, TH, TN, Bimg;
+  ConvTap taps[12];
+  int tiles_m, tiles_n;
+  int M, N;                 // logical output rows (GEMM mode) / channels
+  const float* bias;
+  const enc_t* res;         // residual, same layout as the output (row stride ldr elements)
+  long long ldr;
+  int res_after_act, act;
+  int out_pad;              // output (and residual) tensors carry a 1-pixel zero border: [B][H+2][W+2][C]
+};
+
+template <int BLOCK_N, int STAGES>
+struct PersistSmem {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = (BLOCK_N / 64) * 128 * 128;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BLOCK_N, int STAGES, int MODE>
+__global__ void __launch_bounds__(192, 1) tc_persist_kernel(const __grid_constant__ PersistParams p) {
+  constexpr int BK = 64, UMMA_K = 16, NCH = BLOCK_N / 64;
+  using S = PersistSmem<BLOCK_N, STAGES>;
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* out_s = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_s + S::OUT_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512 columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int tile, int& m_tile, int& n0, int& img0, int& h0) {
+    const int n_tile = tile / p.tiles_m;
+    m_tile = tile - n_tile * p.tiles_m;
+    n0 = n_tile * BLOCK_N;
+    img0 = 0, h0 = 0;
+    if constexpr (MODE != MODE_GEMM) {
+      const int tiles_h = p.Hout / p.TH;
+      img0 = (m_tile / tiles_h) * p.TN;
+      h0 = (m_tile % tiles_h) * p.TH;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int it = 0;  // global k-block counter across tiles
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_tile, n0, img0, h0;
+      tile_origin(tile, m_tile, n0, img0, h0);
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], S::STAGE_BYTES);
+        uint8_t* a_s = smem + s * S::STAGE_BYTES;
+        uint8_t* b_s = a_s + S::A_BYTES;
+        if constexpr (MODE == MODE_GEMM) {
+          tma_load_3d(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
+        } else if constexpr (MODE == MODE_CONV) {
+          const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+          const ConvTap t = p.taps[tap];
+          tma_load_4d(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
+        } else {
+          tma_load_4d(a_s, &p.tmA[0], &full[s], 0, 0, h0 + kb, img0);
+        }
+        tma_load_3d(b_s, &p.tmB, &full[s], kb * BK, n0, 0);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, BLOCK_N);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(&tempty[as], aph ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+          const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
+          tc_mma_f16(tacc, da, db, idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(&tfull[as]);
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      int m_tile, n0, img0, h0;
+      tile_origin(tile, m_tile, n0, img0, h0);
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      // row -> residual row index (same layout as the output)
+      long long out_row;
+      bool row_ok;
+      if constexpr (MODE == MODE_GEMM) {
+        out_row = static_cast<long long>(m_tile) * 128 + row;
+        row_ok = out_row < p.M;
+      } else {
+        const int w = row % p.Wout;
+        const int hh = (row / p.Wout) % p.TH;
+        const int im = row / (p.Wout * p.TH);
+        const int img = img0 + im, h = h0 + hh;
+        row_ok = img < p.Bimg;
+        if (p.out_pad)
+          out_row = (static_cast<long long>(img) * (p.Hout + 2) + h + 1) * (p.Wout + 2) + w + 1;
+        else
+          out_row = (static_cast<long long>(img) * p.Hout + h) * p.Wout + w;
+      }
+      // prefetch this thread's residual row while the MMAs of the tile are still in flight
+      uint4 rres[BLOCK_N / 8];
+      const bool has_res = p.res != nullptr;
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_row * p.ldr + n0);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 8; ++j) rres[j] = row_ok ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
+      // staging buffer must have been read by the previous tile's TMA store
+      if (leader) tma_store_wait_read();
+      epi_bar_sync();
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {  // accumulator fully in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+        const int nb = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]);
+          if (nb + i < p.N) x += p.bias[nb + i];
+          v[i] = x;
+        }
+        if (has_res && !p.res_after_act) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] += enc_to_float(h8[i]);
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+        }
+        if (has_res && p.res_after_act) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * j + i] += enc_to_float(h8[i]);
+          }
+        }
+        // 32 columns = 4 x 16-byte chunks of this row inside 64-channel group g; 128B swizzle: chunk ^= row & 7
+        const int g = c >> 1;
+        uint8_t* rowp = out_s + g * (128 * 128) + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = (c & 1) * 4 + j;
+          uint4 u;
+          u.x = enc_pack2(v[8 * j + 0], v[8 * j + 1]);
+          u.y = enc_pack2(v[8 * j + 2], v[8 * j + 3]);
+          u.z = enc_pack2(v[8 * j + 4], v[8 * j + 5]);
+          u.w = enc_pack2(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (leader) {
+#pragma unroll
+        for (int g = 0; g < NCH; ++g) {
+          if (n0 + g * 64 < p.N) {
+            if constexpr (MODE == MODE_GEMM)
+              tma_store_3d(&p.tmOut, out_s + g * (128 * 128), n0 + g * 64, m_tile * 128, 0);
+            else
+              tma_store_4d(&p.tmOut, out_s + g * (128 * 128), n0 + g * 64, p.out_pad, h0 + p.out_pad, img0);
+          }
+        }
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace cadre

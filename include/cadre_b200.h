@@ -65,10 +65,16 @@ typedef struct cadre_gemm_args {
 int cadre_gemm(const cadre_gemm_args* args, void* stream);
 
 /* NHWC enc16 implicit-GEMM convolution with folded BatchNorm bias, optional residual and ReLU
- * (resnet.py:39-55 BasicBlock, danet.py:21-36 conv5a/5c/51/52, danet.py:41 conv8). */
+ * (resnet.py:39-55 BasicBlock, danet.py:21-36 conv5a/5c/51/52, danet.py:41 conv8). in_pad = 1: the input tensor is
+ * stored with a 1-pixel zero border, [B][Hin+2][Win+2][Cin] (Hin / Win stay the logical sizes). */
 int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const void* w, int Cout, int KH,
                       int KW, int stride, int pad, const float* bias, const void* res, int res_after_act,
-                      int act, void* out, void* stream);
+                      int act, void* out, int in_pad, void* stream);
+
+/* Halo-reuse 3x3 / stride 1 / pad 1 convolution, 64 -> 64 channels (ResNet layer1), on zero-bordered
+ * activations: in / res / out are [B][H+2][W+2][64] enc16 with zero borders (kept zero by the kernel). */
+int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
+                         int act, void* out, void* stream);
 
 /* ResNet stem conv7x7/s2/p3 + folded BN + ReLU over the padded 4-channel image written by
  * cadre_preprocess (resnet.py:169-171). */

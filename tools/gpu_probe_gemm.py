@@ -116,7 +116,7 @@ def run_conv(B, H, W, Cin, Cout, k, stride, pad, act=1, res=False, name=""):
     r = torch.randn(B, Ho, Wo, Cout, device=dev).to(ENC16) if res else None
     out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=ENC16)
     rc = L.cadre_conv2d_nhwc(_lib.ptr(x_nhwc), B, H, W, Cin, _lib.ptr(w_k), Cout, k, k, stride, pad,
-                             _lib.ptr(bias), _lib.ptr(r), 0, act, _lib.ptr(out), _lib.stream_ptr())
+                             _lib.ptr(bias), _lib.ptr(r), 0, act, _lib.ptr(out), 0, _lib.stream_ptr())
     if rc != 0:
         print(f"FAIL {name}: rc={rc} {L.cadre_last_error().decode()}", flush=True)
         return False
@@ -126,6 +126,56 @@ def run_conv(B, H, W, Cin, Cout, k, stride, pad, act=1, res=False, name=""):
         ref = ref + r.float().permute(0, 3, 1, 2)
     if act == 1:
         ref = ref.relu()
+    return report(name, out.float().permute(0, 3, 1, 2), ref, 1e-2)
+
+
+def run_flat(B, H, W, res=False, name=""):
+    x = torch.randn(B, 64, H, W, device=dev).to(ENC16)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24.0).to(ENC16)
+    bias = torch.randn(64, device=dev)
+    xp = torch.zeros(B, H + 2, W + 2, 64, device=dev, dtype=ENC16)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    w_k = w.permute(0, 2, 3, 1).contiguous().view(64, -1)
+    rp = None
+    if res:
+        r = torch.randn(B, 64, H, W, device=dev).to(ENC16)
+        rp = torch.zeros_like(xp)
+        rp[:, 1:-1, 1:-1] = r.permute(0, 2, 3, 1)
+    out = torch.full((B, H + 2, W + 2, 64), 7.0, device=dev, dtype=ENC16)
+    rc = L.cadre_conv3x3_flat64(_lib.ptr(xp), B, H, W, _lib.ptr(w_k), _lib.ptr(bias), _lib.ptr(rp), 1, _lib.ptr(out),
+                                _lib.stream_ptr())
+    if rc != 0:
+        print(f"FAIL {name}: rc={rc} {L.cadre_last_error().decode()}", flush=True)
+        return False
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w.float(), bias, stride=1, padding=1)
+    if res:
+        ref = ref + r.float()
+    ref = ref.relu()
+    border = out.float().clone()
+    border[:, 1:-1, 1:-1] = 0
+    ok = report(name, out[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), ref, 1e-2)
+    print(f"     border max |y| = {border.abs().max().item():.3e} (must be 0)", flush=True)
+    return ok
+
+
+def run_conv_inpad(B, H, W, Cin, Cout, k, stride, pad, name=""):
+    x = torch.randn(B, Cin, H, W, device=dev).to(ENC16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5).to(ENC16)
+    bias = torch.randn(Cout, device=dev)
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    xp = torch.zeros(B, H + 2, W + 2, Cin, device=dev, dtype=ENC16)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    w_k = w.permute(0, 2, 3, 1).contiguous().view(Cout, -1)
+    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=ENC16)
+    rc = L.cadre_conv2d_nhwc(_lib.ptr(xp), B, H, W, Cin, _lib.ptr(w_k), Cout, k, k, stride, pad, _lib.ptr(bias), None, 0,
+                             1, _lib.ptr(out), 1, _lib.stream_ptr())
+    if rc != 0:
+        print(f"FAIL {name}: rc={rc} {L.cadre_last_error().decode()}", flush=True)
+        return False
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=pad).relu()
     return report(name, out.float().permute(0, 3, 1, 2), ref, 1e-2)
 
 
@@ -173,6 +223,13 @@ def main():
         conv_cases()
     if group in ("all", "stem"):
         run_stem(2)
+        run_stem(5, name="stem B=5")
+    if group in ("all", "flat"):
+        run_flat(1, 36, 64, name="flat3x3 B=1")
+        run_flat(3, 36, 64, res=True, name="flat3x3 B=3 +res")
+        run_flat(37, 36, 64, res=True, name="flat3x3 B=37 +res")
+        run_conv_inpad(3, 36, 64, 64, 128, 3, 2, 1, name="conv3x3 s2 from padded input")
+        run_conv_inpad(3, 36, 64, 64, 128, 1, 2, 0, name="conv1x1 s2 from padded input")
     if group in ("all", "perf"):
         perf_cases()
 
@@ -229,7 +286,7 @@ def perf_cases():
     out = torch.empty(B, 36, 64, 64, device=dev, dtype=ENC16)
     sp = _lib.stream_ptr()
     ms = timed(lambda: L.cadre_conv2d_nhwc(_lib.ptr(x), B, 36, 64, 64, _lib.ptr(w), 64, 3, 3, 1, 1, _lib.ptr(bias),
-                                           None, 0, 1, _lib.ptr(out), sp))
+                                           None, 0, 1, _lib.ptr(out), 0, sp))
     fl = 2 * B * 36 * 64 * 64 * 576
     print(f"perf conv3x3 layer1 B={B}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
     x4 = torch.randn(B, 5, 8, 512, device=dev).to(ENC16)
@@ -237,7 +294,7 @@ def perf_cases():
     b4 = torch.randn(512, device=dev)
     o4 = torch.empty(B, 5, 8, 512, device=dev, dtype=ENC16)
     ms = timed(lambda: L.cadre_conv2d_nhwc(_lib.ptr(x4), B, 5, 8, 512, _lib.ptr(w4), 512, 3, 3, 1, 1, _lib.ptr(b4),
-                                           None, 0, 1, _lib.ptr(o4), sp))
+                                           None, 0, 1, _lib.ptr(o4), 0, sp))
     fl = 2 * B * 40 * 512 * 4608
     print(f"perf conv3x3 layer4 B={B}: {ms:.3f} ms = {fl/ms/1e9:.1f} TFLOP/s", flush=True)
 

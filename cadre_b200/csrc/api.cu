@@ -48,6 +48,8 @@ int cadre_gemm(const cadre_gemm_args* s, void* stream) {
   a.mask = s->mask, a.ldm = s->ldm, a.mask_bs = s->mask_bs;
   a.batch_rows = s->batch_rows, a.rows_is_k = s->rows_is_k;
   a.alpha = s->alpha, a.epi = s->epi;
+  if (getenv("CADRE_DBG_CLK")) a.dbg_clk = reinterpret_cast<long long*>(strtoull(getenv("CADRE_DBG_CLK"), nullptr, 0));
+  if (getenv("CADRE_DBG_EPI")) a.dbg_epi = atoi(getenv("CADRE_DBG_EPI"));
   if (getenv("CADRE_DBG_A_SHIFT")) a.dbg_a_shift = atoi(getenv("CADRE_DBG_A_SHIFT"));
   if (getenv("CADRE_DBG_BASE_OFFSET")) a.dbg_base_offset = atoi(getenv("CADRE_DBG_BASE_OFFSET"));
   a.xpart = s->xpart, a.c_prev = s->c_prev, a.c_out = s->c_out, a.h_out = s->h_out;

@@ -19,9 +19,8 @@ void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
 void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
                     cudaStream_t stream);
-void launch_pam(const enc_t* x, enc_t* out, const float* wqk, const float* bqk,
-                const float* wv, const float* bv, float gamma, int B, int ldin, int num_sms,
-                cudaStream_t stream);
+void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, const float* bqk, float gamma,
+                int B, int ldin, int num_sms, cudaStream_t stream);
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
                 cudaStream_t stream);
 void launch_intertask(const float* qkv, float* out, const double* meas, int B, int ld_out,
@@ -38,6 +37,7 @@ struct Encoder {
   enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
   bool use_flat = true;
   enc_t* head5 = nullptr;    // [Bmax][40][256]
+  enc_t* pam_v = nullptr;    // [Bmax][40][128] PAM value projection
   enc_t* sa = nullptr;       // [Bmax][40][128]
   enc_t* sc = nullptr;
   enc_t* sa_conv = nullptr;
@@ -84,6 +84,7 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
   e->use_flat = getenv("CADRE_NO_FLAT") == nullptr;
   e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
+  e->pam_v = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sc = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa_conv = dev_alloc<enc_t>(B * 40 * 128, false);
@@ -99,7 +100,7 @@ static void encoder_destroy(Encoder* e) {
   cudaFree(e->padded), cudaFree(e->stem);
   for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
   for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
-  cudaFree(e->head5), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
+  cudaFree(e->head5), cudaFree(e->pam_v), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
   cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max);
   delete e;
 }
@@ -189,8 +190,15 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     a.Cout = 256, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->head5;
     launch_conv(a, s), step(e, s, n, "conv5a|conv5c");
   }
-  launch_pam(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_wv, e->w.pam_bv, e->w.pam_gamma, B, 256,
-             e->num_sms, s), step(e, s, n, "pam");
+  {  // PAM value projection for the whole batch on the tensor cores: V[B*40,128] = feat1 Wv^T + bv
+    GemmArgs g;
+    g.kind = 0, g.A = e->head5, g.lda = 256, g.B = e->w.pam_wv, g.ldb = 128;
+    g.M = B * 40, g.N = 128, g.K = 128;
+    g.out = e->pam_v, g.ldc = 128, g.out_f32 = 0, g.bias = e->w.pam_bv;
+    launch_gemm(g, s), step(e, s, n, "pam.value_conv");
+  }
+  launch_pam(e->head5, e->pam_v, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_gamma, B, 256, e->num_sms, s);
+  step(e, s, n, "pam");
   launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), step(e, s, n, "cam");
   {
     ConvArgs a;

@@ -152,59 +152,64 @@ void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// PAM_Module.forward (danet_blocks/da_att.py:32-51) fused per frame: q,k = 1x1 conv 128->16, v = 1x1 conv
-// 128->128, energy = q^T k [40x40] (no scale), softmax over keys, out = v att^T, gamma*out + x.
-// One CTA (256 threads) walks frames; weights live in shared memory for the CTA's lifetime; the 40x40 map
-// never leaves the SM. x / out: NHWC bf16 [B][40][128]. Weights fp32: wqk [32][128] (q rows then k rows),
-// bqk [32], wv [128][128], bv [128].
-constexpr int PAM_P = 40, PAM_C = 128;
+// PAM_Module.forward (danet_blocks/da_att.py:32-51) fused per frame: q,k = 1x1 conv 128->16 (fp32), energy =
+// q^T k [40x40] (no scale), softmax over keys, out = v att^T, gamma*out + x. The value projection
+// v = Wv x + bv (80 % of the module's FLOPs, linear in the output) is done beforehand by the tcgen05 tile kernel
+// for the whole batch; q, k, the 40x40 map and the softmax stay in fp32 on CUDA cores and never leave the SM.
+// x: NHWC enc16 rows of `ldin` elements (first 128 channels used), v / out: enc16 [B][40][128].
+constexpr int PAM_P = 40, PAM_C = 128, PAM_LD = 132;
 struct PamSmem {
-  float wv[PAM_C][PAM_C + 1];
-  float wqk[32][PAM_C + 1];
-  float bv[PAM_C];
+  float wqk[32][PAM_LD];
   float bqk[32];
-  float x[PAM_P][PAM_C + 1];
-  float v[PAM_P][PAM_C + 1];
+  float x[PAM_P][PAM_LD];
+  float v[PAM_P][PAM_LD];
   float qk[PAM_P][33];
   float att[PAM_P][PAM_P + 1];
 };
 
-__global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin,
+__global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin, const enc_t* __restrict__ vin,
                                                   enc_t* __restrict__ out, const float* __restrict__ wqk,
-                                                  const float* __restrict__ bqk, const float* __restrict__ wv,
-                                                  const float* __restrict__ bv, float gamma, int B,
-                                                  int ldin) {
+                                                  const float* __restrict__ bqk, float gamma, int B, int ldin) {
   extern __shared__ uint8_t pam_raw[];
   PamSmem& s = *reinterpret_cast<PamSmem*>(pam_raw);
   const int tid = threadIdx.x;
-  for (int i = tid; i < PAM_C * PAM_C; i += 256) s.wv[i / PAM_C][i % PAM_C] = wv[i];
   for (int i = tid; i < 32 * PAM_C; i += 256) s.wqk[i / PAM_C][i % PAM_C] = wqk[i];
-  if (tid < PAM_C) s.bv[tid] = bv[tid];
   if (tid < 32) s.bqk[tid] = bqk[tid];
   for (int f = blockIdx.x; f < B; f += gridDim.x) {
     __syncthreads();
     const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
-    for (int i = tid; i < PAM_P * PAM_C; i += 256)
-      s.x[i / PAM_C][i % PAM_C] = enc_to_float(xf[(i / PAM_C) * ldin + (i % PAM_C)]);
-    __syncthreads();
-    // projections: v[p][c] (40x128 outputs) and qk[p][j] (40x32 outputs)
-    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
-      const int p = o / PAM_C, c = o % PAM_C;
-      float acc = s.bv[c];
-#pragma unroll 8
-      for (int k = 0; k < PAM_C; ++k) acc = fmaf(s.x[p][k], s.wv[c][k], acc);
-      s.v[p][c] = acc;
-    }
-    for (int o = tid; o < PAM_P * 32; o += 256) {
-      const int p = o / 32, j = o % 32;
-      float acc = s.bqk[j];
-#pragma unroll 8
-      for (int k = 0; k < PAM_C; ++k) acc = fmaf(s.x[p][k], s.wqk[j][k], acc);
-      s.qk[p][j] = acc;
+    const enc_t* vf = vin + static_cast<long long>(f) * PAM_P * PAM_C;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {  // 16-byte loads: 8 channels
+      const int p = i / (PAM_C / 8), c8 = (i % (PAM_C / 8)) * 8;
+      const uint4 ux = *reinterpret_cast<const uint4*>(xf + p * ldin + c8);
+      const uint4 uv = *reinterpret_cast<const uint4*>(vf + p * PAM_C + c8);
+      const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
+      const enc_t* hv = reinterpret_cast<const enc_t*>(&uv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s.x[p][c8 + k] = enc_to_float(hx[k]);
+        s.v[p][c8 + k] = enc_to_float(hv[k]);
+      }
     }
     __syncthreads();
-    // energy[i][j] = sum_d q[i][d] k[j][d]
-    for (int o = tid; o < PAM_P * PAM_P; o += 256) {
+    {  // qk[p][j]: thread = (j, group of 5 pixels), float4 along the 128 input channels
+      const int j = tid & 31, p0 = (tid >> 5) * 5;
+      float acc[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) acc[r] = s.bqk[j];
+      for (int k = 0; k < PAM_C; k += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&s.wqk[j][k]);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float4 xv = *reinterpret_cast<const float4*>(&s.x[p0 + r][k]);
+          acc[r] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[r]))));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 5; ++r) s.qk[p0 + r][j] = acc[r];
+    }
+    __syncthreads();
+    for (int o = tid; o < PAM_P * PAM_P; o += 256) {  // energy[i][j] = q_i . k_j
       const int i = o / PAM_P, j = o % PAM_P;
       float acc = 0.f;
 #pragma unroll
@@ -212,8 +217,7 @@ __global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin,
       s.att[i][j] = acc;
     }
     __syncthreads();
-    // row softmax: one warp per row
-    for (int i = tid >> 5; i < PAM_P; i += 8) {
+    for (int i = tid >> 5; i < PAM_P; i += 8) {  // row softmax: one warp per row
       const int l = tid & 31;
       const float e0 = s.att[i][l], e1 = (l + 32 < PAM_P) ? s.att[i][l + 32] : -INFINITY;
       float m = fmaxf(e0, e1);
@@ -225,46 +229,86 @@ __global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin,
       if (l + 32 < PAM_P) s.att[i][l + 32] = p1 / sum;
     }
     __syncthreads();
-    // out[i][c] = gamma * sum_j v[j][c] att[i][j] + x[i][c]
-    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
-    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
-      const int i = o / PAM_C, c = o % PAM_C;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < PAM_P; ++j) acc = fmaf(s.v[j][c], s.att[i][j], acc);
-      of[o] = enc_from_float(gamma * acc + s.x[i][c]);
+    {  // out[i][c] = gamma * sum_j att[i][j] v[j][c] + x[i][c]: thread = (4 channels, 5 pixels)
+      const int c0 = (tid & 31) * 4, i0 = (tid >> 5) * 5;
+      float acc[5][4];
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+      for (int j = 0; j < PAM_P; ++j) {
+        const float4 vv = *reinterpret_cast<const float4*>(&s.v[j][c0]);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float a = s.att[i0 + r][j];
+          acc[r][0] = fmaf(a, vv.x, acc[r][0]);
+          acc[r][1] = fmaf(a, vv.y, acc[r][1]);
+          acc[r][2] = fmaf(a, vv.z, acc[r][2]);
+          acc[r][3] = fmaf(a, vv.w, acc[r][3]);
+        }
+      }
+      enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        uint2 u;
+        u.x = enc_pack2(gamma * acc[r][0] + s.x[i0 + r][c0], gamma * acc[r][1] + s.x[i0 + r][c0 + 1]);
+        u.y = enc_pack2(gamma * acc[r][2] + s.x[i0 + r][c0 + 2], gamma * acc[r][3] + s.x[i0 + r][c0 + 3]);
+        *reinterpret_cast<uint2*>(of + (i0 + r) * PAM_C + c0) = u;
+      }
     }
   }
 }
 
 // CAM_Module.forward (da_att.py:63-83) fused per frame: energy = X X^T [128x128] over the 40 positions,
-// softmax(rowmax - energy), out = att X, gamma*out + x.
+// softmax(rowmax - energy), out = att X, gamma*out + x. Register-tiled fp32 (8x8 gram tiles, 4x5 output tiles).
 struct CamSmem {
-  float x[PAM_P][PAM_C + 1];          // x[p][c]
-  float att[PAM_C][PAM_C + 1];
+  float x[PAM_P][PAM_LD];   // x[p][c]
+  float att[PAM_C][PAM_LD];
 };
 
-__global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
-                                                  enc_t* __restrict__ out, float gamma, int B,
-                                                  int ldin) {
+__global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin, enc_t* __restrict__ out,
+                                                  float gamma, int B, int ldin) {
   extern __shared__ uint8_t cam_raw[];
   CamSmem& s = *reinterpret_cast<CamSmem*>(cam_raw);
   const int tid = threadIdx.x;
   for (int f = blockIdx.x; f < B; f += gridDim.x) {
     __syncthreads();
     const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
-    for (int i = tid; i < PAM_P * PAM_C; i += 256)
-      s.x[i / PAM_C][i % PAM_C] = enc_to_float(xf[(i / PAM_C) * ldin + (i % PAM_C)]);
-    __syncthreads();
-    for (int o = tid; o < PAM_C * PAM_C; o += 256) {
-      const int a = o / PAM_C, b = o % PAM_C;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int p = 0; p < PAM_P; ++p) acc = fmaf(s.x[p][a], s.x[p][b], acc);
-      s.att[a][b] = acc;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
+      const int p = i / (PAM_C / 8), c8 = (i % (PAM_C / 8)) * 8;
+      const uint4 ux = *reinterpret_cast<const uint4*>(xf + p * ldin + c8);
+      const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s.x[p][c8 + k] = enc_to_float(hx[k]);
     }
     __syncthreads();
-    // softmax(rowmax - e) == exp(rowmin - e) / sum: one warp per channel row, 4 values per lane
+    {  // gram: thread owns the 8x8 tile (a0.., b0..)
+      const int a0 = (tid >> 4) * 8, b0 = (tid & 15) * 8;
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int p = 0; p < PAM_P; ++p) {
+        const float4 a_lo = *reinterpret_cast<const float4*>(&s.x[p][a0]);
+        const float4 a_hi = *reinterpret_cast<const float4*>(&s.x[p][a0 + 4]);
+        const float4 b_lo = *reinterpret_cast<const float4*>(&s.x[p][b0]);
+        const float4 b_hi = *reinterpret_cast<const float4*>(&s.x[p][b0 + 4]);
+        const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+        const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        *reinterpret_cast<float4*>(&s.att[a0 + i][b0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(&s.att[a0 + i][b0 + 4]) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    __syncthreads();
+    // softmax(rowmax - e): one warp per channel row, 4 values per lane
     for (int a = tid >> 5; a < PAM_C; a += 8) {
       const int l = tid & 31;
       float e[4], mx = -INFINITY;
@@ -292,28 +336,47 @@ __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
       for (int k = 0; k < 4; ++k) s.att[a][l + 32 * k] = en[k] / sum;
     }
     __syncthreads();
-    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
-    for (int o = tid; o < PAM_P * PAM_C; o += 256) {
-      const int p = o / PAM_C, a = o % PAM_C;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int b = 0; b < PAM_C; ++b) acc = fmaf(s.att[a][b], s.x[p][b], acc);
-      of[o] = enc_from_float(gamma * acc + s.x[p][a]);
+    {  // out[p][a] = gamma * sum_b att[a][b] x[p][b] + x[p][a]: thread = (4 channels a, 5 pixels p)
+      const int a0 = (tid & 31) * 4, p0 = (tid >> 5) * 5;
+      float acc[5][4];
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+      for (int b = 0; b < PAM_C; b += 4) {
+        float4 at[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) at[q] = *reinterpret_cast<const float4*>(&s.att[a0 + q][b]);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float4 xv = *reinterpret_cast<const float4*>(&s.x[p0 + r][b]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[r][q] = fmaf(at[q].x, xv.x, fmaf(at[q].y, xv.y, fmaf(at[q].z, xv.z, fmaf(at[q].w, xv.w, acc[r][q]))));
+        }
+      }
+      enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        uint2 u;
+        u.x = enc_pack2(gamma * acc[r][0] + s.x[p0 + r][a0], gamma * acc[r][1] + s.x[p0 + r][a0 + 1]);
+        u.y = enc_pack2(gamma * acc[r][2] + s.x[p0 + r][a0 + 2], gamma * acc[r][3] + s.x[p0 + r][a0 + 3]);
+        *reinterpret_cast<uint2*>(of + (p0 + r) * PAM_C + a0) = u;
+      }
     }
   }
 }
 
-void launch_pam(const enc_t* x, enc_t* out, const float* wqk, const float* bqk,
-                const float* wv, const float* bv, float gamma, int B, int ldin, int num_sms,
-                cudaStream_t stream) {
+void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, const float* bqk, float gamma,
+                int B, int ldin, int num_sms, cudaStream_t stream) {
   static bool cfg = false;
   if (!cfg) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(pam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(sizeof(PamSmem))));
     cfg = true;
   }
-  const int grid = B < num_sms ? B : num_sms;
-  pam_kernel<<<grid, 256, sizeof(PamSmem), stream>>>(x, out, wqk, bqk, wv, bv, gamma, B, ldin);
+  const int grid = B < 3 * num_sms ? B : 3 * num_sms;
+  pam_kernel<<<grid, 256, sizeof(PamSmem), stream>>>(x, v, out, wqk, bqk, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

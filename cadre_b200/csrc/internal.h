@@ -81,6 +81,8 @@ struct GemmArgs {
   int rows_is_k = 0;
   int block_n = 0;  // 0 = choose
   int dbg_a_shift = 0, dbg_base_offset = 0;
+  long long* dbg_clk = nullptr;
+  int dbg_epi = 0;
   // LSTM-cell epilogue (epi = 1)
   int epi = 0;
   const float* xpart = nullptr;

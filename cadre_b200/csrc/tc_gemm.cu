@@ -124,7 +124,7 @@ static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
   p.mask = a.mask, p.ldm = a.ldm, p.mask_bs = a.mask_bs;
   p.act = a.act, p.alpha = a.alpha;
   p.batch_rows = a.batch_rows, p.rows_is_k = a.rows_is_k;
-  p.dbg_a_shift = a.dbg_a_shift, p.dbg_base_offset = a.dbg_base_offset;
+  p.dbg_a_shift = a.dbg_a_shift, p.dbg_base_offset = a.dbg_base_offset, p.dbg_clk = a.dbg_clk, p.dbg_epi = a.dbg_epi;
   p.xpart = a.xpart, p.ldx = a.ldx, p.x_bs = a.x_bs;
   p.c_prev = a.c_prev, p.c_out = a.c_out, p.h_out = a.h_out, p.gates_out = a.gates_out;
   p.ldh = a.ldh, p.h_bs = a.h_bs;
@@ -176,17 +176,18 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   // bf16 operands (encoder linears)
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 0, enc_t)
-  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 0, enc_t)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 4, EPI_LINEAR, 0, enc_t)
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(0, 0, 1, 128, 3, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(0, 1, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 0, 1, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 1, 1, 128, 4, EPI_LINEAR, 1, float)
   // fp32 operands as TF32 (PPO update: forward, dgrad, wgrad, LSTM cell)
-  CADRE_GEMM_CASE(1, 0, 0, 64, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 1, 128, 3, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 1, 1, 128, 3, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LSTM, 1, float)
+  // the PPO GEMMs are latency-bound (few CTAs, short 128-byte k-blocks): deep pipelines, one CTA per SM
+  CADRE_GEMM_CASE(1, 0, 0, 64, 6, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 1, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 1, 1, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 4, EPI_LSTM, 1, float)
 #undef CADRE_GEMM_CASE
   throw Error(1, "launch_gemm: unsupported (kind, majors, block_n, epilogue, out dtype) combination");
 }
@@ -281,7 +282,7 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   if (bn == 64)
     launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
   else
-    launch_inst<0, 0, 0, 128, 3, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
+    launch_inst<0, 0, 0, 128, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -39,6 +39,8 @@ struct TcGemmParams {
   long long ldm, mask_bs;
   int act;
   float alpha;
+  int dbg_epi;  // experiment: 1 = skip global stores, 2 = skip phase 2, 3 = skip tmem loads
+  long long* dbg_clk;  // optional [gridDim.x*y*z][8] clock64 stamps (profiling experiment)
   int dbg_a_shift, dbg_base_offset;  // experiment: A descriptor start shifted by rows (128 B each)
   const int* batch_rows;  // optional [gridDim.z]: valid rows (M) per batch, or valid K when rows_is_k
   int rows_is_k;
@@ -57,10 +59,13 @@ struct TcGemmSmem {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int EPI_BYTES = 128 * (BLOCK_N + 4) * 4;  // fp32 staging tile of the coalesced epilogue
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// exp-based gates with the hardware ex2 path (__expf: ~2 ulp) — far inside the TF32 noise of the pre-activations
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 template <typename OutT>
 __device__ __forceinline__ float load_as_float(const void* base, long long idx) {
@@ -80,8 +85,8 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   static_assert(BLOCK_N >= 32 && BLOCK_N <= 256 && (BLOCK_N & (BLOCK_N - 1)) == 0, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -89,6 +94,8 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y, batch = blockIdx.z;
   const int n0 = n_tile * BLOCK_N;
+  long long* clk = p.dbg_clk ? p.dbg_clk + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (clk && threadIdx.x == 0) clk[0] = clock64();
 
   int m_valid = p.M;
   int num_kb = p.num_kb;
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (clk && threadIdx.x == 0) clk[1] = clock64();
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -176,6 +184,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
+      if (clk && kb == 0) clk[2] = clock64();
       const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
       const uint32_t b_addr = a_addr + S::A_BYTES;
 #pragma unroll
@@ -191,146 +200,219 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       tc_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
     }
     tc_commit(tmem_full);
+    if (clk) clk[3] = clock64();
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue (TMEM -> registers -> global)
+    // ------------------------------------------------------------ epilogue
+    // Phase 1 (row per thread, the TMEM access pattern): accumulator -> registers -> padded smem staging tile.
+    // Phase 2 (row per warp, lane = 4 consecutive columns): every global load / store of the fused epilogue is
+    // a coalesced 512-byte row segment. (Row-per-thread global stores cost ~9 cycles per 16 bytes: 37 k cycles
+    // per 128x128 fp32 tile on B200, measured with clock64 stamps.)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    long long out_row;  // row index into out/res/mask (units of rows)
-    bool row_ok;
-    if constexpr (MODE == MODE_GEMM) {
-      const int m = m_tile * 128 + row;
-      out_row = m;
-      row_ok = m < m_valid;
-    } else {
-      const int w = row % p.Wout;
-      const int hh = (row / p.Wout) % p.TH;
-      const int im = row / (p.Wout * p.TH);
-      const int img = img0 + im, h = h0 + hh;
-      row_ok = img < p.Bimg && im < p.TN;
-      out_row = (static_cast<long long>(img) * p.Hout + h) * p.Wout + w;
-    }
-    // rows of a batched operand beyond batch_rows are written as zeros (keeps K-padding of later GEMMs clean)
-    const bool zero_fill = (p.batch_rows != nullptr) && !p.rows_is_k && !row_ok &&
-                           (MODE == MODE_GEMM) && (m_tile * 128 + row) < p.M;
+    constexpr int LDS = BLOCK_N + 4;
+    float* stg = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES) + (q * 32) * LDS;  // this warp's 32 rows
     if (num_kb > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    if (clk && threadIdx.x == 64) clk[4] = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-    if constexpr (EPI == EPI_LINEAR) {
-      OutT* out = reinterpret_cast<OutT*>(p.out) + batch * p.out_bs;
-      const float* bias = p.bias ? p.bias + batch * p.bias_bs : nullptr;
-      const OutT* res = p.res ? reinterpret_cast<const OutT*>(p.res) + batch * p.res_bs : nullptr;
-      const OutT* mask = p.mask ? reinterpret_cast<const OutT*>(p.mask) + batch * p.mask_bs : nullptr;
-      const bool vec_ok = (p.ldc * sizeof(OutT)) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        if (num_kb > 0) {
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-        } else {
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t r[32];
+      if (num_kb > 0 && p.dbg_epi != 3) {
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        }
-        const int nb = n0 + c * 32;
-        if (nb < p.N && (row_ok || zero_fill)) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]) * p.alpha;
-          const int n = nb + i;
-          if (n < p.N && row_ok) {
-            if (bias) x += bias[n];
-            if (res && !p.res_after_act) x += load_as_float<OutT>(res, out_row * p.ldr + n);
-            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            if (p.act == ACT_LEAKY) x = x > 0.f ? x : 0.01f * x;
-            if (res && p.res_after_act) x += load_as_float<OutT>(res, out_row * p.ldr + n);
-            if (mask && !(load_as_float<OutT>(mask, out_row * p.ldm + n) > 0.f)) x = 0.f;
-          } else {
-            x = 0.f;
-          }
-          v[i] = x;
-        }
-        OutT* dst = out + out_row * p.ldc + nb;
-        if (vec_ok && nb + 32 <= p.N) {
-          if constexpr (sizeof(OutT) == 2) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = enc_pack2(v[8 * i + 0], v[8 * i + 1]);
-              u.y = enc_pack2(v[8 * i + 2], v[8 * i + 3]);
-              u.z = enc_pack2(v[8 * i + 4], v[8 * i + 5]);
-              u.w = enc_pack2(v[8 * i + 6], v[8 * i + 7]);
-              reinterpret_cast<uint4*>(dst)[i] = u;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) {
-              if constexpr (sizeof(OutT) == 2)
-                dst[i] = enc_from_float(v[i]);
-              else
-                dst[i] = v[i];
-            }
-        }
-        }
-        __syncwarp();
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
       }
-    } else {
-      // EPI_LSTM: nn.LSTMCell pointwise part (ppo_agent/models.py:139-152 -> torch LSTMCell, gate order
-      // i,f,g,o); columns are gate-interleaved so one thread holds all four gates of 8 hidden units.
-      const float* xpart = p.xpart + batch * p.x_bs;
-      const float* c_prev = p.c_prev + batch * p.h_bs;
-      float* c_out = p.c_out + batch * p.h_bs;
-      float* h_out = p.h_out + batch * p.h_bs;
-      float* gates_out = p.gates_out + batch * p.x_bs;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        if (num_kb > 0) {
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-        } else {
+      float* dst = stg + lane * LDS + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        }
-        const int nb = n0 + c * 32;
-        if (nb < p.N && (row_ok || zero_fill)) {
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + 4 * j) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+    }
+    __syncwarp();
+    if (clk && threadIdx.x == 64) clk[7] = clock64();
+
+    // With one epilogue warp per scheduler nothing hides instruction latency, so phase 2 is written for few
+    // instructions per row: everything that depends only on the column (bias, pointers, flags) is hoisted, rows
+    // are processed four at a time (independent chains), and the rare residual / mask / tail cases branch off.
+    if (p.dbg_epi != 2) {
+      constexpr int C4 = (BLOCK_N / 4 + 31) / 32;  // float4 column groups per lane
+      const int row_base = m_tile * 128 + q * 32;  // GEMM mode: first logical row of this warp
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = nb + 4 * j;
-          if (n >= p.N) continue;
-          const int u = n >> 2;
-          float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
-          if (row_ok) {
-            const float4 xp = *reinterpret_cast<const float4*>(xpart + out_row * p.ldx + n);
-            gi = sigmoidf_(__uint_as_float(r[4 * j + 0]) + xp.x);
-            gf = sigmoidf_(__uint_as_float(r[4 * j + 1]) + xp.y);
-            gg = tanhf(__uint_as_float(r[4 * j + 2]) + xp.z);
-            go = sigmoidf_(__uint_as_float(r[4 * j + 3]) + xp.w);
-            cn = gf * c_prev[out_row * p.ldh + u] + gi * gg;
-            hn = go * tanhf(cn);
+      for (int cc = 0; cc < C4; ++cc) {
+        const int c4 = lane + 32 * cc;
+        const int n = n0 + c4 * 4;
+        if (c4 * 4 >= BLOCK_N || n >= p.N) continue;
+        const int nv = min(4, p.N - n);
+        const float* srow = stg + c4 * 4;
+        if constexpr (EPI == EPI_LINEAR) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            const float* bp = p.bias + batch * p.bias_bs + n;
+            b4.x = bp[0];
+            if (nv > 1) b4.y = bp[1];
+            if (nv > 2) b4.z = bp[2];
+            if (nv > 3) b4.w = bp[3];
           }
-          *reinterpret_cast<float4*>(gates_out + out_row * p.ldx + n) = make_float4(gi, gf, gg, go);
-          c_out[out_row * p.ldh + u] = cn;
-          h_out[out_row * p.ldh + u] = hn;
+          const float alpha = p.alpha;
+          const int act = p.act;
+          const bool general = (p.res != nullptr) || (p.mask != nullptr) || (MODE != MODE_GEMM);
+          OutT* obase = reinterpret_cast<OutT*>(p.out) + batch * p.out_bs + n;
+          const bool vec = nv == 4 && ((reinterpret_cast<uintptr_t>(obase) | (p.ldc * sizeof(OutT))) % (4 * sizeof(OutT)) == 0);
+          const bool zero_rows = (p.batch_rows != nullptr) && !p.rows_is_k;
+          if (!general && vec) {
+            // fast path: plain GEMM rows, coalesced 16-byte stores
+#pragma unroll 1
+            for (int rr = 0; rr < 32; rr += 4) {
+              float4 a4[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int m = row_base + rr + k;
+                float v0 = fmaf(a4[k].x, alpha, b4.x), v1 = fmaf(a4[k].y, alpha, b4.y);
+                float v2 = fmaf(a4[k].z, alpha, b4.z), v3 = fmaf(a4[k].w, alpha, b4.w);
+                if (act == ACT_RELU) {
+                  v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+                } else if (act == ACT_LEAKY) {
+                  v0 = v0 > 0.f ? v0 : 0.01f * v0, v1 = v1 > 0.f ? v1 : 0.01f * v1;
+                  v2 = v2 > 0.f ? v2 : 0.01f * v2, v3 = v3 > 0.f ? v3 : 0.01f * v3;
+                }
+                const bool ok = m < m_valid;
+                if (!ok) {
+                  if (!(zero_rows && m < p.M)) continue;
+                  v0 = v1 = v2 = v3 = 0.f;
+                }
+                OutT* o = obase + static_cast<long long>(m) * p.ldc;
+                if constexpr (sizeof(OutT) == 4) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+                } else {
+                  uint2 u;
+                  u.x = enc_pack2(v0, v1), u.y = enc_pack2(v2, v3);
+                  *reinterpret_cast<uint2*>(o) = u;
+                }
+              }
+            }
+          } else {
+            // general path: residual / ReLU-backward mask / ragged N / conv row mapping
+#pragma unroll 1
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = q * 32 + rr;
+              long long out_row;
+              bool row_ok;
+              if constexpr (MODE == MODE_GEMM) {
+                out_row = m_tile * 128 + row;
+                row_ok = out_row < m_valid;
+              } else {
+                const int w = row % p.Wout;
+                const int hh = (row / p.Wout) % p.TH;
+                const int im = row / (p.Wout * p.TH);
+                const int img = img0 + im, h = h0 + hh;
+                row_ok = img < p.Bimg;
+                out_row = (static_cast<long long>(img) * p.Hout + h) * p.Wout + w;
+              }
+              const bool zf = zero_rows && !row_ok && (MODE == MODE_GEMM) && out_row < p.M;
+              if (!(row_ok || zf)) continue;
+              const float4 acc4 = *reinterpret_cast<const float4*>(srow + rr * LDS);
+              float v[4] = {fmaf(acc4.x, alpha, b4.x), fmaf(acc4.y, alpha, b4.y), fmaf(acc4.z, alpha, b4.z),
+                            fmaf(acc4.w, alpha, b4.w)};
+              if (row_ok) {
+                const OutT* res = p.res ? reinterpret_cast<const OutT*>(p.res) + batch * p.res_bs + out_row * p.ldr + n
+                                        : nullptr;
+                const OutT* mask = p.mask ? reinterpret_cast<const OutT*>(p.mask) + batch * p.mask_bs +
+                                                out_row * p.ldm + n
+                                          : nullptr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (i < nv) {
+                    float x = v[i];
+                    if (res && !p.res_after_act) x += load_as_float<OutT>(res, i);
+                    if (act == ACT_RELU) x = fmaxf(x, 0.f);
+                    if (act == ACT_LEAKY) x = x > 0.f ? x : 0.01f * x;
+                    if (res && p.res_after_act) x += load_as_float<OutT>(res, i);
+                    if (mask && !(load_as_float<OutT>(mask, i) > 0.f)) x = 0.f;
+                    v[i] = x;
+                  }
+                }
+              } else {
+                v[0] = v[1] = v[2] = v[3] = 0.f;
+              }
+              OutT* o = obase + out_row * p.ldc;
+              if (vec) {
+                if constexpr (sizeof(OutT) == 4) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                  uint2 u;
+                  u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
+                  *reinterpret_cast<uint2*>(o) = u;
+                }
+              } else {
+                for (int i = 0; i < nv; ++i) {
+                  if constexpr (sizeof(OutT) == 4)
+                    o[i] = v[i];
+                  else
+                    o[i] = enc_from_float(v[i]);
+                }
+              }
+            }
+          }
+        } else {
+          // EPI_LSTM: nn.LSTMCell pointwise part (ppo_agent/models.py:139-152 -> torch LSTMCell, gate order
+          // i,f,g,o); columns are gate-interleaved, so this lane's 4 columns are the four gates of unit u.
+          const int u = n >> 2;
+          const float* xbase = p.xpart + batch * p.x_bs + n;
+          float* gbase = p.gates_out + batch * p.x_bs + n;
+          const float* cpbase = p.c_prev + batch * p.h_bs + u;
+          float* cobase = p.c_out + batch * p.h_bs + u;
+          float* hobase = p.h_out + batch * p.h_bs + u;
+          const bool zero_rows = (p.batch_rows != nullptr);
+#pragma unroll 1
+          for (int rr = 0; rr < 32; rr += 2) {
+            float4 a4[2], x4[2];
+            float cp[2];
+            bool ok[2], wr[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int m = row_base + rr + k;
+              ok[k] = m < m_valid;
+              wr[k] = ok[k] || (zero_rows && m < p.M);
+              a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
+              x4[k] = ok[k] ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(m) * p.ldx)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+              cp[k] = ok[k] ? cpbase[static_cast<long long>(m) * p.ldh] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (!wr[k]) continue;
+              const long long m = row_base + rr + k;
+              float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
+              if (ok[k]) {
+                gi = sigmoidf_(a4[k].x + x4[k].x);
+                gf = sigmoidf_(a4[k].y + x4[k].y);
+                gg = tanhf_(a4[k].z + x4[k].z);
+                go = sigmoidf_(a4[k].w + x4[k].w);
+                cn = fmaf(gf, cp[k], gi * gg);
+                hn = go * tanhf_(cn);
+              }
+              *reinterpret_cast<float4*>(gbase + m * p.ldx) = make_float4(gi, gf, gg, go);
+              cobase[m * p.ldh] = cn;
+              hobase[m * p.ldh] = hn;
+            }
+          }
         }
-        }
-        __syncwarp();
       }
     }
   }
 
+  if (clk && threadIdx.x == 64) clk[5] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (clk && threadIdx.x == 0) clk[6] = clock64();
 }
 
 }  // namespace cadre

@@ -80,7 +80,7 @@ def prepare_weights(sd, device, enc16=torch.float16):
     put("pam_wqk", torch.cat([sd["da_head.sa.query_conv.weight"].view(16, 128),
                               sd["da_head.sa.key_conv.weight"].view(16, 128)], 0), torch.float32)
     put("pam_bqk", torch.cat([sd["da_head.sa.query_conv.bias"], sd["da_head.sa.key_conv.bias"]], 0), torch.float32)
-    put("pam_wv", sd["da_head.sa.value_conv.weight"].view(128, 128), torch.float32)
+    put("pam_wv", sd["da_head.sa.value_conv.weight"].view(128, 128), enc16)
     put("pam_bv", sd["da_head.sa.value_conv.bias"], torch.float32)
     for nm in ("conv51", "conv52"):
         w, b = _fold_bn(sd[f"da_head.{nm}.0.weight"], None, sd, f"da_head.{nm}.1")

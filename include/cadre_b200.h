@@ -96,7 +96,7 @@ typedef struct cadre_encoder_weights {
   const float* head5_b; /* [256] */
   const float* pam_wqk; /* fp32 [32][128]: query_conv rows 0..15, key_conv rows 16..31 */
   const float* pam_bqk; /* [32] */
-  const float* pam_wv;  /* fp32 [128][128] */
+  const void* pam_wv;   /* enc16 [128][128] value_conv (runs on the tensor cores) */
   const float* pam_bv;  /* [128] */
   const void* conv51_w; /* enc16 [128][3][3][128] */
   const float* conv51_b;

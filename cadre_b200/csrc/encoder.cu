@@ -35,7 +35,7 @@ struct Encoder {
   enc_t* stem = nullptr;     // [Bmax][72][128][64]
   enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
   enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
-  bool use_flat = true;
+  bool use_flat = true, fuse_stem = true;
   enc_t* head5 = nullptr;    // [Bmax][40][256]
   enc_t* pam_v = nullptr;    // [Bmax][40][128] PAM value projection
   enc_t* sa = nullptr;       // [Bmax][40][128]
@@ -83,6 +83,7 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
   e->use_flat = getenv("CADRE_NO_FLAT") == nullptr;
+  e->fuse_stem = getenv("CADRE_NO_STEM_FUSION") == nullptr;
   e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
   e->pam_v = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
@@ -128,9 +129,14 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
   StemArgs st;
   st.in = e->padded, st.B = B, st.w = static_cast<const enc_t*>(e->w.stem_w), st.bias = e->w.stem_b;
   st.out = e->stem;
-  launch_stem(st, s), step(e, s, n, "stem");
-  launch_maxpool(e->stem, e->use_flat ? e->padact[0] : e->act[0], B, 72, 128, 64, e->use_flat ? 1 : 0, s);
-  step(e, s, n, "maxpool");
+  if (e->use_flat && e->fuse_stem) {
+    st.out = e->padact[0];
+    launch_stem_pool(st, s), step(e, s, n, "stem+pool");
+  } else {
+    launch_stem(st, s), step(e, s, n, "stem");
+    launch_maxpool(e->stem, e->use_flat ? e->padact[0] : e->act[0], B, 72, 128, 64, e->use_flat ? 1 : 0, s);
+    step(e, s, n, "maxpool");
+  }
 
   // ResNet-18 BasicBlocks (resnet.py:39-55, 116-119); conv indices follow execution order
   int cur = 0, ci = 0, H = 36, W = 64, C = 64;

@@ -132,6 +132,8 @@ struct StemArgs {
   enc_t* out = nullptr;
 };
 void launch_stem(const StemArgs& a, cudaStream_t stream);
+// fused stem + ReLU + maxpool -> zero-bordered [B][38][66][64] (tc_stem_pool.cuh); `out` of StemArgs is that buffer
+void launch_stem_pool(const StemArgs& a, cudaStream_t stream);
 
 // Segmented (per-module) gradient norm + clip + Adam over flat buffers cut into chunks (rollout_optim_kernels.cu)
 struct OptTables {

@@ -3,6 +3,7 @@
 #include "tc_gemm.cuh"
 #include "tc_flat3x3.cuh"
 #include "tc_persist.cuh"
+#include "tc_stem_pool.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -354,6 +355,31 @@ void launch_stem(const StemArgs& a, cudaStream_t stream) {
     return;
   }
   launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, enc_t>(p, grid, stream);
+}
+
+void launch_stem_pool(const StemArgs& a, cudaStream_t stream) {
+  StemPoolParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t pitch = 262 * 16;
+  const uint64_t dims[4] = {64, 128, 75, (uint64_t)a.B};
+  const uint64_t str[3] = {32, pitch, 75 * pitch};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  make_map(&p.tmX, 2, 4, a.in, dims, str, box);
+  const uint64_t wdims[2] = {256, 64};
+  const uint64_t wstr[1] = {256 * 2};
+  const uint32_t wbox[2] = {64, 64};
+  make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox);
+  p.bias = a.bias, p.out = a.out, p.B = a.B;
+  p.pool_rows = 12;
+  p.num_units = a.B * (36 / p.pool_rows);
+  static bool configured = false;
+  if (!configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+    configured = true;
+  }
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
+  tc_stem_pool_kernel<<<grid, 320, SP_SMEM, stream>>>(p);
+  CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace cadre

@@ -1,0 +1,211 @@
+// Fused ResNet stem: conv7x7/s2/p3 (Cin = 4, bias + folded BN) -> ReLU -> MaxPool2d(3, s2, p1)
+// (danet_blocks/resnet.py:169-172), writing the pooled map straight into the zero-bordered layer1 input
+// [B][38][66][64]. The 72x128x64 stem activation (1.18 MB / frame) never reaches HBM.
+//
+// Implicit GEMM as in tc_gemm.cuh MODE_STEM: conv row oh = sum_{j<4} A[rp = oh + j] * W[j], where
+// A[rp] (128 pixels x 128 B, one 4-D TMA box over the row-pair interleaved image) depends only on the input
+// row pair rp. A persistent CTA therefore walks the conv rows of a unit (image, block of pooled rows) in order and
+// keeps the A tiles in a shared-memory ring: each new conv row needs ONE new 16 KB tile instead of four
+// (L2 traffic / 3.5), the four 8 KB weight tiles stay resident. Eight epilogue warps drain the double-buffered
+// TMEM accumulator (bias, ReLU, fp16) into a 3-row ring and emit one pooled row for every second conv row.
+#pragma once
+#include "tc_persist.cuh"
+
+namespace cadre {
+
+struct StemPoolParams {
+  CUtensorMap tmX;   // row-pair interleaved image: dims {64, 128, 75, B}, box {64, 128, 1, 1}
+  CUtensorMap tmW;   // [64][256] weights, box {64, 64}
+  const float* bias; // [64]
+  enc_t* out;        // [B][38][66][64] zero-bordered
+  int B, pool_rows;  // pooled rows per unit (divides 36)
+  int num_units;
+};
+
+constexpr int SP_RING = 6;                                 // A tiles in flight (>= 4 live + prefetch)
+constexpr int SP_A_BYTES = 128 * 128;
+constexpr int SP_W_BYTES = 4 * 64 * 128;
+constexpr int SP_ROW_BYTES = 128 * 128;                    // one conv row: 128 px x 64 ch fp16
+constexpr int SP_SMEM = SP_RING * SP_A_BYTES + SP_W_BYTES + 3 * SP_ROW_BYTES + 32 * 8 + 16 + 1024;
+
+__device__ __forceinline__ void sp_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_constant__ StemPoolParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_s = smem;                                   // SP_RING x 16 KB
+  uint8_t* w_s = a_s + SP_RING * SP_A_BYTES;             // 4 x 8 KB
+  uint8_t* row_s = w_s + SP_W_BYTES;                     // 3 x 16 KB conv-row ring (128B-swizzled pixels)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(row_s + 3 * SP_ROW_BYTES);
+  uint64_t* a_empty = a_full + SP_RING;
+  uint64_t* w_full = a_empty + SP_RING;
+  uint64_t* tfull = w_full + 1;   // [2]
+  uint64_t* tempty = tfull + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  __shared__ float s_bias[64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW);
+    for (int i = 0; i < SP_RING; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int units_per_img = 36 / p.pool_rows;
+
+  // unit -> image, first / last conv row (the row above the first pooled row is recomputed as a halo)
+  auto unit_rows = [&](int unit, int& img, int& r0, int& c0, int& c1) {
+    img = unit / units_per_img;
+    r0 = (unit - img * units_per_img) * p.pool_rows;
+    c0 = r0 == 0 ? 0 : 2 * r0 - 1;
+    c1 = 2 * (r0 + p.pool_rows - 1) + 1;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    mbar_expect_tx(w_full, SP_W_BYTES);
+    for (int j = 0; j < 4; ++j) tma_load_2d(w_s + j * 8192, &p.tmW, w_full, j * 64, 0);
+    int seq = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int img, r0, c0, c1;
+      unit_rows(unit, img, r0, c0, c1);
+      for (int rp = c0; rp <= c1 + 3; ++rp, ++seq) {
+        const int slot = seq % SP_RING;
+        const uint32_t ph = (seq / SP_RING) & 1;
+        mbar_wait(&a_empty[slot], ph ^ 1);
+        mbar_expect_tx(&a_full[slot], SP_A_BYTES);
+        tma_load_4d(a_s + slot * SP_A_BYTES, &p.tmX, &a_full[slot], 0, 0, rp, img);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 64);
+    mbar_wait(w_full, 0);
+    const uint32_t w_addr = smem_u32(w_s), a_addr0 = smem_u32(a_s);
+    int seq0 = 0;   // sequence number of tile rp == c0 of the current unit
+    int waited = 0; // tiles [.., waited) have been observed full
+    int lt = 0;     // conv rows issued (accumulator ring position)
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int img, r0, c0, c1;
+      unit_rows(unit, img, r0, c0, c1);
+      for (int oh = c0; oh <= c1; ++oh, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        const int need = seq0 + (oh - c0) + 4;  // tiles oh .. oh+3 must have landed
+        for (; waited < need; ++waited) mbar_wait(&a_full[waited % SP_RING], (waited / SP_RING) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int slot = (seq0 + (oh - c0) + j) % SP_RING;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr0 + slot * SP_A_BYTES + k * 32, 16, 1024, 2);
+            const uint64_t db = umma_smem_desc(w_addr + j * 8192 + k * 32, 16, 1024, 2);
+            tc_mma_f16(tacc, da, db, idesc, (j | k) != 0);
+          }
+        }
+        // tile rp == oh is not needed by later conv rows
+        tc_commit(&a_empty[(seq0 + (oh - c0)) % SP_RING]);
+        tc_commit(&tfull[as]);
+      }
+      // the last three tiles of the unit (rp = c1+1 .. c1+3) are released with the unit's last row
+      for (int j = 1; j <= 3; ++j) tc_commit(&a_empty[(seq0 + (c1 - c0) + j) % SP_RING]);
+      seq0 += (c1 - c0) + 4;
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter
+    const int ew = warp - 2;            // 0..7
+    const int q = warp & 3;             // TMEM lane quarter
+    const int half = ew >> 2;           // which 32 of the 64 channels
+    const int px = q * 32 + lane;       // conv pixel (0..127)
+    const int et = threadIdx.x - 64;    // 0..255
+    int lt = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int img, r0, c0, c1;
+      unit_rows(unit, img, r0, c0, c1);
+      for (int oh = c0; oh <= c1; ++oh, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + as * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        // bias + ReLU + fp16 into the conv-row ring: pixel px = 128 B, 16-byte chunk index XOR (px & 7)
+        uint8_t* rowp = row_s + (oh % 3) * SP_ROW_BYTES + px * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = half * 32 + 8 * j;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + s_bias[ch + i], 0.f);
+          uint4 u;
+          u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
+          u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
+          const int chunk = half * 4 + j;
+          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (px & 7)) << 4)) = u;
+        }
+        sp_epi_bar();
+        if ((oh & 1) && ((oh - 1) >> 1) >= r0) {  // (the unit's halo row above r0 only feeds pooled row r0)
+          // pooled row r = (oh-1)/2 from conv rows oh-2 (absent for r == 0), oh-1, oh; 64 px x 8 chunks
+          const int r = (oh - 1) >> 1;
+          const int ylo = (oh >= 2) ? oh - 2 : oh - 1;
+          enc_t* orow = p.out + ((static_cast<long long>(img) * 38 + r + 1) * 66 + 1) * 64;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int item = et + it * 256;      // 0..511
+            const int pw = item >> 3, chunk = item & 7;
+            float m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = 0.f;  // post-ReLU values are >= 0, so 0 acts as the -inf padding
+            for (int y = ylo; y <= oh; ++y) {
+              const uint8_t* yrow = row_s + (y % 3) * SP_ROW_BYTES;
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int x = 2 * pw + dx;
+                if (x < 0) continue;
+                const uint4 u = *reinterpret_cast<const uint4*>(yrow + x * 128 + ((chunk ^ (x & 7)) << 4));
+                const enc_t* h = reinterpret_cast<const enc_t*>(&u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], enc_to_float(h[i]));
+              }
+            }
+            uint4 o;
+            o.x = enc_pack2(m[0], m[1]), o.y = enc_pack2(m[2], m[3]);
+            o.z = enc_pack2(m[4], m[5]), o.w = enc_pack2(m[6], m[7]);
+            *reinterpret_cast<uint4*>(orow + pw * 64 + chunk * 8) = o;
+          }
+          sp_epi_bar();  // the ring slot of row oh-2 is overwritten by conv row oh+1
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace cadre

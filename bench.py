@@ -41,7 +41,7 @@ def encoder_flops_per_frame():
     """name -> FLOPs/frame of each encoder launch as EXECUTED here (SURVEY.md §8d counts 3.0875 GFLOP/frame for
     the unfused reference graph; the folded fc1 does less work)."""
     f = {}
-    f["stem"] = 2 * 72 * 128 * 64 * 196
+    f["stem"] = f["stem+pool"] = 2 * 72 * 128 * 64 * 196
     H, W, C = 36, 64, 64
     for li, planes in enumerate((64, 128, 256, 512), start=1):
         for bi in range(2):
@@ -57,6 +57,7 @@ def encoder_flops_per_frame():
     f["conv51"] = f["conv52+sum"] = 2 * 40 * 128 * 128 * 9
     f["fc1(folded)"] = 2 * 5120 * 3072
     f["fc2"] = 2 * 6 * 512 * 256
+    f["pam.value_conv"] = 2 * 40 * 128 * 128
     return f
 
 

@@ -29,10 +29,25 @@ using enc_t = __nv_bfloat16;
 __device__ __forceinline__ enc_t enc_from_float(float f) { return __float2bfloat16_rn(f); }
 __device__ __forceinline__ float enc_to_float(enc_t h) { return __bfloat162float(h); }
 #endif
+// two floats -> one packed 32-bit word with a single cvt.rn.f16x2 (values clamped to the finite fp16 range)
 __device__ __forceinline__ uint32_t enc_pack2(float a, float b) {
-  enc_t lo = enc_from_float(a), hi = enc_from_float(b);
-  return static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&lo)) |
-         (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hi)) << 16);
+#if CADRE_ENC_FP16
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+#else
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// same for values already known to be >= 0 (post-ReLU): one clamp instead of two
+__device__ __forceinline__ uint32_t enc_pack2_pos(float a, float b) {
+#if CADRE_ENC_FP16
+  __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+#else
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 struct Error : public std::runtime_error {

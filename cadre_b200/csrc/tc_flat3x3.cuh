@@ -31,7 +31,8 @@ constexpr int FLAT_WIN_A = 136;               // rows of the first TMA box (17 K
 constexpr int FLAT_WIN_ROWS = FLAT_WIN_A + 128;  // 264 >= 128 + 2*66 + 2
 constexpr int FLAT_WIN_BYTES = FLAT_WIN_ROWS * 128;
 constexpr int FLAT_W_BYTES = 9 * 64 * 128;
-constexpr int FLAT_SMEM = FLAT_W_BYTES + 2 * FLAT_WIN_BYTES + 128 * 128 + 16 * 8 + 16 + 1024;
+constexpr int FLAT_NWIN = 3;  // input windows in flight (a 33 KB window takes longer to land than 36 MMAs take to run)
+constexpr int FLAT_SMEM = FLAT_W_BYTES + FLAT_NWIN * FLAT_WIN_BYTES + 128 * 128 + 16 * 8 + 16 + 1024;
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -40,16 +41,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constant__ FlatParams p) {
+__global__ void __launch_bounds__(320, 1) tc_flat3x3_kernel(const __grid_constant__ FlatParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;                                   // 9 x 8 KB
   uint8_t* win_s = w_s + FLAT_W_BYTES;                   // 2 x 33 KB
-  uint8_t* out_s = win_s + 2 * FLAT_WIN_BYTES;           // 16 KB
+  uint8_t* out_s = win_s + FLAT_NWIN * FLAT_WIN_BYTES;   // 16 KB
   uint64_t* w_full = reinterpret_cast<uint64_t*>(out_s + 128 * 128);
-  uint64_t* win_full = w_full + 1;   // [2]
-  uint64_t* win_empty = win_full + 2;
-  uint64_t* tfull = win_empty + 2;
+  uint64_t* win_full = w_full + 1;   // [FLAT_NWIN]
+  uint64_t* win_empty = win_full + FLAT_NWIN;
+  uint64_t* tfull = win_empty + FLAT_NWIN;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -62,11 +63,13 @@ __global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmY);
     mbar_init(w_full, 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < FLAT_NWIN; ++a) {
       mbar_init(&win_full[a], 1);
       mbar_init(&win_empty[a], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -85,8 +88,8 @@ __global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constan
     for (int t = 0; t < 9; ++t) tma_load_2d(w_s + t * 8192, &p.tmW, w_full, t * 64, 0);
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      const int b = lt & 1;
-      const uint32_t ph = (lt >> 1) & 1;
+      const int b = lt % FLAT_NWIN;
+      const uint32_t ph = (lt / FLAT_NWIN) & 1;
       mbar_wait(&win_empty[b], ph ^ 1);
       mbar_expect_tx(&win_full[b], FLAT_WIN_BYTES);
       const int row0 = tile * 128 - p.PW - 1;  // may be negative: TMA zero-fills out-of-range rows
@@ -102,10 +105,11 @@ __global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constan
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int b = lt & 1;
       const uint32_t ph = (lt >> 1) & 1;
+      const int wb = lt % FLAT_NWIN;
       mbar_wait(&tempty[b], ph ^ 1);
-      mbar_wait(&win_full[b], ph);
+      mbar_wait(&win_full[wb], (lt / FLAT_NWIN) & 1);
       tc_fence_after();
-      const uint32_t win_addr = smem_u32(win_s + b * FLAT_WIN_BYTES);
+      const uint32_t win_addr = smem_u32(win_s + wb * FLAT_WIN_BYTES);
       const uint32_t tacc = tmem_base + b * 64;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
@@ -118,12 +122,15 @@ __global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constan
           tc_mma_f16(tacc, da, db, idesc, (t | k) != 0);
         }
       }
-      tc_commit(&win_empty[b]);
+      tc_commit(&win_empty[wb]);
       tc_commit(&tfull[b]);
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter
+    // (with 4 warps the ~600 instructions per thread and tile were the bottleneck: 3.3 k cycles per tile
+    //  against 1.7 k cycles of MMA; measured on B200)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;     // which 32 of the 64 output channels
     const int row = q * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
     const int img_pix = (p.H + 2) * p.PW;
@@ -135,58 +142,50 @@ __global__ void __launch_bounds__(192, 1) tc_flat3x3_kernel(const __grid_constan
       const int rem = pix % img_pix;
       const int y = rem / p.PW, x = rem - y * p.PW;
       const bool interior = pix < p.P && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
-      uint4 rres[8];
+      uint4 rres[4];
       const bool has_res = p.res != nullptr;
       if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(pix) * 64);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(pix) * 64 + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rres[j] = interior ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) rres[j] = interior ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
       if (leader) tma_store_wait_read();
-      epi_bar_sync();
+      epi_bar_sync256();
       mbar_wait(&tfull[b], ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + b * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + b * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
       uint8_t* rowp = out_s + row * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[b]);
-        }
-        float v[32];
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + s_bias[c * 32 + i];
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + s_bias[half * 32 + 8 * j + i];
         if (has_res) {
+          const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[j]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * j + i] += enc_to_float(h8[i]);
-          }
+          for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
         }
+        uint4 u;
+        if (p.act == ACT_RELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (p.act == ACT_RELU) v[i] = fmaxf(v[i], 0.f);
-          if (!interior) v[i] = 0.f;  // keep the zero border intact
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          u.x = enc_pack2_pos(v[0], v[1]), u.y = enc_pack2_pos(v[2], v[3]);
+          u.z = enc_pack2_pos(v[4], v[5]), u.w = enc_pack2_pos(v[6], v[7]);
+        } else {
+          u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
+          u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = c * 4 + j;
-          uint4 u;
-          u.x = enc_pack2(v[8 * j + 0], v[8 * j + 1]);
-          u.y = enc_pack2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = enc_pack2(v[8 * j + 4], v[8 * j + 5]);
-          u.w = enc_pack2(v[8 * j + 6], v[8 * j + 7]);
-          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
-        }
+        if (!interior) u = make_uint4(0, 0, 0, 0);  // keep the zero border intact
+        const int chunk = half * 4 + j;
+        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
       }
       fence_proxy_async_smem();
-      epi_bar_sync();
+      epi_bar_sync256();
       if (leader) {
         tma_store_2d(&p.tmY, out_s, 0, tile * 128);
         tma_store_commit();

@@ -114,7 +114,7 @@ static void launch_persist(const PersistParams& p, cudaStream_t stream) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 192, smem, stream>>>(p);
+  kern<<<grid, 320, smem, stream>>>(p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -207,7 +207,8 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int TH = 1;
   while (TH * 2 <= rows_per_tile && Hout % (TH * 2) == 0) TH *= 2;
   const int TN = rows_per_tile / TH;
-  const int bn = a.Cout <= 64 ? 64 : 128;
+  static const bool allow_bn256 = getenv("CADRE_NO_BN256") == nullptr;
+  const int bn = a.Cout <= 64 ? 64 : ((a.Cout % 256 == 0 && allow_bn256 && !g_use_v1) ? 256 : 128);
 
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -276,8 +277,10 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
     q.bias = a.bias, q.res = a.res, q.ldr = a.Cout, q.res_after_act = a.res_after_act, q.act = a.act;
     if (bn == 64)
       launch_persist<64, 6, MODE_CONV>(q, stream);
-    else
+    else if (bn == 128)
       launch_persist<128, 5, MODE_CONV>(q, stream);
+    else
+      launch_persist<256, 3, MODE_CONV>(q, stream);  // 128x256 tiles: half the A-operand smem traffic per FLOP
     return;
   }
   if (bn == 64)
@@ -313,7 +316,7 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tc_flat3x3_kernel<<<grid, 192, FLAT_SMEM, stream>>>(p);
+  tc_flat3x3_kernel<<<grid, 320, FLAT_SMEM, stream>>>(p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -54,10 +54,10 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int BLOCK_N, int STAGES, int MODE>
-__global__ void __launch_bounds__(192, 1) tc_persist_kernel(const __grid_constant__ PersistParams p) {
+__global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constant__ PersistParams p) {
   constexpr int BK = 64, UMMA_K = 16, NCH = BLOCK_N / 64;
   using S = PersistSmem<BLOCK_N, STAGES>;
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(192, 1) tc_persist_kernel(const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[a], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -163,10 +163,14 @@ __global__ void __launch_bounds__(192, 1) tc_persist_kernel(const __grid_constan
       tc_commit(&tfull[as]);
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter;
+    // warps 2..5 own the first half of the tile's columns, warps 6..9 the second half
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
+    constexpr int HC = BLOCK_N / 2;          // columns per thread
+    const int cbase = half * HC;             // first column (within the tile) of this thread
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       int m_tile, n0, img0, h0;
@@ -190,77 +194,68 @@ __global__ void __launch_bounds__(192, 1) tc_persist_kernel(const __grid_constan
         else
           out_row = (static_cast<long long>(img) * p.Hout + h) * p.Wout + w;
       }
-      // prefetch this thread's residual row while the MMAs of the tile are still in flight
-      uint4 rres[BLOCK_N / 8];
+      // prefetch this thread's residual half-row while the MMAs of the tile are still in flight
+      uint4 rres[HC / 8];
       const bool has_res = p.res != nullptr;
       if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_row * p.ldr + n0);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_row * p.ldr + n0 + cbase);
 #pragma unroll
-        for (int j = 0; j < BLOCK_N / 8; ++j) rres[j] = row_ok ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < HC / 8; ++j) rres[j] = row_ok ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
       // staging buffer must have been read by the previous tile's TMA store
       if (leader) tma_store_wait_read();
-      epi_bar_sync();
+      epi_bar_sync256();
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BLOCK_N + cbase + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < HC / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {  // accumulator fully in registers: hand it back to the MMA warp
+        if (c == HC / 32 - 1) {  // this warp's part of the accumulator is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[as]);
         }
-        const int nb = n0 + c * 32;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]);
-          if (nb + i < p.N) x += p.bias[nb + i];
-          v[i] = x;
-        }
-        if (has_res && !p.res_after_act) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * j + i] += enc_to_float(h8[i]);
-          }
-        }
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else if (p.act == ACT_LEAKY) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
-        }
-        if (has_res && p.res_after_act) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * j + i] += enc_to_float(h8[i]);
-          }
-        }
-        // 32 columns = 4 x 16-byte chunks of this row inside 64-channel group g; 128B swizzle: chunk ^= row & 7
-        const int g = c >> 1;
-        uint8_t* rowp = out_s + g * (128 * 128) + row * 128;
+        const int col = cbase + c * 32;  // column within the tile
+        const int nb = n0 + col;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int chunk = (c & 1) * 4 + j;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = nb + 8 * j + i;
+            v[i] = __uint_as_float(r[8 * j + i]) + (n < p.N ? p.bias[n] : 0.f);
+          }
+          if (has_res && !p.res_after_act) {
+            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
+          }
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+          }
+          if (has_res && p.res_after_act) {
+            const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
+          }
+          // 16-byte chunk of this row inside 64-channel group g; 128B swizzle: chunk ^= row & 7
+          const int g = (col + 8 * j) >> 6;
+          const int chunk = ((col + 8 * j) & 63) >> 3;
           uint4 u;
-          u.x = enc_pack2(v[8 * j + 0], v[8 * j + 1]);
-          u.y = enc_pack2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = enc_pack2(v[8 * j + 4], v[8 * j + 5]);
-          u.w = enc_pack2(v[8 * j + 6], v[8 * j + 7]);
-          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = u;
+          u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
+          u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(out_s + g * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
         }
       }
       fence_proxy_async_smem();
-      epi_bar_sync();
+      epi_bar_sync256();
       if (leader) {
 #pragma unroll
         for (int g = 0; g < NCH; ++g) {

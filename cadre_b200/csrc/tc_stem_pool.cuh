@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + s_bias[ch + i], 0.f);
           uint4 u;
-          u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
-          u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
+          u.x = enc_pack2_pos(v[0], v[1]), u.y = enc_pack2_pos(v[2], v[3]);
+          u.z = enc_pack2_pos(v[4], v[5]), u.w = enc_pack2_pos(v[6], v[7]);
           const int chunk = half * 4 + j;
           *reinterpret_cast<uint4*>(rowp + ((chunk ^ (px & 7)) << 4)) = u;
         }
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
               }
             }
             uint4 o;
-            o.x = enc_pack2(m[0], m[1]), o.y = enc_pack2(m[2], m[3]);
-            o.z = enc_pack2(m[4], m[5]), o.w = enc_pack2(m[6], m[7]);
+            o.x = enc_pack2_pos(m[0], m[1]), o.y = enc_pack2_pos(m[2], m[3]);
+            o.z = enc_pack2_pos(m[4], m[5]), o.w = enc_pack2_pos(m[6], m[7]);
             *reinterpret_cast<uint4*>(orow + pw * 64 + chunk * 8) = o;
           }
           sp_epi_bar();  // the ring slot of row oh-2 is overwritten by conv row oh+1

@@ -95,6 +95,8 @@ struct GemmArgs {
   const int* batch_rows = nullptr;
   int rows_is_k = 0;
   int block_n = 0;  // 0 = choose
+  int ksplit = 1;                  // split-K: partial sums go to out + ks * split_out_stride
+  long long split_out_stride = 0;
   int dbg_a_shift = 0, dbg_base_offset = 0;
   long long* dbg_clk = nullptr;
   int dbg_epi = 0;

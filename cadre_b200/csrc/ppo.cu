@@ -148,6 +148,7 @@ struct HeadParams {
 };
 
 constexpr int HEAD_ROWS_PER_CTA = 64;
+constexpr int DGRAD_SPLIT = 4;  // split-K factor of the recurrent dgrad GEMMs (K = 2120)
 
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   const int e = blockIdx.y, head = e >> 2;
@@ -159,31 +160,23 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float w3aT[HID][AMAX];      // [k][j]
   __shared__ float b3a[AMAX + 3];
   __shared__ float w3c[HID];
-  __shared__ float acc_w3a[AMAX * HID];  // [j][k]
-  __shared__ float acc_b3a[AMAX + 3];
-  __shared__ float acc_w3c[HID];
-  __shared__ float acc_b3c;
   __shared__ float s_y[8][2 * HID];
-  __shared__ float s_dl[8][AMAX + 3];
+  __shared__ float s_dl[HEAD_ROWS_PER_CTA][AMAX + 3];  // d loss / d logits of the CTA's rows
+  __shared__ float s_dv[HEAD_ROWS_PER_CTA];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* W3A = p.params + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
   for (int i = tid; i < AMAX * HID; i += 256) {
     const int j = i / HID, k = i - j * HID;
     w3aT[k][j] = W3A[i];
-    acc_w3a[i] = 0.f;
   }
-  if (tid < AMAX) {
-    b3a[tid] = p.params[OFF_B3A + e * B3A_LD + tid];
-    acc_b3a[tid] = 0.f;
-  }
-  if (tid < HID) {
-    w3c[tid] = p.params[OFF_W3C + e * HID + tid];
-    acc_w3c[tid] = 0.f;
-  }
-  if (tid == 0) acc_b3c = 0.f;
+  if (tid < AMAX) b3a[tid] = p.params[OFF_B3A + e * B3A_LD + tid];
+  if (tid < HID) w3c[tid] = p.params[OFF_W3C + e * HID + tid];
+  for (int i = tid; i < HEAD_ROWS_PER_CTA * (AMAX + 3); i += 256) (&s_dl[0][0])[i] = 0.f;
+  if (tid < HEAD_ROWS_PER_CTA) s_dv[tid] = 0.f;
   const float b3c = p.params[OFF_B3C + e * 4];
   __syncthreads();
 
+  // ---- phase 1: one warp per row: logits, Categorical, PPO objective, backward seeds, d hidden2
   const int row_end = min(row0 + HEAD_ROWS_PER_CTA, rows_pad);
   for (int slot = row0 + warp; slot < row_end; slot += 8) {
     const long long row = static_cast<long long>(e) * p.cap + slot;
@@ -202,7 +195,6 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
       s_y[warp][lane + 32 * q] = ya[q];
     }
     __syncwarp();
-    // logits (lane j and, for A = 33, j = 32 on lane 0) and value
     float l0 = -INFINITY, l1 = -INFINITY;
     if (lane < A) {
       float acc = b3a[lane];
@@ -255,7 +247,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     // backward seeds (autograd conventions of torch.min / torch.max / clamp: ties split evenly, clamp passes
     // the gradient on the closed interval)
     const float inside_r = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-    float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // weight of surr1 in min()
+    const float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // weight of surr1 in min()
     const float dmin_dlp = g1 * adv * ratio + (1.f - g1) * adv * ratio * inside_r;
     const float dlp = -p.clip_coeff * wgt * dmin_dlp;
     const float inside_v = (dvv >= -p.clip && dvv <= p.clip) ? 1.f : 0.f;
@@ -265,36 +257,60 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     float dl0 = 0.f, dl1 = 0.f;
     if (lane < A) dl0 = dlp * ((a == lane ? 1.f : 0.f) - p0) + ew * p0 * (lp0 + ent);
     if (lane + 32 < A) dl1 = dlp * ((a == lane + 32 ? 1.f : 0.f) - p1) + ew * p1 * (lp1 + ent);
-    if (lane < A) s_dl[warp][lane] = dl0;
-    if (lane + 32 < A) s_dl[warp][lane + 32] = dl1;
+    float* dl = s_dl[slot - row0];
+    if (lane < A) dl[lane] = dl0;
+    if (lane + 32 < A) dl[lane + 32] = dl1;
+    if (lane == 0) s_dv[slot - row0] = dv;
     __syncwarp();
     // d hidden2 = dlogits W3a (actor), dv * w3c (critic), through the ReLU
     float da[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < A; ++j) {
-      const float d = s_dl[warp][j];
+      const float d = dl[j];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        da[q] = fmaf(d, w3aT[lane + 32 * q][j], da[q]);
-        atomicAdd(&acc_w3a[j * HID + lane + 32 * q], d * ya[q]);
-      }
+      for (int q = 0; q < 4; ++q) da[q] = fmaf(d, w3aT[lane + 32 * q][j], da[q]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       dz[lane + 32 * q] = ya[q] > 0.f ? da[q] : 0.f;
       dz[HID + lane + 32 * q] = yc[q] > 0.f ? dv * w3c[lane + 32 * q] : 0.f;
-      atomicAdd(&acc_w3c[lane + 32 * q], dv * yc[q]);
     }
-    if (lane < A) atomicAdd(&acc_b3a[lane], dl0);
-    if (lane + 32 < A) atomicAdd(&acc_b3a[lane + 32], dl1);
-    if (lane == 0) atomicAdd(&acc_b3c, dv);
     __syncwarp();
   }
   __syncthreads();
-  float* gW3A = p.grads + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
-  for (int i = tid; i < A * HID; i += 256) atomicAdd(gW3A + i, acc_w3a[i]);
-  if (tid < A) atomicAdd(p.grads + OFF_B3A + e * B3A_LD + tid, acc_b3a[tid]);
-  if (tid < HID) atomicAdd(p.grads + OFF_W3C + e * HID + tid, acc_w3c[tid]);
-  if (tid == 0) atomicAdd(p.grads + OFF_B3C + e * 4, acc_b3c);
+
+  // ---- phase 2: last-layer weight gradients of the CTA's rows as small register-tiled products over the
+  // rows (hidden2 is re-read from L2, d logits / d value sit in shared memory), one global atomic per element
+  const int nrows = min(count, row0 + HEAD_ROWS_PER_CTA) - row0;  // valid rows (padding rows carry zeros anyway)
+  if (nrows <= 0) return;
+  const float* Ybase = p.Y2 + (static_cast<long long>(e) * p.cap + row0) * 2 * HID;
+  {
+    const int k = tid & (HID - 1), jh = tid >> 7;          // column k, logits [jh*17, jh*17+17)
+    const int j0 = jh * 17, j1 = min(A, j0 + 17);
+    float acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = 0.f;
+    float accc = 0.f, accb = 0.f;
+    for (int r = 0; r < nrows; ++r) {
+      const float yv = Ybase[r * 2 * HID + k];
+#pragma unroll
+      for (int i = 0; i < 17; ++i)
+        if (j0 + i < j1) acc[i] = fmaf(s_dl[r][j0 + i], yv, acc[i]);
+      if (jh == 0) accc = fmaf(s_dv[r], Ybase[r * 2 * HID + HID + k], accc);
+    }
+    float* gW3A = p.grads + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
+#pragma unroll
+    for (int i = 0; i < 17; ++i)
+      if (j0 + i < j1) atomicAdd(gW3A + (j0 + i) * HID + k, acc[i]);
+    if (jh == 0) atomicAdd(p.grads + OFF_W3C + e * HID + k, accc);
+    // bias gradients: column sums of d logits / d value
+    if (tid < A) {
+      for (int r = 0; r < nrows; ++r) accb += s_dl[r][tid];
+      atomicAdd(p.grads + OFF_B3A + e * B3A_LD + tid, accb);
+    } else if (tid == 64) {
+      for (int r = 0; r < nrows; ++r) accb += s_dv[r];
+      atomicAdd(p.grads + OFF_B3C + e * 4, accb);
+    }
+  }
 }
 
 // Forward-only variant for act() / get_value() / evaluate_actions (agent.py:114-164, models.py:184-212): writes,
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ G9,
                                                        const float* __restrict__ C9, float* __restrict__ dG9,
                                                        const int* __restrict__ counts, int cap, int t,
-                                                       int first) {
+                                                       int first, int nsplit, long long split_stride) {
   const int e = blockIdx.y;
   const int count = counts[e];
   const int rows_pad = min(cap, (count + 31) & ~31);
@@ -370,7 +386,8 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__
   }
   const float4 g = *(reinterpret_cast<const float4*>(G9 + (row * 9 + t) * G) + u);  // i, f, g, o
   const float c_prev = C9[(row * 9 + t) * LDF + u], c_t = C9[(row * 9 + t + 1) * LDF + u];
-  const float dh = dH[row * LDF + u];
+  float dh = dH[row * LDF + u];  // split-K partial sums of the previous step's dgrad GEMM
+  for (int k = 1; k < nsplit; ++k) dh += dH[k * split_stride + row * LDF + u];
   const float tc = tanhf(c_t);
   float dc = dh * g.w * (1.f - tc * tc);
   if (!first) dc += dC[row * LDF + u];
@@ -445,7 +462,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->Y2 = dalloc<float>(rows * 2 * HID);
   P->dZ1 = dalloc<float>(rows * 2 * HID);
   P->dZ2 = dalloc<float>(rows * 2 * HID);
-  P->dH = dalloc<float>(rows * LDF);
+  P->dH = dalloc<float>(rows * LDF * DGRAD_SPLIT);
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->sc.action = dalloc<int>(rows);
@@ -651,9 +668,10 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     launch_gemm(g, s), ++n;
   }
   const unsigned bwd_blocks = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
+  const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
   for (int t = 7; t >= 0; --t) {
     lstm_bwd_kernel<<<dim3(bwd_blocks, E), 256, 0, s>>>(P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
-                                                        t == 7),
+                                                        t == 7, t == 7 ? 1 : DGRAD_SPLIT, dh_split_stride),
         ++n;
     if (t > 0) {  // dh_{t-1} = dG_t W_hh
       GemmArgs g = tf32_gemm(0, 1);
@@ -662,6 +680,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
       g.M = cap, g.N = F, g.K = G;
       g.out = P->dH, g.ldc = LDF, g.out_bs = static_cast<long long>(cap) * LDF;
       g.batch_rows = P->counts;
+      g.ksplit = DGRAD_SPLIT, g.split_out_stride = dh_split_stride;  // 40 -> 160 CTAs; lstm_bwd sums the partials
       launch_gemm(g, s), ++n;
     }
   }

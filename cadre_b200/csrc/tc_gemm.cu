@@ -168,7 +168,12 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   make_operand_map(&p.tmB, es, a.b_mn, a.B, a.ldb, a.b_bs, a.N, a.K, a.batch, bn);
   p.M = a.M, p.N = a.N, p.num_kb = (a.K + bk - 1) / bk;
   fill_epilogue(p, a);
-  dim3 grid((a.M + 127) / 128, (a.N + bn - 1) / bn, a.batch);
+  p.ksplit = a.ksplit > 1 ? a.ksplit : 1;
+  p.kb_per_split = (p.num_kb + p.ksplit - 1) / p.ksplit;
+  p.split_out_stride = a.split_out_stride;
+  CADRE_REQUIRE(p.ksplit == 1 || (!a.bias && !a.res && !a.mask && a.act == 0 && !a.rows_is_k && a.epi == 0),
+                "split-K supports plain partial sums only");
+  dim3 grid((a.M + 127) / 128, (a.N + bn - 1) / bn, a.batch * p.ksplit);
 
 #define CADRE_GEMM_CASE(KIND, AMN, BMN, BN, ST, EPI, OUT_F32, OutT)                                   \
   if (a.kind == KIND && a.a_mn == AMN && a.b_mn == BMN && bn == BN && a.epi == EPI && a.out_f32 == OUT_F32) { \

@@ -39,6 +39,9 @@ struct TcGemmParams {
   long long ldm, mask_bs;
   int act;
   float alpha;
+  int ksplit;             // >1: blockIdx.z = batch*ksplit + ks; split ks accumulates k-blocks [ks*kb_per_split, ...)
+  int kb_per_split;       //     into out + ks*split_out_stride (the consumer sums the partials)
+  long long split_out_stride;
   int dbg_epi;  // experiment: 1 = skip global stores, 2 = skip phase 2, 3 = skip tmem loads
   long long* dbg_clk;  // optional [gridDim.x*y*z][8] clock64 stamps (profiling experiment)
   int dbg_a_shift, dbg_base_offset;  // experiment: A descriptor start shifted by rows (128 B each)
@@ -92,13 +95,17 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y, batch = blockIdx.z;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int ks = p.ksplit > 1 ? static_cast<int>(blockIdx.z) % p.ksplit : 0;
+  const int batch = p.ksplit > 1 ? static_cast<int>(blockIdx.z) / p.ksplit : static_cast<int>(blockIdx.z);
   const int n0 = n_tile * BLOCK_N;
   long long* clk = p.dbg_clk ? p.dbg_clk + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (clk && threadIdx.x == 0) clk[0] = clock64();
 
   int m_valid = p.M;
   int num_kb = p.num_kb;
+  const int kb0 = ks * p.kb_per_split;  // first k-block of this split (0 without split-K)
+  if (p.ksplit > 1) num_kb = max(0, min(p.kb_per_split, p.num_kb - kb0));
   if (p.batch_rows != nullptr) {
     const int cnt = p.batch_rows[batch];
     if (p.rows_is_k) {
@@ -150,9 +157,9 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
         if constexpr (A_MN) {
 #pragma unroll
           for (int c = 0; c < 128 / CHUNK; ++c)
-            tma_load_3d(a_s + c * BK * 128, &p.tmA[0], &full[s], m_tile * 128 + c * CHUNK, kb * BK, batch);
+            tma_load_3d(a_s + c * BK * 128, &p.tmA[0], &full[s], m_tile * 128 + c * CHUNK, (kb0 + kb) * BK, batch);
         } else {
-          tma_load_3d(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, batch);
+          tma_load_3d(a_s, &p.tmA[0], &full[s], (kb0 + kb) * BK, m_tile * 128, batch);
         }
       } else if constexpr (MODE == MODE_CONV) {
         const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
@@ -164,9 +171,9 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       if constexpr (B_MN) {
 #pragma unroll
         for (int c = 0; c < BLOCK_N / CHUNK; ++c)
-          tma_load_3d(b_s + c * BK * 128, &p.tmB, &full[s], n0 + c * CHUNK, kb * BK, batch);
+          tma_load_3d(b_s + c * BK * 128, &p.tmB, &full[s], n0 + c * CHUNK, (kb0 + kb) * BK, batch);
       } else {
-        tma_load_3d(b_s, &p.tmB, &full[s], kb * BK, n0, batch);
+        tma_load_3d(b_s, &p.tmB, &full[s], (kb0 + kb) * BK, n0, batch);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           const float alpha = p.alpha;
           const int act = p.act;
           const bool general = (p.res != nullptr) || (p.mask != nullptr) || (MODE != MODE_GEMM);
-          OutT* obase = reinterpret_cast<OutT*>(p.out) + batch * p.out_bs + n;
+          OutT* obase = reinterpret_cast<OutT*>(p.out) + batch * p.out_bs + ks * p.split_out_stride + n;
           const bool vec = nv == 4 && ((reinterpret_cast<uintptr_t>(obase) | (p.ldc * sizeof(OutT))) % (4 * sizeof(OutT)) == 0);
           const bool zero_rows = (p.batch_rows != nullptr) && !p.rows_is_k;
           if (!general && vec) {

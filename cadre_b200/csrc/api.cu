@@ -4,6 +4,7 @@
 #include "internal.h"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace cadre {
 static thread_local std::string g_last_error;
@@ -32,6 +33,44 @@ int cadre_enc_dtype(void) { return CADRE_ENC_FP16 ? 1 : 0; }
 int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream) {
   CADRE_API_BEGIN
   CADRE_CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  CADRE_API_END
+}
+
+int cadre_l2_persist(const void* ptr, int64_t nbytes, void* stream) {
+  CADRE_API_BEGIN
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0;
+  CADRE_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  static bool have = false;
+  static size_t max_persist = 0, max_window = 0;
+  if (!have) {
+    CADRE_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    max_persist = prop.persistingL2CacheMaxSize, max_window = prop.accessPolicyMaxWindowSize;
+    have = true;
+  }
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (ptr != nullptr && nbytes > 0 && max_persist > 0) {
+    const size_t want = static_cast<size_t>(nbytes) < max_persist ? static_cast<size_t>(nbytes) : max_persist;
+    static size_t limit_set = 0;
+    if (limit_set != want) {
+      CADRE_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      limit_set = want;
+    }
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+    attr.accessPolicyWindow.num_bytes = static_cast<size_t>(nbytes) < max_window ? static_cast<size_t>(nbytes) : max_window;
+    attr.accessPolicyWindow.hitRatio = static_cast<float>(want) / static_cast<float>(attr.accessPolicyWindow.num_bytes);
+    if (attr.accessPolicyWindow.hitRatio > 1.f) attr.accessPolicyWindow.hitRatio = 1.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  }
+  CADRE_CUDA_CHECK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (ptr == nullptr || nbytes <= 0) CADRE_CUDA_CHECK(cudaCtxResetPersistingL2Cache());
   CADRE_API_END
 }
 

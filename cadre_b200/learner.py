@@ -11,9 +11,13 @@ replicas hold identical parameters afterwards. How it is done here:
   * every rank then runs the same deterministic clip + Adam kernel, so no parameter broadcast
     (agent.py:239-243) is needed and replicas stay bit-identical.
 """
+import ctypes
+import os
+
 import numpy as np
 import torch
 
+from . import _lib
 from . import ppo as _ppo
 from . import ppo_params
 from .storage import RolloutStorage
@@ -73,6 +77,7 @@ class Learner:
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.losses = torch.zeros(workers, 2, 3, device=self.device)
         self.step_count = 0
+        self.l2_persist = os.environ.get("CADRE_L2_PERSIST", "0") == "1"   # measured: no gain on B200, costs the encoder L2
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -132,10 +137,15 @@ class Learner:
         """ppo_epoch x minibatches of update_step over already computed returns/advantages (train.py:93-110)."""
         storages = pool_or_storages.storages if hasattr(pool_or_storages, "storages") else pool_or_storages
         n = 0
+        if self.l2_persist:   # keep W_ih / W_hh (the first 72 MB of the flat buffer) L2-resident during the update
+            nbytes = 2 * ppo_params.E * ppo_params.G * ppo_params.LDF * 4
+            _lib.check(_lib.lib().cadre_l2_persist(_lib.ptr(self.params), ctypes.c_int64(nbytes), _lib.stream_ptr()))
         for _ in range(ppo_epoch):
             for idx in self.sample_epoch_indices(storages):
                 self.update_step(storages, idx)
                 n += 1
+        if self.l2_persist:
+            _lib.check(_lib.lib().cadre_l2_persist(None, ctypes.c_int64(0), _lib.stream_ptr()))
         return n
 
     def state(self):

@@ -26,6 +26,10 @@ const char* cadre_version(void);
 /* 16-bit storage / tensor-core operand type of the encoder path: 1 = IEEE fp16 (default build), 0 = bf16.
  * Every "enc16" buffer below (activations, conv / linear weights) uses this type. */
 int cadre_enc_dtype(void);
+/* Pin [ptr, ptr+nbytes) in the persisting part of L2 for kernels subsequently launched on `stream`
+ * (cudaAccessPolicyWindow); ptr = NULL or nbytes = 0 removes the window. Used by the learner to keep the LSTM
+ * weights (72 MB fp32) L2-resident across the 8 recurrent steps and 7 dgrad GEMMs of an update. */
+int cadre_l2_persist(const void* ptr, int64_t nbytes, void* stream);
 /* stream-ordered device-to-device copy (test / debug helper) */
 int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream);
 

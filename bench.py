@@ -109,6 +109,15 @@ def sample_clocks_stop(p, path):
     return out
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the tcgen05 launches of one encoder forward at batch 640, from the committed
+    `ncu --set full` capture (profiles/r1_final_encoder_ncu_full.md); None if the summary is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["tcgen05_family_dram_bytes_per_forward_b640"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -352,7 +361,7 @@ def run_cadre(args):
         roofline = {"kernel": "tcgen05 tile kernels (implicit-GEMM conv / linear launches of one encoder forward, "
                               f"{len(conv)} launches, batch {ENC_CHUNK})",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": round(ach / tf_peak, 4), "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                    "frac": round(ach / tf_peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src + " (sustained bf16)",
                     "share_of_encoder_ms": round(tot_ms / sum(k["ms"] for k in kernels), 3)}
         launches = (n // ENC_CHUNK) * enc.launches_per_forward + 1 + n_upd * (learner.engine.launches + 3)
         cpu_val, cpu_detail = cpu_reference_rate(64, 64, os.cpu_count() or 1)

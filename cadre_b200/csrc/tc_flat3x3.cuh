@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(320, 1) tc_flat3x3_kernel(const __grid_constan
     const int row = q * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
     const int img_pix = (p.H + 2) * p.PW;
+    float bias_r[32];                     // this thread always handles the same 32 channels
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[half * 32 + i];
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       const int b = lt & 1;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(320, 1) tc_flat3x3_kernel(const __grid_constan
       for (int j = 0; j < 4; ++j) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + s_bias[half * 32 + 8 * j + i];
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + bias_r[8 * j + i];
         if (has_res) {
           const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[j]);
 #pragma unroll

@@ -103,6 +103,29 @@ static int num_sms() {
 }
 static const bool g_use_v1 = getenv("CADRE_CONV_V1") != nullptr;  // A/B switch: non-persistent encoder kernels
 
+// CTA-pair variant (cta_group::2): clusters of two CTAs, one 256 x BN tile per pair
+template <int BN, int STAGES, int MODE>
+static void launch_persist2(const PersistParams& p, cudaStream_t stream) {
+  auto kern = tc_persist_kernel<BN, STAGES, MODE, true>;
+  constexpr int smem = PersistSmem<BN, STAGES, true>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int pairs_needed = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  int pairs = num_sms() / 2;
+  if (pairs_needed < pairs) pairs = pairs_needed;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+}
+
 template <int BN, int STAGES, int MODE>
 static void launch_persist(const PersistParams& p, cudaStream_t stream) {
   auto kern = tc_persist_kernel<BN, STAGES, MODE>;
@@ -280,12 +303,24 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
     q.tiles_m = grid.x, q.tiles_n = grid.y;
     q.N = a.Cout;
     q.bias = a.bias, q.res = a.res, q.ldr = a.Cout, q.res_after_act = a.res_after_act, q.act = a.act;
+    static const bool use_pairs = getenv("CADRE_NO_CTA_PAIRS") == nullptr;  // cta_group::2 pairs (A/B switch)
     if (bn == 64)
       launch_persist<64, 6, MODE_CONV>(q, stream);
-    else if (bn == 128)
-      launch_persist<128, 5, MODE_CONV>(q, stream);
-    else
-      launch_persist<256, 3, MODE_CONV>(q, stream);  // 128x256 tiles: half the A-operand smem traffic per FLOP
+    else if (bn == 128) {
+      if (use_pairs) {
+        make_operand_map(&q.tmB, 2, false, a.w, nt * a.Cin, 0, a.Cout, nt * a.Cin, 1, 64);  // half-tile B boxes
+        launch_persist2<128, 6, MODE_CONV>(q, stream);
+      } else {
+        launch_persist<128, 5, MODE_CONV>(q, stream);
+      }
+    } else {
+      if (use_pairs) {
+        make_operand_map(&q.tmB, 2, false, a.w, nt * a.Cin, 0, a.Cout, nt * a.Cin, 1, 128);
+        launch_persist2<256, 4, MODE_CONV>(q, stream);
+      } else {
+        launch_persist<256, 3, MODE_CONV>(q, stream);  // 128x256 tiles: half the A-operand smem traffic per FLOP
+      }
+    }
     return;
   }
   if (bn == 64)

@@ -27,10 +27,10 @@ struct PersistParams {
   int out_pad;              // output (and residual) tensors carry a 1-pixel zero border: [B][H+2][W+2][C]
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool CTA2 = false>
 struct PersistSmem {
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;  // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BYTES = (BLOCK_N / 64) * 128 * 128;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -56,10 +56,83 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BLOCK_N, int STAGES, int MODE>
+// ---- cta_group::2 (CTA pair) helpers. Shared::cluster addresses carry the CTA rank in bit 24; clearing it
+// addresses the same offset in the leader (even) CTA (cute/arch/copy_sm100_tma.hpp Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, uint64_t* leader_bar, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint64_t* leader_bar, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's barrier
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// CTA2 = true: the kernel is launched in clusters of two CTAs that compute one 256 x BLOCK_N tile with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA loads its own 128 rows of A and HALF of the B tile, the leader
+// CTA issues the MMAs for both, each CTA drains the 128 accumulator rows in its own TMEM. Per FLOP this halves
+// the B-operand shared-memory traffic (TMA write + UMMA read), which is what bounds the 1-CTA kernel.
+template <int BLOCK_N, int STAGES, int MODE, bool CTA2 = false>
 __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constant__ PersistParams p) {
   constexpr int BK = 64, UMMA_K = 16, NCH = BLOCK_N / 64;
-  using S = PersistSmem<BLOCK_N, STAGES>;
+  using S = PersistSmem<BLOCK_N, STAGES, CTA2>;
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +145,11 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader of the pair
+  const int tiles_m_sched = CTA2 ? (p.tiles_m + 1) / 2 : p.tiles_m;     // pairs of 128-row m-tiles
+  const int total_tiles = tiles_m_sched * p.tiles_n;
+  const int worker = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 128 / 256 / 512 columns
 
   if (warp == 0 && lane == 0) {
@@ -85,22 +162,28 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty[a], CTA2 ? 16 : 8);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_origin = [&](int tile, int& m_tile, int& n0, int& img0, int& h0) {
-    const int n_tile = tile / p.tiles_m;
-    m_tile = tile - n_tile * p.tiles_m;
+    const int n_tile = tile / tiles_m_sched;
+    m_tile = tile - n_tile * tiles_m_sched;
+    if constexpr (CTA2) m_tile = 2 * m_tile + rank;  // this CTA's half of the 256-row tile
     n0 = n_tile * BLOCK_N;
     img0 = 0, h0 = 0;
     if constexpr (MODE != MODE_GEMM) {
@@ -113,33 +196,48 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int it = 0;  // global k-block counter across tiles
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
       int m_tile, n0, img0, h0;
       tile_origin(tile, m_tile, n0, img0, h0);
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], S::STAGE_BYTES);
         uint8_t* a_s = smem + s * S::STAGE_BYTES;
         uint8_t* b_s = a_s + S::A_BYTES;
-        if constexpr (MODE == MODE_GEMM) {
-          tma_load_3d(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
-        } else if constexpr (MODE == MODE_CONV) {
-          const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
-          const ConvTap t = p.taps[tap];
-          tma_load_4d(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
+        if constexpr (CTA2) {
+          // both CTAs load into their own smem; all bytes are accounted on the LEADER's full barrier
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+          if constexpr (MODE == MODE_GEMM) {
+            tma_load_3d_2sm(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
+          } else if constexpr (MODE == MODE_CONV) {
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            const ConvTap t = p.taps[tap];
+            tma_load_4d_2sm(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
+          } else {
+            tma_load_4d_2sm(a_s, &p.tmA[0], &full[s], 0, 0, h0 + kb, img0);
+          }
+          tma_load_3d_2sm(b_s, &p.tmB, &full[s], kb * BK, n0 + rank * (BLOCK_N / 2), 0);
         } else {
-          tma_load_4d(a_s, &p.tmA[0], &full[s], 0, 0, h0 + kb, img0);
+          mbar_expect_tx(&full[s], S::STAGE_BYTES);
+          if constexpr (MODE == MODE_GEMM) {
+            tma_load_3d(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
+          } else if constexpr (MODE == MODE_CONV) {
+            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            const ConvTap t = p.taps[tap];
+            tma_load_4d(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
+          } else {
+            tma_load_4d(a_s, &p.tmA[0], &full[s], 0, 0, h0 + kb, img0);
+          }
+          tma_load_3d(b_s, &p.tmB, &full[s], kb * BK, n0, 0);
         }
-        tma_load_3d(b_s, &p.tmB, &full[s], kb * BK, n0, 0);
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, BLOCK_N);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, CTA2 ? 256 : 128, BLOCK_N);
     int it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++lt) {
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(&tempty[as], aph ^ 1);  // epilogue has drained this accumulator
@@ -156,11 +254,14 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
           const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
-          tc_mma_f16(tacc, da, db, idesc, (kb | k) != 0);
+          if constexpr (CTA2)
+            tc_mma_f16_2sm(tacc, da, db, idesc, (kb | k) != 0);
+          else
+            tc_mma_f16(tacc, da, db, idesc, (kb | k) != 0);
         }
-        tc_commit(&empty[s]);
+        if constexpr (CTA2) tc_commit_2sm(&empty[s]); else tc_commit(&empty[s]);
       }
-      tc_commit(&tfull[as]);
+      if constexpr (CTA2) tc_commit_2sm(&tfull[as]); else tc_commit(&tfull[as]);
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter;
@@ -172,7 +273,7 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
     constexpr int HC = BLOCK_N / 2;          // columns per thread
     const int cbase = half * HC;             // first column (within the tile) of this thread
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++lt) {
       int m_tile, n0, img0, h0;
       tile_origin(tile, m_tile, n0, img0, h0);
       const int as = lt & 1;
@@ -216,18 +317,23 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         if (c == HC / 32 - 1) {  // this warp's part of the accumulator is in registers
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
+          }
         }
         const int col = cbase + c * 32;  // column within the tile
         const int nb = n0 + col;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = nb + 8 * j + i;
-            v[i] = __uint_as_float(r[8 * j + i]) + (n < p.N ? p.bias[n] : 0.f);
+          float4 b_lo = make_float4(0.f, 0.f, 0.f, 0.f), b_hi = b_lo;
+          if (nb + 8 * j < p.N) {  // N is a multiple of 8 on this path: two 16-byte bias loads per 8 columns
+            b_lo = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 8 * j));
+            b_hi = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 8 * j + 4));
           }
+          const float bb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + bb[i];
           if (has_res && !p.res_after_act) {
             const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
 #pragma unroll
@@ -273,8 +379,13 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CTA2) {
+    cluster_sync_all();  // the peer may still multicast into this CTA's barriers / read its smem
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace cadre

@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     const int half = ew >> 2;           // which 32 of the 64 channels
     const int px = q * 32 + lane;       // conv pixel (0..127)
     const int et = threadIdx.x - 64;    // 0..255
+    float bias_r[32];                   // this thread always handles the same 32 channels
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[half * 32 + i];
     int lt = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
@@ -157,10 +160,9 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
         uint8_t* rowp = row_s + (oh % 3) * SP_ROW_BYTES + px * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch = half * 32 + 8 * j;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + s_bias[ch + i], 0.f);
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + bias_r[8 * j + i], 0.f);
           uint4 u;
           u.x = enc_pack2_pos(v[0], v[1]), u.y = enc_pack2_pos(v[2], v[3]);
           u.z = enc_pack2_pos(v[4], v[5]), u.w = enc_pack2_pos(v[6], v[7]);

@@ -113,6 +113,11 @@ int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const vo
   CADRE_API_END
 }
 
+int cadre_debug_clk(long long* dev_counters) {
+  cadre::g_dbg_clk = dev_counters;
+  return 0;
+}
+
 int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
                          int act, void* out, void* stream) {
   CADRE_API_BEGIN

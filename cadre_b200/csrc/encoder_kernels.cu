@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the perception encoder forward pass (HBM / latency bound, fp32 math on CUDA cores):
 // uint8 ingest, max-pool, fused position attention (PAM), fused channel attention (CAM), inter-task attention.
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace cadre {
 
@@ -10,6 +11,8 @@ namespace cadre {
 // transposed -> channel 3. Output: the stem's row-pair interleaved, 3-pixel padded bf16 image
 // P[B][75][262][2][4] (borders stay zero from allocation time).
 __global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __restrict__ mx) {
+  pdl_trigger();
+  pdl_wait();
   const uint8_t* r = route + static_cast<long long>(blockIdx.x) * 256 * 144;
   unsigned m = 0;
   const uint4* r4 = reinterpret_cast<const uint4*>(r);
@@ -38,6 +41,8 @@ __global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __r
 __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ route,
                                   const uint8_t* __restrict__ route_max, enc_t* __restrict__ out,
                                   int B) {
+  pdl_trigger();
+  pdl_wait();
   // one thread per (image, row pair y2 in 1..73, pixel x in 0..255): writes 16 bytes
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * 73 * 256;
@@ -68,15 +73,17 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t
 
 void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
                        int B, cudaStream_t stream) {
-  route_max_kernel<<<B, 256, 0, stream>>>(route, route_max_ws);
+  launch_k(route_max_kernel, dim3(B), dim3(256), 0, stream, route, route_max_ws);
   const long long total = static_cast<long long>(B) * 73 * 256;
-  preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(rgb, route, route_max_ws,
+  launch_k(preprocess_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, rgb, route, route_max_ws,
                                                                                      out, B);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
 // same layout from an already-normalised fp32 NCHW tensor [B,4,144,256] (parity tests / encoder sweep input)
 __global__ void pack_f32_kernel(const float* __restrict__ x, enc_t* __restrict__ out, int B) {
+  pdl_trigger();
+  pdl_wait();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * 73 * 256;
   if (gid >= total) return;
@@ -100,7 +107,7 @@ __global__ void pack_f32_kernel(const float* __restrict__ x, enc_t* __restrict__
 
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * 73 * 256;
-  pack_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, out, B);
+  launch_k(pack_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x, out, B);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -109,6 +116,8 @@ void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream) {
 // One thread = one output pixel x 8 channels (16 B); inputs are post-ReLU so padding never wins.
 __global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__ out, int B,
                                int Hin, int Win, int C, int out_pad) {
+  pdl_trigger();
+  pdl_wait();
   const int Hout = Hin / 2, Wout = Win / 2, CV = C / 8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Hout * Wout * CV;
@@ -147,7 +156,7 @@ __global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__
 void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
                     cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2) * (C / 8);
-  maxpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, B, Hin, Win, C, out_pad);
+  launch_k(maxpool_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, in, out, B, Hin, Win, C, out_pad);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -170,6 +179,8 @@ struct PamSmem {
 __global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin, const enc_t* __restrict__ vin,
                                                   enc_t* __restrict__ out, const float* __restrict__ wqk,
                                                   const float* __restrict__ bqk, float gamma, int B, int ldin) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t pam_raw[];
   PamSmem& s = *reinterpret_cast<PamSmem*>(pam_raw);
   const int tid = threadIdx.x;
@@ -185,11 +196,10 @@ __global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin,
       const uint4 uv = *reinterpret_cast<const uint4*>(vf + p * PAM_C + c8);
       const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
       const enc_t* hv = reinterpret_cast<const enc_t*>(&uv);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s.x[p][c8 + k] = enc_to_float(hx[k]);
-        s.v[p][c8 + k] = enc_to_float(hv[k]);
-      }
+      *reinterpret_cast<float4*>(&s.x[p][c8]) = make_float4(enc_to_float(hx[0]), enc_to_float(hx[1]), enc_to_float(hx[2]), enc_to_float(hx[3]));
+      *reinterpret_cast<float4*>(&s.x[p][c8 + 4]) = make_float4(enc_to_float(hx[4]), enc_to_float(hx[5]), enc_to_float(hx[6]), enc_to_float(hx[7]));
+      *reinterpret_cast<float4*>(&s.v[p][c8]) = make_float4(enc_to_float(hv[0]), enc_to_float(hv[1]), enc_to_float(hv[2]), enc_to_float(hv[3]));
+      *reinterpret_cast<float4*>(&s.v[p][c8 + 4]) = make_float4(enc_to_float(hv[4]), enc_to_float(hv[5]), enc_to_float(hv[6]), enc_to_float(hv[7]));
     }
     __syncthreads();
     {  // qk[p][j]: thread = (j, group of 5 pixels), float4 along the 128 input channels
@@ -268,6 +278,8 @@ struct CamSmem {
 
 __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin, enc_t* __restrict__ out,
                                                   float gamma, int B, int ldin) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t cam_raw[];
   CamSmem& s = *reinterpret_cast<CamSmem*>(cam_raw);
   const int tid = threadIdx.x;
@@ -278,22 +290,24 @@ __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
       const int p = i / (PAM_C / 8), c8 = (i % (PAM_C / 8)) * 8;
       const uint4 ux = *reinterpret_cast<const uint4*>(xf + p * ldin + c8);
       const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s.x[p][c8 + k] = enc_to_float(hx[k]);
+      *reinterpret_cast<float4*>(&s.x[p][c8]) = make_float4(enc_to_float(hx[0]), enc_to_float(hx[1]), enc_to_float(hx[2]), enc_to_float(hx[3]));
+      *reinterpret_cast<float4*>(&s.x[p][c8 + 4]) = make_float4(enc_to_float(hx[4]), enc_to_float(hx[5]), enc_to_float(hx[6]), enc_to_float(hx[7]));
     }
     __syncthreads();
-    {  // gram: thread owns the 8x8 tile (a0.., b0..)
-      const int a0 = (tid >> 4) * 8, b0 = (tid & 15) * 8;
+    {  // gram: thread owns rows a0..a0+7 x columns {b0..b0+3, 64+b0..64+b0+3}: the 16 lanes that differ in b0
+       // read consecutive float4 (conflict-free), the two a0 values of a warp are broadcasts
+      const int a0 = (tid >> 4) * 8, b0 = (tid & 15) * 4;
       float acc[8][8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
       for (int p = 0; p < PAM_P; ++p) {
         const float4 a_lo = *reinterpret_cast<const float4*>(&s.x[p][a0]);
         const float4 a_hi = *reinterpret_cast<const float4*>(&s.x[p][a0 + 4]);
         const float4 b_lo = *reinterpret_cast<const float4*>(&s.x[p][b0]);
-        const float4 b_hi = *reinterpret_cast<const float4*>(&s.x[p][b0 + 4]);
+        const float4 b_hi = *reinterpret_cast<const float4*>(&s.x[p][64 + b0]);
         const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
         const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
 #pragma unroll
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         *reinterpret_cast<float4*>(&s.att[a0 + i][b0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        *reinterpret_cast<float4*>(&s.att[a0 + i][b0 + 4]) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        *reinterpret_cast<float4*>(&s.att[a0 + i][64 + b0]) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
       }
     }
     __syncthreads();
@@ -336,17 +350,20 @@ __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
       for (int k = 0; k < 4; ++k) s.att[a][l + 32 * k] = en[k] / sum;
     }
     __syncthreads();
-    {  // out[p][a] = gamma * sum_b att[a][b] x[p][b] + x[p][a]: thread = (4 channels a, 5 pixels p)
-      const int a0 = (tid & 31) * 4, p0 = (tid >> 5) * 5;
+    {  // out[p][a] = gamma * sum_b att[a][b] x[p][b] + x[p][a]: thread = channels {lane + 32q}, 5 pixels p.
+       // Lanes read CONSECUTIVE att rows (row stride 132 words = 4 banks: conflict-free float4 loads; the former
+       // lane*4 mapping put every other lane on the same bank and made this loop 8x slower); x reads are broadcasts.
+      const int lane = tid & 31, p0 = (tid >> 5) * 5;
       float acc[5][4];
 #pragma unroll
       for (int r = 0; r < 5; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+#pragma unroll 2
       for (int b = 0; b < PAM_C; b += 4) {
         float4 at[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) at[q] = *reinterpret_cast<const float4*>(&s.att[a0 + q][b]);
+        for (int q = 0; q < 4; ++q) at[q] = *reinterpret_cast<const float4*>(&s.att[lane + 32 * q][b]);
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
           const float4 xv = *reinterpret_cast<const float4*>(&s.x[p0 + r][b]);
@@ -357,12 +374,12 @@ __global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin,
       }
       enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        uint2 u;
-        u.x = enc_pack2(gamma * acc[r][0] + s.x[p0 + r][a0], gamma * acc[r][1] + s.x[p0 + r][a0 + 1]);
-        u.y = enc_pack2(gamma * acc[r][2] + s.x[p0 + r][a0 + 2], gamma * acc[r][3] + s.x[p0 + r][a0 + 3]);
-        *reinterpret_cast<uint2*>(of + (p0 + r) * PAM_C + a0) = u;
-      }
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int a = lane + 32 * q;
+          of[(p0 + r) * PAM_C + a] = enc_from_float(gamma * acc[r][q] + s.x[p0 + r][a]);
+        }
     }
   }
 }
@@ -376,7 +393,7 @@ void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, co
     cfg = true;
   }
   const int grid = B < 3 * num_sms ? B : 3 * num_sms;
-  pam_kernel<<<grid, 256, sizeof(PamSmem), stream>>>(x, v, out, wqk, bqk, gamma, B, ldin);
+  launch_k(pam_kernel, dim3(grid), dim3(256), sizeof(PamSmem), stream, x, v, out, wqk, bqk, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -389,7 +406,7 @@ void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int nu
     cfg = true;
   }
   const int grid = B < 2 * num_sms ? B : 2 * num_sms;
-  cam_kernel<<<grid, 256, sizeof(CamSmem), stream>>>(x, out, gamma, B, ldin);
+  launch_k(cam_kernel, dim3(grid), dim3(256), sizeof(CamSmem), stream, x, out, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -399,9 +416,18 @@ void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int nu
 //   att_vis[i] = sum_j v_vis[j] softmax_j((q_bc[i]/16)  k_vis[j]) + v_vis[i]
 // qkv: fp32 [6][B][256] in the order (vis q, vis k, vis v, bc q, bc k, bc v). Output row: [att_vis | att_bc |
 // optional 18 measurement floats] fp32 with row stride ld_out (danet.py:233 + agent.py:106-111).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(256) intertask_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                         const double* __restrict__ meas, int B, int ld_out) {
-  __shared__ float sk[2][256], sv[2][256];
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float sk[2][256], sv[2][256];
+  __shared__ float s_ext[2][2][8];   // [direction][max, min][warp]
   const int f = blockIdx.x, i = threadIdx.x;
   const long long BS = static_cast<long long>(B) * 256;
   const float* base = qkv + static_cast<long long>(f) * 256;
@@ -409,19 +435,38 @@ __global__ void __launch_bounds__(256) intertask_kernel(const float* __restrict_
   const float bq = base[3 * BS + i], bk = base[4 * BS + i], bv = base[5 * BS + i];
   sk[0][i] = bk, sv[0][i] = bv;  // direction 0: visual query -> bc keys/values  => att_bc
   sk[1][i] = vk, sv[1][i] = vv;  // direction 1: bc query -> visual keys/values  => att_vis
+  {  // extrema of the keys: max_j(q k_j) = q * (q >= 0 ? kmax : kmin), so no per-thread max pass is needed
+    float mx0 = bk, mn0 = bk, mx1 = vk, mn1 = vk;
+    for (int o = 16; o > 0; o >>= 1) {
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o)), mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)), mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    }
+    if ((i & 31) == 0) {
+      s_ext[0][0][i >> 5] = mx0, s_ext[0][1][i >> 5] = mn0;
+      s_ext[1][0][i >> 5] = mx1, s_ext[1][1][i >> 5] = mn1;
+    }
+  }
   __syncthreads();
+  constexpr float LOG2E = 1.4426950408889634f;
   const float qs[2] = {vq / 16.0f, bq / 16.0f};
   float res[2];
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
     const float q = qs[d];
-    float m = -INFINITY;
-    for (int j = 0; j < 256; ++j) m = fmaxf(m, q * sk[d][j]);
+    float kmax = s_ext[d][0][0], kmin = s_ext[d][1][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) kmax = fmaxf(kmax, s_ext[d][0][w]), kmin = fminf(kmin, s_ext[d][1][w]);
+    const float ql = q * LOG2E;                         // softmax in base 2: exp(x - m) = 2^(x*log2e - m*log2e)
+    const float ml = ql * (q >= 0.f ? kmax : kmin);
     float sum = 0.f, acc = 0.f;
-    for (int j = 0; j < 256; ++j) {
-      const float p = expf(q * sk[d][j] - m);
-      sum += p;
-      acc = fmaf(p, sv[d][j], acc);
+#pragma unroll 4
+    for (int j = 0; j < 256; j += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(&sk[d][j]);
+      const float4 v4 = *reinterpret_cast<const float4*>(&sv[d][j]);
+      const float p0 = ex2_approx(fmaf(ql, k4.x, -ml)), p1 = ex2_approx(fmaf(ql, k4.y, -ml));
+      const float p2 = ex2_approx(fmaf(ql, k4.z, -ml)), p3 = ex2_approx(fmaf(ql, k4.w, -ml));
+      sum += (p0 + p1) + (p2 + p3);
+      acc = fmaf(p0, v4.x, fmaf(p1, v4.y, fmaf(p2, v4.z, fmaf(p3, v4.w, acc))));
     }
     res[d] = acc / sum + sv[d][i];
   }
@@ -433,7 +478,7 @@ __global__ void __launch_bounds__(256) intertask_kernel(const float* __restrict_
 
 void launch_intertask(const float* qkv, float* out, const double* meas, int B, int ld_out,
                       cudaStream_t stream) {
-  intertask_kernel<<<B, 256, 0, stream>>>(qkv, out, meas, B, ld_out);
+  launch_k(intertask_kernel, dim3(B), dim3(256), 0, stream, qkv, out, meas, B, ld_out);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

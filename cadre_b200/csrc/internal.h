@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <stdexcept>
 #include <string>
@@ -29,26 +30,31 @@ using enc_t = __nv_bfloat16;
 __device__ __forceinline__ enc_t enc_from_float(float f) { return __float2bfloat16_rn(f); }
 __device__ __forceinline__ float enc_to_float(enc_t h) { return __bfloat162float(h); }
 #endif
-// two floats -> one packed 32-bit word with a single cvt.rn.f16x2 (values clamped to the finite fp16 range)
+// two floats -> one packed 32-bit word, clamped to the finite fp16 range: ONE instruction on sm_100a
+// (F2FP.SATFINITE[.RELU].F16.F32.PACK_AB) instead of clamp + clamp (+ max) + convert per value
 __device__ __forceinline__ uint32_t enc_pack2(float a, float b) {
 #if CADRE_ENC_FP16
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // a -> low half
+  return r;
 #else
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-#endif
   return *reinterpret_cast<uint32_t*>(&h);
+#endif
 }
-// same for values already known to be >= 0 (post-ReLU): one clamp instead of two
-__device__ __forceinline__ uint32_t enc_pack2_pos(float a, float b) {
+// pack(max(a, 0), max(b, 0)): the ReLU rides in the conversion
+__device__ __forceinline__ uint32_t enc_pack2_relu(float a, float b) {
 #if CADRE_ENC_FP16
-  __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 #else
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-#endif
+  __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
   return *reinterpret_cast<uint32_t*>(&h);
+#endif
 }
+// values already known to be >= 0
+__device__ __forceinline__ uint32_t enc_pack2_pos(float a, float b) { return enc_pack2(a, b); }
 
 struct Error : public std::runtime_error {
   int code;
@@ -163,6 +169,23 @@ struct OptTables {
   float* clip_coef = nullptr;      // [16]
   float* norms = nullptr;          // [16]
 };
+// Launch with the programmatic-stream-serialization attribute (PDL, see ptx.cuh): all kernels of the library
+// call pdl_wait() before touching global memory, so consecutive launches overlap prologue and launch latency
+// with the predecessor's tail. CADRE_NO_PDL=1 restores plain stream order (A/B switch).
+bool pdl_enabled();
+extern long long* g_dbg_clk;
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
                       float lr, float beta1, float beta2, float eps, int step, cudaStream_t s);
 

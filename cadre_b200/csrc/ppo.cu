@@ -12,6 +12,7 @@
 // weight gradients of all eight steps are single GEMMs over K = 9*rows: dW_ih = dG9^T X9, dW_hh = dG9^T H9.
 #include "../../include/cadre_b200.h"
 #include "internal.h"
+#include "ptx.cuh"
 #include "ppo_layout.h"
 
 #include <algorithm>
@@ -40,6 +41,8 @@ __global__ void __launch_bounds__(1024) route_kernel(const StorageRef* __restric
                                                      const int* __restrict__ idx, int W, int mb,
                                                      int* __restrict__ row_slot, int* __restrict__ row_expert,
                                                      int* __restrict__ counts, int* __restrict__ counts9) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int base[4];
   __shared__ int wcnt[32][4];
   const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,6 +101,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
                                                    const int* __restrict__ row_expert, float* __restrict__ X9,
                                                    float* __restrict__ H9, float* __restrict__ C9,
                                                    RowScalars sc) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, h = blockIdx.y, R = W * mb;
   const int w = r / mb, i = r - w * mb;
   const StorageRef ref = refs[w * 2 + h];
@@ -128,6 +133,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
 
 __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
                             int n) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
 }
@@ -151,6 +158,8 @@ constexpr int HEAD_ROWS_PER_CTA = 64;
 constexpr int DGRAD_SPLIT = 4;  // split-K factor of the recurrent dgrad GEMMs (K = 2120)
 
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.y, head = e >> 2;
   const int A = head == 0 ? 33 : 3;
   const int count = p.counts[e];
@@ -322,6 +331,8 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const float* __restrict_
                                                         const int* __restrict__ row_expert,
                                                         const int* __restrict__ actions_by_row, int R, int cap,
                                                         float* __restrict__ row_out) {
+  pdl_trigger();
+  pdl_wait();
   // one warp per (head, row r); r enumerates (worker, i) like the gather
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * 8 + warp;
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ C9, float* __restrict__ dG9,
                                                        const int* __restrict__ counts, int cap, int t,
                                                        int first, int nsplit, long long split_stride) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.y;
   const int count = counts[e];
   const int rows_pad = min(cap, (count + 31) & ~31);
@@ -401,6 +414,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
                                                      long long src_bs, const int* __restrict__ rows, int N,
                                                      float* __restrict__ dst, long long dst_bs,
                                                      float* __restrict__ dst2) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[8][33];
   const int e = blockIdx.y;
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -552,11 +567,11 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   int n = 0;
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, idx_host, sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s));
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, refs_host, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
-  route_kernel<<<2, 1024, 0, s>>>(P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
+  launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
                                   P->counts9), ++n;
-  pack_kernel<<<dim3(R, 2), 256, 0, s>>>(P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
+  launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
                                          P->X9, P->H9, P->C9, P->sc), ++n;
-  add2_kernel<<<(E * G + 255) / 256, 256, 0, s>>>(params + OFF_BIH, params + OFF_BHH, P->bsum, E * G), ++n;
+  launch_k(add2_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
   // ---- forward
@@ -618,7 +633,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     hp.losses = losses, hp.cap = cap, hp.inv_mb = 1.f / static_cast<float>(mb);
     hp.clip = P->cfg.clip, hp.value_coeff = P->cfg.value_coeff, hp.clip_coeff = P->cfg.clip_coeff;
     hp.ent_coeff = P->cfg.ent_coeff;
-    head_kernel<<<dim3(cap / HEAD_ROWS_PER_CTA, E), 256, 0, s>>>(hp), ++n;
+    launch_k(head_kernel, dim3(dim3(cap / HEAD_ROWS_PER_CTA, E)), dim3(256), 0, s, hp), ++n;
     CADRE_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -645,9 +660,9 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
       launch_gemm(g, s), ++n;
     }
   }
-  colsum_kernel<<<dim3(8, E), 256, 0, s>>>(P->dZ2, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B2, 2 * HID,
+  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s, P->dZ2, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B2, 2 * HID,
                                            nullptr), ++n;
-  colsum_kernel<<<dim3(8, E), 256, 0, s>>>(P->dZ1, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B1, 2 * HID,
+  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s, P->dZ1, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B1, 2 * HID,
                                            nullptr), ++n;
   {  // dW1 = dZ1^T h_8
     GemmArgs g = tf32_gemm(1, 1);
@@ -670,7 +685,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   const unsigned bwd_blocks = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
   const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
   for (int t = 7; t >= 0; --t) {
-    lstm_bwd_kernel<<<dim3(bwd_blocks, E), 256, 0, s>>>(P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
+    launch_k(lstm_bwd_kernel, dim3(dim3(bwd_blocks, E)), dim3(256), 0, s, P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
                                                         t == 7, t == 7 ? 1 : DGRAD_SPLIT, dh_split_stride),
         ++n;
     if (t > 0) {  // dh_{t-1} = dG_t W_hh
@@ -694,7 +709,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.batch_rows = P->counts9, g.rows_is_k = 1;
     launch_gemm(g, s), ++n;
   }
-  colsum_kernel<<<dim3((G + 31) / 32, E), 256, 0, s>>>(P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
+  launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
                                                        grads + OFF_BHH), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
   P->launches = n;
@@ -751,7 +766,7 @@ int cadre_ppo_evaluate(void* handle, const cadre_storage_ref* storages_host, con
   CADRE_REQUIRE(P && storages_host && indices_host && params && row_out, "ppo_evaluate pointers");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int n = cadre::ppo_forward(P, storages_host, indices_host, params, s);
-  cadre::head_eval_kernel<<<(2 * P->R + 7) / 8, 256, 0, s>>>(P->Y2, params, P->row_slot, P->row_expert,
+  cadre::launch_k(cadre::head_eval_kernel, dim3((2 * P->R + 7) / 8), dim3(256), 0, s, P->Y2, params, P->row_slot, P->row_expert,
                                                              P->sc.action, P->R, P->cap, row_out);
   CADRE_CUDA_CHECK(cudaGetLastError());
   P->launches = n + 1;

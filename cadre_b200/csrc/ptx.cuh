@@ -45,6 +45,27 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ---------------------------------------------------------------- TMA loads (tile mode)
+// Programmatic dependent launch (PDL): every kernel of the library starts with pdl_trigger() so that the next
+// launch in the stream may be scheduled as soon as this grid's CTAs are all resident / retiring, and executes
+// pdl_wait() before its first access to global memory a predecessor may have written (or may still read).
+// One lane of a CONVERGED warp. The MMA / TMA roles run with the whole warp converged and issue through
+// `if (elect_one())`: with a divergent `lane == 0` branch instead, ptxas wraps every tcgen05.mma in an
+// ELECT / R2UR / BRA.U.ANY sequence (~14 instructions, ~75 cycles per MMA on B200), which made instruction
+// issue the bottleneck of all kernels whose MMA runs for less than that (N = 64, N = 128).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

@@ -2,6 +2,7 @@
 // norm + fused clip + Adam over the flat parameter buffer.
 #include "../../include/cadre_b200.h"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace cadre {
 
@@ -18,6 +19,8 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewa
                                                   const float* __restrict__ next_value,
                                                   float* __restrict__ returns, float* __restrict__ adv, int E,
                                                   int T, float gamma, float tau, int normalize) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float gsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -102,6 +105,8 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
                                                              const long long* __restrict__ chunk_off,
                                                              const int* __restrict__ chunk_len,
                                                              float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   const long long off = chunk_off[blockIdx.x];
   const int len = chunk_len[blockIdx.x];
   const float4* g4 = reinterpret_cast<const float4*>(g + off);
@@ -123,6 +128,8 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
 
 __global__ void sqnorm_final_kernel(const float* __restrict__ partial, const int* __restrict__ mod_first,
                                     float max_norm, float* __restrict__ clip_coef, float* __restrict__ norms) {
+  pdl_trigger();
+  pdl_wait();
   // one warp per module; chunks of a module are contiguous in the chunk table
   const int m = blockIdx.x, lane = threadIdx.x;
   double s = 0.0;
@@ -143,6 +150,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const float* __restrict__ clip_coef, float beta1,
                                                    float beta2, float eps, float step_size,
                                                    float bc2_sqrt) {
+  pdl_trigger();
+  pdl_wait();
   const long long off = chunk_off[blockIdx.x];
   const int len = chunk_len[blockIdx.x];
   const float coef = clip_coef[chunk_mod[blockIdx.x]];
@@ -170,12 +179,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
                       float lr, float beta1, float beta2, float eps, int step, cudaStream_t s) {
-  sqnorm_partial_kernel<<<t.num_chunks, 256, 0, s>>>(grads, t.chunk_off, t.chunk_len, t.partial);
-  sqnorm_final_kernel<<<16, 32, 0, s>>>(t.partial, t.mod_first, max_norm, t.clip_coef, t.norms);
+  launch_k(sqnorm_partial_kernel, dim3(t.num_chunks), dim3(256), 0, s, grads, t.chunk_off, t.chunk_len, t.partial);
+  launch_k(sqnorm_final_kernel, dim3(16), dim3(32), 0, s, t.partial, t.mod_first, max_norm, t.clip_coef, t.norms);
   // torch.optim.Adam: step_size = lr / (1 - beta1^step); denom = sqrt(v) / sqrt(1 - beta2^step) + eps
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  adam_kernel<<<t.num_chunks, 256, 0, s>>>(params, grads, m, v, t.chunk_off, t.chunk_len, t.chunk_mod,
+  launch_k(adam_kernel, dim3(t.num_chunks), dim3(256), 0, s, params, grads, m, v, t.chunk_off, t.chunk_len, t.chunk_mod,
                                            t.clip_coef, beta1, beta2, eps, static_cast<float>(lr / bc1),
                                            static_cast<float>(sqrt(bc2)));
   CADRE_CUDA_CHECK(cudaGetLastError());
@@ -214,7 +223,7 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
                                           static_cast<int>(smem)));
     configured = smem;
   }
-  cadre::gae_kernel<<<(E + warps - 1) / warps, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  cadre::launch_k(cadre::gae_kernel, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream), 
       rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
   CADRE_CUDA_CHECK(cudaGetLastError());
   CADRE_API_END

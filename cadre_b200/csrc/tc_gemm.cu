@@ -88,7 +88,7 @@ static void launch_inst(const TcGemmParams& p, dim3 grid, cudaStream_t stream) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, 192, smem, stream>>>(p);
+  launch_k(kern, dim3(grid), dim3(192), smem, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -101,6 +101,13 @@ static int num_sms() {
   }
   return n;
 }
+long long* g_dbg_clk = nullptr;   // cadre_debug_clk: per-CTA cycle counters of the flat / stem kernels
+
+bool pdl_enabled() {
+  static const bool on = getenv("CADRE_NO_PDL") == nullptr;
+  return on;
+}
+
 static const bool g_use_v1 = getenv("CADRE_CONV_V1") != nullptr;  // A/B switch: non-persistent encoder kernels
 
 // CTA-pair variant (cta_group::2): clusters of two CTAs, one 256 x BN tile per pair
@@ -119,10 +126,12 @@ static void launch_persist2(const PersistParams& p, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
 }
 
@@ -137,7 +146,7 @@ static void launch_persist(const PersistParams& p, cudaStream_t stream) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 320, smem, stream>>>(p);
+  launch_k(kern, dim3(grid), dim3(320), smem, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -160,7 +169,7 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const int es = a.kind ? 4 : 2;
   const int bk = 128 / es;
   int bn = a.block_n ? a.block_n : (a.N <= 64 ? 64 : 128);
-  if (!g_use_v1 && a.kind == 0 && !a.a_mn && !a.b_mn && a.batch == 1 && !a.out_f32 && a.epi == 0 && !a.mask &&
+  if (!g_use_v1 && a.K > 0 && a.kind == 0 && !a.a_mn && !a.b_mn && a.batch == 1 && !a.out_f32 && a.epi == 0 && !a.mask &&
       !a.batch_rows && a.alpha == 1.f && a.N % 8 == 0) {
     PersistParams q;
     memset(&q, 0, sizeof(q));
@@ -343,6 +352,7 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
   make_map(&p.tmX, 2, 2, a.in, dims, str, box_a);
   make_map(&p.tmX2, 2, 2, a.in, dims, str, box_b);
   make_map(&p.tmY, 2, 2, a.out, dims, str, box_b);
+  if (a.res) make_map(&p.tmR, 2, 2, a.res, dims, str, box_b);
   const uint64_t wdims[2] = {576, 64};
   const uint64_t wstr[1] = {576 * 2};
   const uint32_t wbox[2] = {64, 64};
@@ -350,13 +360,14 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
   p.P = static_cast<int>(P), p.H = a.H, p.W = a.W, p.PW = PW;
   p.num_tiles = static_cast<int>((P + 127) / 128);
   p.bias = a.bias, p.res = a.res, p.act = a.act;
+  p.dbg = g_dbg_clk ? g_dbg_clk + (a.res ? 2 : 1) * 148 * 16 : nullptr;  // region 0: stem, 1: conv, 2: conv + residual
   static bool configured = false;
   if (!configured) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  tc_flat3x3_kernel<<<grid, 320, FLAT_SMEM, stream>>>(p);
+  launch_k(tc_flat3x3_kernel, dim3(grid), dim3(320), FLAT_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -415,13 +426,14 @@ void launch_stem_pool(const StemArgs& a, cudaStream_t stream) {
   p.bias = a.bias, p.out = a.out, p.B = a.B;
   p.pool_rows = 12;
   p.num_units = a.B * (36 / p.pool_rows);
+  p.dbg = g_dbg_clk;
   static bool configured = false;
   if (!configured) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
     configured = true;
   }
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  tc_stem_pool_kernel<<<grid, 320, SP_SMEM, stream>>>(p);
+  launch_k(tc_stem_pool_kernel, dim3(grid), dim3(320), SP_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

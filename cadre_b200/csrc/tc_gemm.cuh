@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+  pdl_trigger();
+  pdl_wait();   // batch_rows / bias below may have been written by the previous launch (route kernel, Adam)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y;
   const int ks = p.ksplit > 1 ? static_cast<int>(blockIdx.z) % p.ksplit : 0;
@@ -144,12 +146,13 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
   const uint32_t tmem_base = *tmem_slot;
   if (clk && threadIdx.x == 0) clk[1] = clock64();
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp, elected lane)
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
       mbar_expect_tx(&full[s], S::STAGE_BYTES);
       uint8_t* a_s = smem + s * S::STAGE_BYTES;
       uint8_t* b_s = a_s + S::A_BYTES;
@@ -175,9 +178,11 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       } else {
         tma_load_3d(b_s, &p.tmB, &full[s], (kb0 + kb) * BK, n0, batch);
       }
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
     constexpr uint32_t idesc = umma_idesc(KIND ? 2u : (CADRE_ENC_FP16 ? 0u : 1u), A_MN, B_MN, 128, BLOCK_N);
     constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : 32;
     constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : 32;
@@ -191,9 +196,10 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      if (clk && kb == 0) clk[2] = clock64();
+      if (clk && kb == 0 && lane == 0) clk[2] = clock64();
       const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
       const uint32_t b_addr = a_addr + S::A_BYTES;
+      if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
         uint64_t da = umma_smem_desc(a_addr + k * A_KSTEP + p.dbg_a_shift * 128, A_LBO, A_SBO, A_LAYOUT);
@@ -205,9 +211,11 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           tc_mma_f16(tmem_base, da, db, idesc, (kb | k) != 0);
       }
       tc_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+      if (kb == num_kb - 1) tc_commit(tmem_full);
+      }
+      __syncwarp();
     }
-    tc_commit(tmem_full);
-    if (clk) clk[3] = clock64();
+    if (clk && lane == 0) clk[3] = clock64();
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue
     // Phase 1 (row per thread, the TMEM access pattern): accumulator -> registers -> padded smem staging tile.

@@ -53,6 +53,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -131,6 +134,7 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 // the B-operand shared-memory traffic (TMA write + UMMA read), which is what bounds the 1-CTA kernel.
 template <int BLOCK_N, int STAGES, int MODE, bool CTA2 = false>
 __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constant__ PersistParams p) {
+  pdl_trigger();
   constexpr int BK = 64, UMMA_K = 16, NCH = BLOCK_N / 64;
   using S = PersistSmem<BLOCK_N, STAGES, CTA2>;
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // nothing above reads or writes global memory
 
   auto tile_origin = [&](int tile, int& m_tile, int& n0, int& img0, int& h0) {
     const int n_tile = tile / tiles_m_sched;
@@ -193,8 +198,8 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
     }
   };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp, elected lane)
     int it = 0;  // global k-block counter across tiles
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
       int m_tile, n0, img0, h0;
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* a_s = smem + s * S::STAGE_BYTES;
         uint8_t* b_s = a_s + S::A_BYTES;
+        if (elect_one()) {
         if constexpr (CTA2) {
           // both CTAs load into their own smem; all bytes are accounted on the LEADER's full barrier
           if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
@@ -231,10 +237,14 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           }
           tma_load_3d(b_s, &p.tmB, &full[s], kb * BK, n0, 0);
         }
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+  } else if (warp == 1) {
+    if (rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of a pair;
+    // converged warp, elected lane)
     constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, CTA2 ? 256 : 128, BLOCK_N);
     int it = 0, lt = 0;
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++lt) {
@@ -250,18 +260,24 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
-          const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
-          if constexpr (CTA2)
-            tc_mma_f16_2sm(tacc, da, db, idesc, (kb | k) != 0);
-          else
-            tc_mma_f16(tacc, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
+            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
+            if constexpr (CTA2)
+              tc_mma_f16_2sm(tacc, da, db, idesc, (kb | k) != 0);
+            else
+              tc_mma_f16(tacc, da, db, idesc, (kb | k) != 0);
+          }
+          if constexpr (CTA2) tc_commit_2sm(&empty[s]); else tc_commit(&empty[s]);
+          if (kb == p.num_kb - 1) {
+            if constexpr (CTA2) tc_commit_2sm(&tfull[as]); else tc_commit(&tfull[as]);
+          }
         }
-        if constexpr (CTA2) tc_commit_2sm(&empty[s]); else tc_commit(&empty[s]);
+        __syncwarp();
       }
-      if constexpr (CTA2) tc_commit_2sm(&tfull[as]); else tc_commit(&tfull[as]);
+    }
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter;
@@ -298,6 +314,7 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
       // prefetch this thread's residual half-row while the MMAs of the tile are still in flight
       uint4 rres[HC / 8];
       const bool has_res = p.res != nullptr;
+      const bool relu_at_pack = p.act == ACT_RELU && !(has_res && p.res_after_act);
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_row * p.ldr + n0 + cbase);
 #pragma unroll
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
           }
-          if (p.act == ACT_RELU) {
+          if (p.act == ACT_RELU && !relu_at_pack) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           } else if (p.act == ACT_LEAKY) {
@@ -355,8 +372,13 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           const int g = (col + 8 * j) >> 6;
           const int chunk = ((col + 8 * j) & 63) >> 3;
           uint4 u;
-          u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
-          u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
+          if (relu_at_pack) {   // ReLU folded into the fp16 conversion
+            u.x = enc_pack2_relu(v[0], v[1]), u.y = enc_pack2_relu(v[2], v[3]);
+            u.z = enc_pack2_relu(v[4], v[5]), u.w = enc_pack2_relu(v[6], v[7]);
+          } else {
+            u.x = enc_pack2(v[0], v[1]), u.y = enc_pack2(v[2], v[3]);
+            u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
+          }
           *reinterpret_cast<uint4*>(out_s + g * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
         }
       }

@@ -20,9 +20,10 @@ struct StemPoolParams {
   enc_t* out;        // [B][38][66][64] zero-bordered
   int B, pool_rows;  // pooled rows per unit (divides 36)
   int num_units;
+  long long* dbg;    // optional per-CTA cycle counters [16] (cadre_debug_clk), nullptr in production
 };
 
-constexpr int SP_RING = 6;                                 // A tiles in flight (>= 4 live + prefetch)
+constexpr int SP_RING = 8;                                 // A tiles in flight (>= 4 live + prefetch)
 constexpr int SP_A_BYTES = 128 * 128;
 constexpr int SP_W_BYTES = 4 * 64 * 128;
 constexpr int SP_ROW_BYTES = 128 * 128;                    // one conv row: 128 px x 64 ch fp16
@@ -31,6 +32,7 @@ constexpr int SP_SMEM = SP_RING * SP_A_BYTES + SP_W_BYTES + 3 * SP_ROW_BYTES + 3
 __device__ __forceinline__ void sp_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_constant__ StemPoolParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_s = smem;                                   // SP_RING x 16 KB
@@ -78,10 +80,14 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     c1 = 2 * (r0 + p.pool_rows - 1) + 1;
   };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
-    mbar_expect_tx(w_full, SP_W_BYTES);
-    for (int j = 0; j < 4; ++j) tma_load_2d(w_s + j * 8192, &p.tmW, w_full, j * 64, 0);
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (converged warp, elected lane)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, SP_W_BYTES);
+      for (int j = 0; j < 4; ++j) tma_load_2d(w_s + j * 8192, &p.tmW, w_full, j * 64, 0);
+    }
+    __syncwarp();
+    pdl_wait();   // weights / bias are never written by a stream predecessor; the packed input is
     int seq = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
@@ -89,30 +95,41 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
       for (int rp = c0; rp <= c1 + 3; ++rp, ++seq) {
         const int slot = seq % SP_RING;
         const uint32_t ph = (seq / SP_RING) & 1;
+        const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&a_empty[slot], ph ^ 1);
-        mbar_expect_tx(&a_full[slot], SP_A_BYTES);
-        tma_load_4d(a_s + slot * SP_A_BYTES, &p.tmX, &a_full[slot], 0, 0, rp, img);
+        if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 1] += clock64() - t0;
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[slot], SP_A_BYTES);
+          tma_load_4d(a_s + slot * SP_A_BYTES, &p.tmX, &a_full[slot], 0, 0, rp, img);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
     constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 64);
     mbar_wait(w_full, 0);
     const uint32_t w_addr = smem_u32(w_s), a_addr0 = smem_u32(a_s);
     int seq0 = 0;   // sequence number of tile rp == c0 of the current unit
     int waited = 0; // tiles [.., waited) have been observed full
     int lt = 0;     // conv rows issued (accumulator ring position)
+    long long d_te = 0, d_wf = 0, d_is = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
       unit_rows(unit, img, r0, c0, c1);
       for (int oh = c0; oh <= c1; ++oh, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
+        const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty[as], aph ^ 1);
+        const long long t1 = p.dbg ? clock64() : 0;
         const int need = seq0 + (oh - c0) + 4;  // tiles oh .. oh+3 must have landed
         for (; waited < need; ++waited) mbar_wait(&a_full[waited % SP_RING], (waited / SP_RING) & 1);
+        const long long t2 = p.dbg ? clock64() : 0;
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * 64;
+        if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int slot = (seq0 + (oh - c0) + j) % SP_RING;
@@ -126,13 +143,23 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
         // tile rp == oh is not needed by later conv rows
         tc_commit(&a_empty[(seq0 + (oh - c0)) % SP_RING]);
         tc_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (p.dbg) d_te += t1 - t0, d_wf += t2 - t1, d_is += clock64() - t2;
       }
       // the last three tiles of the unit (rp = c1+1 .. c1+3) are released with the unit's last row
-      for (int j = 1; j <= 3; ++j) tc_commit(&a_empty[(seq0 + (c1 - c0) + j) % SP_RING]);
+      if (elect_one())
+        for (int j = 1; j <= 3; ++j) tc_commit(&a_empty[(seq0 + (c1 - c0) + j) % SP_RING]);
+      __syncwarp();
       seq0 += (c1 - c0) + 4;
+    }
+    if (p.dbg && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[2] += d_te, d[3] += d_wf, d[4] += d_is, d[5] += clock64() - tstart, d[10] += lt;
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter
+    pdl_wait();
     const int ew = warp - 2;            // 0..7
     const int q = warp & 3;             // TMEM lane quarter
     const int half = ew >> 2;           // which 32 of the 64 channels
@@ -148,7 +175,10 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
       for (int oh = c0; oh <= c1; ++oh, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
+        const bool dbgl = p.dbg && et == 0;
+        const long long e0 = dbgl ? clock64() : 0;
         mbar_wait(&tfull[as], aph);
+        const long long e1 = dbgl ? clock64() : 0;
         tc_fence_after();
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + as * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
@@ -162,14 +192,16 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
         for (int j = 0; j < 4; ++j) {
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + bias_r[8 * j + i], 0.f);
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + bias_r[8 * j + i];
           uint4 u;
-          u.x = enc_pack2_pos(v[0], v[1]), u.y = enc_pack2_pos(v[2], v[3]);
-          u.z = enc_pack2_pos(v[4], v[5]), u.w = enc_pack2_pos(v[6], v[7]);
+          u.x = enc_pack2_relu(v[0], v[1]), u.y = enc_pack2_relu(v[2], v[3]);
+          u.z = enc_pack2_relu(v[4], v[5]), u.w = enc_pack2_relu(v[6], v[7]);
           const int chunk = half * 4 + j;
           *reinterpret_cast<uint4*>(rowp + ((chunk ^ (px & 7)) << 4)) = u;
         }
         sp_epi_bar();
+        const long long e2 = dbgl ? clock64() : 0;
+        if (dbgl) p.dbg[blockIdx.x * 16 + 7] += e1 - e0, p.dbg[blockIdx.x * 16 + 8] += e2 - e1;
         if ((oh & 1) && ((oh - 1) >> 1) >= r0) {  // (the unit's halo row above r0 only feeds pooled row r0)
           // pooled row r = (oh-1)/2 from conv rows oh-2 (absent for r == 0), oh-1, oh; 64 px x 8 chunks
           const int r = (oh - 1) >> 1;
@@ -179,9 +211,15 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
           for (int it = 0; it < 2; ++it) {
             const int item = et + it * 256;      // 0..511
             const int pw = item >> 3, chunk = item & 7;
-            float m[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = 0.f;  // post-ReLU values are >= 0, so 0 acts as the -inf padding
+            // max over the 3x3 window on packed pairs (4 HMNMX2 per 16 bytes); post-ReLU values are >= 0,
+            // so 0 acts as the -inf padding
+#if CADRE_ENC_FP16
+            typedef __half2 enc2_t;
+#else
+            typedef __nv_bfloat162 enc2_t;
+#endif
+            uint4 o = make_uint4(0, 0, 0, 0);
+            enc2_t* m2 = reinterpret_cast<enc2_t*>(&o);
             for (int y = ylo; y <= oh; ++y) {
               const uint8_t* yrow = row_s + (y % 3) * SP_ROW_BYTES;
 #pragma unroll
@@ -189,17 +227,15 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
                 const int x = 2 * pw + dx;
                 if (x < 0) continue;
                 const uint4 u = *reinterpret_cast<const uint4*>(yrow + x * 128 + ((chunk ^ (x & 7)) << 4));
-                const enc_t* h = reinterpret_cast<const enc_t*>(&u);
+                const enc2_t* h2 = reinterpret_cast<const enc2_t*>(&u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], enc_to_float(h[i]));
+                for (int i = 0; i < 4; ++i) m2[i] = __hmax2(m2[i], h2[i]);
               }
             }
-            uint4 o;
-            o.x = enc_pack2_pos(m[0], m[1]), o.y = enc_pack2_pos(m[2], m[3]);
-            o.z = enc_pack2_pos(m[4], m[5]), o.w = enc_pack2_pos(m[6], m[7]);
             *reinterpret_cast<uint4*>(orow + pw * 64 + chunk * 8) = o;
           }
           sp_epi_bar();  // the ring slot of row oh-2 is overwritten by conv row oh+1
+          if (dbgl) p.dbg[blockIdx.x * 16 + 9] += clock64() - e2;
         }
       }
     }

@@ -77,6 +77,10 @@ int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const vo
 
 /* Halo-reuse 3x3 / stride 1 / pad 1 convolution, 64 -> 64 channels (ResNet layer1), on zero-bordered
  * activations: in / res / out are [B][H+2][W+2][64] enc16 with zero borders (kept zero by the kernel). */
+/* Debug: per-CTA cycle counters ([grid][16] int64, device memory) filled by the layer1 / stem kernels while
+ * the pointer is set; pass NULL to switch off. Not part of the reference interface. */
+int cadre_debug_clk(long long* dev_counters);
+
 int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
                          int act, void* out, void* stream);
 

@@ -9,12 +9,18 @@ namespace cadre {
 // ---------------------------------------------------------------------------------------------------------
 // RolloutStorage.compute_returns (ppo_agent/storage.py:68-76, GAE branch) + advantage normalisation
 // (ppo_agent/train.py:82-88). One warp per (env, head) sequence; the reverse-time recurrence
-//   A_t = (r_t + g V_{t+1} m_t - V_t) + g*tau*m_t * A_{t+1}
+//   A_t = delta_t + a_t * A_{t+1},   delta_t = r_t + g V_{t+1} m_t - V_t,   a_t = g*tau*m_t
 // is an affine scan: each lane composes its chunk's affine map, the 32 maps are suffix-scanned with shuffles,
-// then every lane replays its chunk. Sequences are staged in shared memory with coalesced loads/stores.
+// then every lane replays its chunk. Global traffic is coalesced and streamed once: 12 B read + 8 B written
+// per step (V is re-read from L2 for the output pass). Only (delta, a) are staged in shared memory -- 8 B per
+// step and warp -- so that ~24 warps per SM keep enough loads in flight to stream HBM.
 __device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
 
-__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+// ITERS = ceil(T / 32) when T <= 32 * ITERS is known at launch (8: T <= 256, 32: T <= 1024): every global load
+// of the sequence is issued before the first use (3 * ITERS independent loads per lane, ~12 KB per warp in
+// flight) and V stays in registers for the output pass. ITERS = 0 is the general loop (V re-read from L2).
+template <int ITERS>
+__global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
                                                   const float* __restrict__ masks,
                                                   const float* __restrict__ next_value,
                                                   float* __restrict__ returns, float* __restrict__ adv, int E,
@@ -25,28 +31,63 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * (blockDim.x >> 5) + warp;
   if (e >= E) return;
-  const int L = skew(T + 1) + 1;
-  float* sr = gsm + warp * 3 * L;
-  float* sv = sr + L;
-  float* sm = sv + L;
+  const int L = skew(T) + 1;
+  float* sd = gsm + warp * 2 * L;   // delta_t, later the raw advantage
+  float* sa_ = sd + L;              // a_t
   const long long base = static_cast<long long>(e) * (T + 1);
-  for (int i = lane; i <= T; i += 32) {
-    sr[skew(i)] = rewards[base + i];
-    sv[skew(i)] = (i == T) ? next_value[e] : values[base + i];
-    sm[skew(i)] = masks[base + i];
+  const float nv = next_value[e];
+  const float gt = gamma * tau;
+  constexpr int NV = ITERS > 0 ? ITERS : 1;
+  float vreg[NV];
+  if constexpr (ITERS > 0) {
+    // batches of <= 16 iterations, LAST batch first (V_{i+1} of a batch's last element lives in the next batch):
+    // 48 loads per lane in flight, r / m registers are recycled, so ~20 warps per SM fit at T = 1024
+    constexpr int HB = ITERS > 16 ? 16 : ITERS;
+#pragma unroll
+    for (int h = ITERS / HB - 1; h >= 0; --h) {
+      float rreg[HB], mreg[HB];
+#pragma unroll
+      for (int kk = 0; kk < HB; ++kk) {
+        const int k = h * HB + kk;
+        const int i = lane + 32 * k;
+        const bool ok = i < T;
+        rreg[kk] = ok ? rewards[base + i] : 0.f;
+        vreg[k] = ok ? values[base + i] : 0.f;
+        mreg[kk] = ok ? masks[base + i] : 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < HB; ++kk) {
+        const int k = h * HB + kk;
+        const int i = lane + 32 * k;
+        // V_{i+1}: the next lane's element, lane 31 takes lane 0's next element, the last step takes next_value
+        const float dn = __shfl_down_sync(0xffffffffu, vreg[k], 1);
+        const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, vreg[k + 1 < ITERS ? k + 1 : k], 0) : nv;
+        float vn = lane < 31 ? dn : wrap;
+        if (i + 1 == T) vn = nv;
+        if (i < T) {
+          sd[skew(i)] = rreg[kk] + gamma * vn * mreg[kk] - vreg[k];
+          sa_[skew(i)] = gt * mreg[kk];
+        }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int i = lane; i < T; i += 32) {
+      const float r = rewards[base + i], v = values[base + i], m = masks[base + i];
+      const float vn = (i + 1 == T) ? nv : values[base + i + 1];   // neighbouring lane's line: L1 hit
+      sd[skew(i)] = r + gamma * vn * m - v;
+      sa_[skew(i)] = gt * m;
+    }
   }
-  if (lane == 0) values[base + T] = next_value[e];  // storage.py:70 value_preds[-1] = next_value
+  if (lane == 0) values[base + T] = nv;  // storage.py:70 value_preds[-1] = next_value
   __syncwarp();
   const int cs = (T + 31) / 32;
-  const int t0 = lane * cs, t1 = min(T, t0 + cs);
+  const int t0 = min(T, lane * cs), t1 = min(T, t0 + cs);
   // chunk map x -> a*x + b (x = gae entering the chunk from later time steps)
   float a = 1.f, b = 0.f;
   for (int t = t1 - 1; t >= t0; --t) {
-    const float m = sm[skew(t)];
-    const float delta = sr[skew(t)] + gamma * sv[skew(t + 1)] * m - sv[skew(t)];
-    const float at = gamma * tau * m;
-    // F_t o F_chunk_so_far : later steps were composed first
-    b = at * b + delta;
+    const float at = sa_[skew(t)];
+    b = at * b + sd[skew(t)];   // F_t o F_chunk_so_far : later steps were composed first
     a = at * a;
   }
   // inclusive suffix composition S_l = F_l o F_{l+1} o ... o F_31
@@ -62,35 +103,53 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewa
   }
   float gae = __shfl_down_sync(0xffffffffu, sb, 1);  // S_{l+1}(0)
   if (lane == 31) gae = 0.f;
-  // replay the chunk; returns_t = gae + V_t, advantage = returns_t - V_t (train.py:82)
-  float lsum = 0.f;
-  for (int t = t1 - 1; t >= t0; --t) {
-    const float m = sm[skew(t)];
-    const float v = sv[skew(t)];
-    const float delta = sr[skew(t)] + gamma * sv[skew(t + 1)] * m - v;
-    gae = delta + gamma * tau * m * gae;
-    const float ret = gae + v;
-    const float ad = ret - v;
-    sr[skew(t)] = ret;  // r_t is dead from here on
-    sm[skew(t)] = ad;   // m_t too
-    lsum += ad;
+  for (int t = t1 - 1; t >= t0; --t) {   // replay the chunk
+    gae = sd[skew(t)] + sa_[skew(t)] * gae;
+    sd[skew(t)] = gae;
   }
   __syncwarp();
+  // returns_t = gae_t + V_t (storage.py:75); advantage_t = returns_t - V_t (train.py:82: the rounding of the
+  // round trip through returns is kept); coalesced, V from L2
+  float lsum = 0.f;
+  if constexpr (ITERS > 0) {
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = lane + 32 * k;
+      if (i < T) {
+        const float v = vreg[k];
+        const float ret = sd[skew(i)] + v;
+        const float ad = ret - v;
+        returns[base + i] = ret;
+        sd[skew(i)] = ad;
+        lsum += ad;
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int i = lane; i < T; i += 32) {
+      const float v = values[base + i];
+      const float ret = sd[skew(i)] + v;
+      const float ad = ret - v;
+      returns[base + i] = ret;
+      sd[skew(i)] = ad;
+      lsum += ad;
+    }
+  }
   float mean = 0.f, denom = 1.f;
   if (normalize) {
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     mean = lsum / static_cast<float>(T);
     float lsq = 0.f;
-    for (int t = t0; t < t1; ++t) {
-      const float d = sm[skew(t)] - mean;
+    for (int i = lane; i < T; i += 32) {
+      const float d = sd[skew(i)] - mean;
       lsq += d * d;
     }
     for (int o = 16; o > 0; o >>= 1) lsq += __shfl_xor_sync(0xffffffffu, lsq, o);
     denom = sqrtf(lsq / static_cast<float>(T - 1)) + 1e-8f;  // torch.std is unbiased; train.py:86
   }
+#pragma unroll 4
   for (int i = lane; i < T; i += 32) {
-    returns[base + i] = sr[skew(i)];
-    const float ad = sm[skew(i)];
+    const float ad = sd[skew(i)];
     adv[static_cast<long long>(e) * T + i] = normalize ? (ad - mean) / denom : ad;
   }
 }
@@ -212,19 +271,20 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   CADRE_API_BEGIN
   CADRE_REQUIRE(rewards && values && masks && next_value && returns && adv, "gae pointers");
   CADRE_REQUIRE(E > 0 && T > 1 && T <= 16384, "gae sizes (1 < T <= 16384)");
-  const int L = (T + 1) + ((T + 1) >> 5) + 1;
-  const size_t per_warp = 3 * static_cast<size_t>(L) * sizeof(float);
-  int warps = 4;
-  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  const int L = T + (T >> 5) + 1;
+  const size_t per_warp = 2 * static_cast<size_t>(L) * sizeof(float);
+  int warps = (T > 256 && T <= 1024) ? 4 : 8;   // the register-resident variant (146 registers) runs 3 x 4 warps per SM
+  while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(cadre::gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(smem)));
-    configured = smem;
+  auto kern = T <= 256 ? cadre::gae_kernel<8> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>);
+  static size_t configured[3] = {0, 0, 0};
+  const int which = T <= 256 ? 0 : (T <= 1024 ? 1 : 2);
+  if (smem > 48 * 1024 && smem > configured[which]) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured[which] = smem;
   }
-  cadre::launch_k(cadre::gae_kernel, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream), 
-      rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
+  cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
+                  rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
   CADRE_CUDA_CHECK(cudaGetLastError());
   CADRE_API_END
 }

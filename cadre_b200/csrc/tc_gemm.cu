@@ -221,11 +221,20 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_GEMM_CASE(0, 1, 1, 128, 4, EPI_LINEAR, 1, float)
   // fp32 operands as TF32 (PPO update: forward, dgrad, wgrad, LSTM cell)
   // the PPO GEMMs are latency-bound (few CTAs, short 128-byte k-blocks): deep pipelines, one CTA per SM
-  CADRE_GEMM_CASE(1, 0, 0, 64, 6, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 0, 128, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 1, 128, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 1, 1, 128, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(1, 0, 0, 128, 4, EPI_LSTM, 1, float)
+  static const bool tf32_deep = getenv("CADRE_TF32_DEEP") != nullptr;  // A/B: one CTA per SM, 6-stage pipeline
+  if (tf32_deep) {
+    CADRE_GEMM_CASE(1, 0, 0, 64, 8, EPI_LINEAR, 1, float)
+    CADRE_GEMM_CASE(1, 0, 0, 128, 6, EPI_LINEAR, 1, float)
+    CADRE_GEMM_CASE(1, 0, 1, 128, 6, EPI_LINEAR, 1, float)
+    CADRE_GEMM_CASE(1, 1, 1, 128, 6, EPI_LINEAR, 1, float)
+    CADRE_GEMM_CASE(1, 0, 0, 128, 6, EPI_LSTM, 1, float)
+  }
+  // default: 3 stages (97 KB) -> two CTAs per SM
+  CADRE_GEMM_CASE(1, 0, 0, 64, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 1, 1, 128, 3, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LSTM, 1, float)
 #undef CADRE_GEMM_CASE
   throw Error(1, "launch_gemm: unsupported (kind, majors, block_n, epilogue, out dtype) combination");
 }

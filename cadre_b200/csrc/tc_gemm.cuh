@@ -63,7 +63,11 @@ struct TcGemmSmem {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 128 * (BLOCK_N + 4) * 4;  // fp32 staging tile of the coalesced epilogue
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  // The staging tile ALIASES the operand stages: one tile per CTA, and the epilogue starts after tmem_full, i.e.
+  // after every MMA has read its operands. That leaves room for two CTAs per SM (3 x 32 KB TF32 stages), so one
+  // CTA's prologue / epilogue overlaps the other's main loop.
+  static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
+  static constexpr int TOTAL = DATA_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
 // exp-based gates with the hardware ex2 path (__expf: ~2 ulp) — far inside the TF32 noise of the pre-activations
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::DATA_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
     // per 128x128 fp32 tile on B200, measured with clock64 stamps.)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     constexpr int LDS = BLOCK_N + 4;
-    float* stg = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES) + (q * 32) * LDS;  // this warp's 32 rows
+    float* stg = reinterpret_cast<float*>(smem) + (q * 32) * LDS;  // this warp's 32 rows (aliases the stages)
     if (num_kb > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();

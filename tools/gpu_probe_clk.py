@@ -20,3 +20,17 @@ import statistics
 for i, n in enumerate(names):
     col = d[:, i].tolist()
     print(f"{n:28s} median {statistics.median(col):9.0f} cyc  min {min(col):9.0f} max {max(col):9.0f}")
+# back-to-back timing of the same launch (no stamps)
+g2 = _lib.GemmArgs.from_buffer_copy(g)
+os.environ.pop("CADRE_DBG_CLK", None)
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+for name, gg in (("stamped", g),):
+    for _ in range(5):
+        L.cadre_gemm(ctypes.byref(gg), _lib.stream_ptr())
+    e0.record()
+    for _ in range(50):
+        L.cadre_gemm(ctypes.byref(gg), _lib.stream_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 50 * 1e3
+    print(f"{name}: {us:.1f} us per launch, weights {8*2120*532*4/1e6:.1f} MB -> {8*2120*532*4/us/1e6:.2f} TB/s, {2*8*128*2120*530/us/1e6:.1f} TFLOP/s")

@@ -339,6 +339,27 @@ def run_cadre(args):
              "encoder_frames_per_s": round(n / (ev[0].elapsed_time(ev[1]) * 1e-3)),
              "ppo_samples_per_s": round(WORKERS * T * PPO_EPOCH / (ev[2].elapsed_time(ev[3]) * 1e-3))}
 
+    # ---- the one exchange step of the path: all-reduce(sum) of the flat fp32 gradient, timed alone
+    if world > 1:
+        dist.barrier()
+        for _ in range(3):
+            dist.all_reduce(learner.grads, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        ar0, ar1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        ar0.record()
+        for _ in range(10):
+            dist.all_reduce(learner.grads, op=dist.ReduceOp.SUM)
+        ar1.record()
+        torch.cuda.synchronize()
+        ar = torch.tensor([ar0.elapsed_time(ar1) / 10], device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        nbytes = learner.grads.numel() * 4
+        phase["allreduce"] = {"bytes": nbytes, "ms": round(float(ar.item()), 4),
+                              "algbw_GBps": round(nbytes / (float(ar.item()) * 1e-3) / 1e9, 1),
+                              "busbw_GBps": round(2 * (world - 1) / world * nbytes / (float(ar.item()) * 1e-3) / 1e9, 1),
+                              "per_step": n_upd}
+        learner.grads.zero_()
+
     # ---- per-kernel view (rank 0): encoder launches timed with CUDA events inside the library
     roofline, kernels = None, None
     if rank == 0:

@@ -2,6 +2,7 @@
 // uint8 ingest, max-pool, fused position attention (PAM), fused channel attention (CAM), inter-task attention.
 #include "internal.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace cadre {
 
@@ -397,6 +398,148 @@ void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, co
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
+#if CADRE_ENC_FP16
+// ---------------------------------------------------------------------------------------------------------
+// CAM on tensor cores. The shapes are tiny (128x128x40 gram, 128x40x128 product per frame), so the kernel uses
+// warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate) and keeps the whole chain in registers, flash-attention
+// style: warp w owns channel rows [16w, 16w+16): gram row block (16 n-tiles x 3 k-steps) -> rowmax/rowmin ->
+// exp -> the accumulator fragments ARE the A fragments of the second product (x X, K = 128) -> 1/rowsum ->
+// staged fp32 -> gamma * out + x, coalesced. X is read once from global; both products read it from shared
+// memory with ldmatrix (transposed for the gram: A[m=c][k=p] and B[k=p][n=c] are X^T blocks).
+struct CamMmaSmem {
+  __half x[48][136];   // X[p][c]; rows 40..47 are zero (K / N padding); 272-byte pitch: conflict-free ldmatrix
+  float o[40][132];    // att X, before gamma and the residual
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) cam_mma_kernel(const enc_t* __restrict__ xin, enc_t* __restrict__ out,
+                                                      float gamma, int B, int ldin) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t cam_raw[];
+  CamMmaSmem& s = *reinterpret_cast<CamMmaSmem*>(cam_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (tid < 128) *reinterpret_cast<uint4*>(&s.x[40 + (tid >> 4)][(tid & 15) * 8]) = make_uint4(0, 0, 0, 0);
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    __syncthreads();   // previous frame's readers of s.x / s.o are done
+    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
+      const int p = i >> 4, c8 = (i & 15) * 8;
+      *reinterpret_cast<uint4*>(&s.x[p][c8]) = __ldg(reinterpret_cast<const uint4*>(xf + p * ldin + c8));
+    }
+    __syncthreads();
+    // ---- gram rows [16w, 16w+16): E[a][b] = sum_p X[p][a] X[p][b]
+    float e[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j][0] = e[j][1] = e[j][2] = e[j][3] = 0.f;
+    const int a0 = warp * 16;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int p0 = kk * 16;
+      uint32_t af[4];
+      ldsm_x4_trans(af, &s.x[p0 + (lane & 7) + ((lane >> 4) & 1) * 8][a0 + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+      for (int jp = 0; jp < 8; ++jp) {
+        uint32_t bf[4];
+        ldsm_x4_trans(bf, &s.x[p0 + (lane & 7) + ((lane >> 3) & 1) * 8][jp * 16 + ((lane >> 4) & 1) * 8]);
+        mma_16816(e[2 * jp], af, bf[0], bf[1]);
+        mma_16816(e[2 * jp + 1], af, bf[2], bf[3]);
+      }
+    }
+    // ---- softmax(rowmax - E) (da_att.py:76-77); this thread holds 32 values of rows g (regs 0,1) and g+8 (2,3)
+    float mx[2] = {-INFINITY, -INFINITY}, mn[2] = {INFINITY, INFINITY};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      mx[0] = fmaxf(mx[0], fmaxf(e[j][0], e[j][1])), mn[0] = fminf(mn[0], fminf(e[j][0], e[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(e[j][2], e[j][3])), mn[1] = fminf(mn[1], fminf(e[j][2], e[j][3]));
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+        mn[r] = fminf(mn[r], __shfl_xor_sync(0xffffffffu, mn[r], o));
+      }
+    }
+    // energy_new = mx - e; its row maximum is mx - mn (rounding is monotonic); p = exp(energy_new - max)
+    const float m2[2] = {mx[0] - mn[0], mx[1] - mn[1]};
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      e[j][0] = __expf((mx[0] - e[j][0]) - m2[0]), e[j][1] = __expf((mx[0] - e[j][1]) - m2[0]);
+      e[j][2] = __expf((mx[1] - e[j][2]) - m2[1]), e[j][3] = __expf((mx[1] - e[j][3]) - m2[1]);
+      sum[0] += e[j][0] + e[j][1], sum[1] += e[j][2] + e[j][3];
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+      sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+    }
+    // ---- out[a][p] = sum_b P[a][b] X[p][b]: the C fragments of tiles (2kk, 2kk+1) are the A fragment of k-step kk
+    float oacc[6][4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      uint32_t af[4];
+      af[0] = pack_h2(e[2 * kk][0], e[2 * kk][1]), af[1] = pack_h2(e[2 * kk][2], e[2 * kk][3]);
+      af[2] = pack_h2(e[2 * kk + 1][0], e[2 * kk + 1][1]), af[3] = pack_h2(e[2 * kk + 1][2], e[2 * kk + 1][3]);
+#pragma unroll
+      for (int jp = 0; jp < 3; ++jp) {
+        uint32_t bf[4];
+        ldsm_x4(bf, &s.x[jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8][kk * 16 + ((lane >> 3) & 1) * 8]);
+        mma_16816(oacc[2 * jp], af, bf[0], bf[1]);
+        mma_16816(oacc[2 * jp + 1], af, bf[2], bf[3]);
+      }
+    }
+    const float inv[2] = {1.f / sum[0], 1.f / sum[1]};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {   // n-tile 5 is the zero padding (p = 40..47)
+      const int p = 8 * j + 2 * t;
+      s.o[p][a0 + g] = oacc[j][0] * inv[0], s.o[p + 1][a0 + g] = oacc[j][1] * inv[0];
+      s.o[p][a0 + g + 8] = oacc[j][2] * inv[1], s.o[p + 1][a0 + g + 8] = oacc[j][3] * inv[1];
+    }
+    __syncthreads();
+    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
+      const int p = i >> 4, c8 = (i & 15) * 8;
+      const float4 o_lo = *reinterpret_cast<const float4*>(&s.o[p][c8]);
+      const float4 o_hi = *reinterpret_cast<const float4*>(&s.o[p][c8 + 4]);
+      const uint4 ux = *reinterpret_cast<const uint4*>(&s.x[p][c8]);
+      const __half* hx = reinterpret_cast<const __half*>(&ux);
+      uint4 u;
+      u.x = enc_pack2(gamma * o_lo.x + __half2float(hx[0]), gamma * o_lo.y + __half2float(hx[1]));
+      u.y = enc_pack2(gamma * o_lo.z + __half2float(hx[2]), gamma * o_lo.w + __half2float(hx[3]));
+      u.z = enc_pack2(gamma * o_hi.x + __half2float(hx[4]), gamma * o_hi.y + __half2float(hx[5]));
+      u.w = enc_pack2(gamma * o_hi.z + __half2float(hx[6]), gamma * o_hi.w + __half2float(hx[7]));
+      *reinterpret_cast<uint4*>(of + p * PAM_C + c8) = u;
+    }
+  }
+}
+#endif
+
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
                 cudaStream_t stream) {
   static bool cfg = false;
@@ -405,6 +548,15 @@ void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int nu
                                           static_cast<int>(sizeof(CamSmem))));
     cfg = true;
   }
+#if CADRE_ENC_FP16
+  static const bool fp32_path = getenv("CADRE_CAM_FP32") != nullptr;   // A/B switch: CUDA-core fp32 kernel
+  if (!fp32_path) {
+    const int grid2 = B < 6 * num_sms ? B : 6 * num_sms;
+    launch_k(cam_mma_kernel, dim3(grid2), dim3(256), sizeof(CamMmaSmem), stream, x, out, gamma, B, ldin);
+    CADRE_CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+#endif
   const int grid = B < 2 * num_sms ? B : 2 * num_sms;
   launch_k(cam_kernel, dim3(grid), dim3(256), sizeof(CamSmem), stream, x, out, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());

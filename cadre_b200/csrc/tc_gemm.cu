@@ -200,6 +200,13 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   make_operand_map(&p.tmB, es, a.b_mn, a.B, a.ldb, a.b_bs, a.N, a.K, a.batch, bn);
   p.M = a.M, p.N = a.N, p.num_kb = (a.K + bk - 1) / bk;
   fill_epilogue(p, a);
+  {  // debug: CADRE_DBG_CLK_EPI=<epi>:<device pointer> stamps every GEMM with that epilogue kind (in-situ probe)
+    static const char* spec = getenv("CADRE_DBG_CLK_EPI");
+    static const char* zsel = getenv("CADRE_DBG_CLK_Z");   // optional: only launches with this grid.z
+    const int gz = a.batch * (a.ksplit > 1 ? a.ksplit : 1);
+    if (spec && atoi(spec) == a.epi && strchr(spec, ':') && (!zsel || atoi(zsel) == gz))
+      p.dbg_clk = reinterpret_cast<long long*>(strtoull(strchr(spec, ':') + 1, nullptr, 0));
+  }
   p.ksplit = a.ksplit > 1 ? a.ksplit : 1;
   p.kb_per_split = (p.num_kb + p.ksplit - 1) / p.ksplit;
   p.split_out_stride = a.split_out_stride;

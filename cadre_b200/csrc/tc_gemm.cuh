@@ -389,31 +389,34 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           float* cobase = p.c_out + batch * p.h_bs + u;
           float* hobase = p.h_out + batch * p.h_bs + u;
           const bool zero_rows = (p.batch_rows != nullptr);
+          // 16 rows per batch: all of a batch's global loads (x-part gates, c_{t-1}: HBM latency, the x-part is
+          // 122 MB) are in flight together. With two rows per batch the 16 exposed round trips made this
+          // epilogue 30 k cycles, longer than the GEMM main loop (in-situ clock64 stamps, B200).
+          constexpr int RB = 16;
 #pragma unroll 1
-          for (int rr = 0; rr < 32; rr += 2) {
-            float4 a4[2], x4[2];
-            float cp[2];
-            bool ok[2], wr[2];
+          for (int rr = 0; rr < 32; rr += RB) {
+            float4 x4[RB];
+            float cp[RB];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < RB; ++k) {
               const int m = row_base + rr + k;
-              ok[k] = m < m_valid;
-              wr[k] = ok[k] || (zero_rows && m < p.M);
-              a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
-              x4[k] = ok[k] ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(m) * p.ldx)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-              cp[k] = ok[k] ? cpbase[static_cast<long long>(m) * p.ldh] : 0.f;
+              const bool ok = m < m_valid;
+              x4[k] = ok ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(m) * p.ldx)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+              cp[k] = ok ? cpbase[static_cast<long long>(m) * p.ldh] : 0.f;
             }
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (!wr[k]) continue;
+            for (int k = 0; k < RB; ++k) {
               const long long m = row_base + rr + k;
+              const bool ok = m < m_valid;
+              if (!(ok || (zero_rows && m < p.M))) continue;
               float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
-              if (ok[k]) {
-                gi = sigmoidf_(a4[k].x + x4[k].x);
-                gf = sigmoidf_(a4[k].y + x4[k].y);
-                gg = tanhf_(a4[k].z + x4[k].z);
-                go = sigmoidf_(a4[k].w + x4[k].w);
+              if (ok) {
+                const float4 a4 = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
+                gi = sigmoidf_(a4.x + x4[k].x);
+                gf = sigmoidf_(a4.y + x4[k].y);
+                gg = tanhf_(a4.z + x4[k].z);
+                go = sigmoidf_(a4.w + x4[k].w);
                 cn = fmaf(gf, cp[k], gi * gg);
                 hn = go * tanhf_(cn);
               }

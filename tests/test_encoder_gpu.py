@@ -73,3 +73,30 @@ def test_batch_chunking_is_consistent(encoders):
     full = enc.forward_f32(x)
     part = enc.forward_f32(x[32:].contiguous())
     assert torch.equal(full[32:], part)
+
+
+@pytest.mark.parametrize("tag", ["base", "peaky"])
+def test_attention_stages_match_oracle(encoders, tag):
+    """Intermediate maps of the DA head (danet.py:43-69): layer4, conv5a|conv5c, PAM (fp32 CUDA-core kernel),
+    CAM (tensor-core mma.sync kernel, fp16 attention weights) and their fused sum, against the oracle."""
+    import torch.nn.functional as F  # noqa: F401
+    enc = encoders[tag]
+    sd = R.danet_fixture_state(0, peaky=(tag == "peaky"))
+    B = 5
+    x = torch.from_numpy(np.random.RandomState(3).rand(B, 4, 144, 256).astype(np.float32))
+    enc.forward_f32(x.cuda())
+    with torch.no_grad():
+        l4 = R.backbone(x, sd)
+        f1 = R._conv_bn_relu(l4, sd, "da_head.conv5a")
+        f2 = R._conv_bn_relu(l4, sd, "da_head.conv5c")
+        sa, sc = R.pam(f1, sd), R.cam(f2, sd)
+        fs = R._conv_bn_relu(sa, sd, "da_head.conv51") + R._conv_bn_relu(sc, sd, "da_head.conv52")
+
+    def nhwc(buf, c):
+        return enc.debug_buffer(buf, B).view(B, 5, 8, c).float().cpu().permute(0, 3, 1, 2)
+    assert rel_l2(nhwc(0, 512), l4) < 5e-3
+    h5 = nhwc(2, 256)
+    assert rel_l2(h5[:, :128], f1) < 5e-3 and rel_l2(h5[:, 128:], f2) < 5e-3
+    assert rel_l2(nhwc(3, 128), sa) < REL_FEATURE
+    assert rel_l2(nhwc(4, 128), sc) < 5e-3
+    assert rel_l2(nhwc(1, 128), fs) < REL_FEATURE

@@ -36,6 +36,29 @@ def test_gae_matches_reference_golden(golden_dir, i, T, seed):
     assert v[0, T].item() == pytest.approx(0.37 * (i + 1))      # value_preds[-1] = next_value (storage.py:70)
 
 
+@pytest.mark.parametrize("T", [2, 31, 32, 33, 255, 256, 257, 800, 1023, 1024, 1025, 3000])
+def test_gae_all_kernel_variants_match_oracle(T):
+    """Sequence lengths on both sides of every kernel switch (register-resident <= 256, <= 1024, general loop)
+    and of the 32-lane chunking, with ~10 % episode boundaries; with and without advantage normalisation."""
+    from cadre_b200 import ppo
+    E = 5
+    gen = torch.Generator().manual_seed(T)
+    r = torch.rand(E, T + 1, generator=gen)
+    v = torch.randn(E, T + 1, generator=gen)
+    m = (torch.rand(E, T + 1, generator=gen) > 0.1).float()
+    nv = torch.randn(E, generator=gen)
+    for normalize in (True, False):
+        vd = v.to(DEV).clone()
+        ret, adv = torch.zeros(E, T + 1, device=DEV), torch.zeros(E, T, device=DEV)
+        ppo.gae(r.to(DEV), vd, m.to(DEV), nv.to(DEV), ret, adv, normalize=normalize)
+        for e in range(E):
+            ref_ret, vp = R.compute_returns(r[e].view(-1, 1), v[e].view(-1, 1).clone(), m[e].view(-1, 1), nv[e].view(1, 1))
+            np.testing.assert_allclose(ret[e, :T].cpu().numpy(), ref_ret[:T, 0].numpy(), rtol=1e-5, atol=1e-5)
+            ref_adv = R.normalized_advantages(ref_ret, vp) if normalize else (ref_ret[:-1] - vp[:-1])
+            assert rel(adv[e], ref_adv[:, 0]) < 2e-5
+            assert vd[e, T].item() == pytest.approx(nv[e].item())
+
+
 def test_gae_large_sweep_properties():
     """65 536 sequences x 1 024 steps (1.3 GB): linearity in the rewards and the all-masked closed form."""
     from cadre_b200 import ppo

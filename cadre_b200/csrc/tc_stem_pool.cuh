@@ -27,7 +27,8 @@ constexpr int SP_RING = 8;                                 // A tiles in flight 
 constexpr int SP_A_BYTES = 128 * 128;
 constexpr int SP_W_BYTES = 4 * 64 * 128;
 constexpr int SP_ROW_BYTES = 128 * 128;                    // one conv row: 128 px x 64 ch fp16
-constexpr int SP_SMEM = SP_RING * SP_A_BYTES + SP_W_BYTES + 3 * SP_ROW_BYTES + 32 * 8 + 16 + 1024;
+constexpr int SP_SLOTS = 8;                                // 64-column accumulator slots (conv rows in flight): all of TMEM
+constexpr int SP_SMEM = SP_RING * SP_A_BYTES + SP_W_BYTES + 3 * SP_ROW_BYTES + 48 * 8 + 16 + 1024;
 
 __device__ __forceinline__ void sp_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -41,9 +42,9 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
   uint64_t* a_full = reinterpret_cast<uint64_t*>(row_s + 3 * SP_ROW_BYTES);
   uint64_t* a_empty = a_full + SP_RING;
   uint64_t* w_full = a_empty + SP_RING;
-  uint64_t* tfull = w_full + 1;   // [2]
-  uint64_t* tempty = tfull + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = w_full + 1;          // [SP_SLOTS]
+  uint64_t* tempty = tfull + SP_SLOTS;   // [SP_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + SP_SLOTS);
   __shared__ float s_bias[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -56,14 +57,14 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
       mbar_init(&a_empty[i], 1);
     }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < SP_SLOTS; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 64 * SP_SLOTS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     // ------------------------------------------------------------ TMA producer (converged warp, elected lane)
     if (elect_one()) {
       mbar_expect_tx(w_full, SP_W_BYTES);
-      for (int j = 0; j < 4; ++j) tma_load_2d(w_s + j * 8192, &p.tmW, w_full, j * 64, 0);
+      for (int j = 0; j < 4; ++j) tma_load_2d(w_s + (3 - j) * 8192, &p.tmW, w_full, j * 64, 0);  // W_3 first
     }
     __syncwarp();
     pdl_wait();   // weights / bias are never written by a stream predecessor; the packed input is
@@ -107,55 +108,61 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
-    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 64);
+    // SCATTER form: conv row oh = sum_j A[oh + j] W_j, so A tile rp contributes W_j-wise to the four rows
+    // rp-3 .. rp. With the weights stacked as one [W_3 | W_2 | W_1 | W_0] operand (N = 256) and the rows'
+    // accumulators in CONSECUTIVE 64-column TMEM slots (slot = row mod 8), ONE tcgen05.mma per k-step serves all
+    // four rows: the A tile is read from shared memory once instead of four times, and a 128x256x16 MMA keeps the
+    // tensor pipe busy for 128 cycles where four N = 64 MMAs were operand-read bound (~60 cycles each, measured).
+    // The epilogue hands every slot back ZEROED, so all MMAs accumulate; a slot range that wraps around the ring
+    // is issued as two MMAs, and the first / last tiles of a unit use the sub-range of W blocks whose rows exist.
     mbar_wait(w_full, 0);
     const uint32_t w_addr = smem_u32(w_s), a_addr0 = smem_u32(a_s);
-    int seq0 = 0;   // sequence number of tile rp == c0 of the current unit
-    int waited = 0; // tiles [.., waited) have been observed full
-    int lt = 0;     // conv rows issued (accumulator ring position)
+    int seq = 0;    // A tiles consumed (ring position)
+    int lt0 = 0;    // global index of the unit's first conv row (accumulator ring position)
     long long d_te = 0, d_wf = 0, d_is = 0;
     const long long tstart = p.dbg ? clock64() : 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
       unit_rows(unit, img, r0, c0, c1);
-      for (int oh = c0; oh <= c1; ++oh, ++lt) {
-        const int as = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
+      const int nrows = c1 - c0 + 1;
+      for (int ti = 0; ti < nrows + 3; ++ti, ++seq) {   // tile rp = c0 + ti feeds local rows ti-3 .. ti
+        const int jhi = ti < 3 ? ti : 3;                      // oldest row it feeds: ti - jhi
+        const int jlo = ti > nrows - 1 ? ti - (nrows - 1) : 0;
+        const int first = ti - jhi, cnt = jhi - jlo + 1;      // local rows first .. first+cnt-1 <- blocks 3-jhi ..
         const long long t0 = p.dbg ? clock64() : 0;
-        mbar_wait(&tempty[as], aph ^ 1);
+        if (jlo == 0) {   // row ti is new: its slot must have been drained and zeroed by the epilogue
+          const int lt = lt0 + ti;
+          mbar_wait(&tempty[lt % SP_SLOTS], (lt / SP_SLOTS) & 1);
+        }
         const long long t1 = p.dbg ? clock64() : 0;
-        const int need = seq0 + (oh - c0) + 4;  // tiles oh .. oh+3 must have landed
-        for (; waited < need; ++waited) mbar_wait(&a_full[waited % SP_RING], (waited / SP_RING) & 1);
+        const int aslot = seq % SP_RING;
+        mbar_wait(&a_full[aslot], (seq / SP_RING) & 1);
         const long long t2 = p.dbg ? clock64() : 0;
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * 64;
         if (elect_one()) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int slot = (seq0 + (oh - c0) + j) % SP_RING;
+          const int s0 = (lt0 + first) % SP_SLOTS;
+          const int n1 = cnt < SP_SLOTS - s0 ? cnt : SP_SLOTS - s0;   // rows before the ring wraps
+          const uint32_t b0 = w_addr + (3 - jhi) * 8192;
+          const uint32_t idesc1 = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 64 * n1);
+          const uint32_t idesc2 = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 64 * (cnt - n1));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc(a_addr0 + slot * SP_A_BYTES + k * 32, 16, 1024, 2);
-            const uint64_t db = umma_smem_desc(w_addr + j * 8192 + k * 32, 16, 1024, 2);
-            tc_mma_f16(tacc, da, db, idesc, (j | k) != 0);
+            const uint64_t da = umma_smem_desc(a_addr0 + aslot * SP_A_BYTES + k * 32, 16, 1024, 2);
+            tc_mma_f16(tmem_base + s0 * 64, da, umma_smem_desc(b0 + k * 32, 16, 1024, 2), idesc1, 1);
+            if (cnt > n1)
+              tc_mma_f16(tmem_base, da, umma_smem_desc(b0 + n1 * 8192 + k * 32, 16, 1024, 2), idesc2, 1);
           }
-        }
-        // tile rp == oh is not needed by later conv rows
-        tc_commit(&a_empty[(seq0 + (oh - c0)) % SP_RING]);
-        tc_commit(&tfull[as]);
+          tc_commit(&a_empty[aslot]);
+          if (ti >= 3) tc_commit(&tfull[(lt0 + ti - 3) % SP_SLOTS]);   // row ti-3 has all four contributions
         }
         __syncwarp();
         if (p.dbg) d_te += t1 - t0, d_wf += t2 - t1, d_is += clock64() - t2;
       }
-      // the last three tiles of the unit (rp = c1+1 .. c1+3) are released with the unit's last row
-      if (elect_one())
-        for (int j = 1; j <= 3; ++j) tc_commit(&a_empty[(seq0 + (c1 - c0) + j) % SP_RING]);
-      __syncwarp();
-      seq0 += (c1 - c0) + 4;
+      lt0 += nrows;
     }
     if (p.dbg && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[2] += d_te, d[3] += d_wf, d[4] += d_is, d[5] += clock64() - tstart, d[10] += lt;
+      d[2] += d_te, d[3] += d_wf, d[4] += d_is, d[5] += clock64() - tstart, d[10] += lt0;
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter
@@ -168,21 +175,32 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     float bias_r[32];                   // this thread always handles the same 32 channels
 #pragma unroll
     for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[half * 32 + i];
+    // all accumulator slots start zeroed (TMEM is not cleared by the allocator); this is tempty's phase 0
+    for (int sl = 0; sl < SP_SLOTS; ++sl)
+      tmem_st_zero_32x32(tmem_base + sl * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16));
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int sl = 0; sl < SP_SLOTS; ++sl) mbar_arrive(&tempty[sl]);
     int lt = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
       unit_rows(unit, img, r0, c0, c1);
       for (int oh = c0; oh <= c1; ++oh, ++lt) {
-        const int as = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
+        const int as = lt % SP_SLOTS;
+        const uint32_t aph = (lt / SP_SLOTS) & 1;
         const bool dbgl = p.dbg && et == 0;
         const long long e0 = dbgl ? clock64() : 0;
         mbar_wait(&tfull[as], aph);
         const long long e1 = dbgl ? clock64() : 0;
         tc_fence_after();
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + as * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
+        const uint32_t tslot = tmem_base + as * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16);
+        tmem_ld_32x32(tslot, r);
         tmem_ld_wait();
+        tmem_st_zero_32x32(tslot);   // hand the slot back zeroed: every MMA accumulates
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
@@ -243,7 +261,7 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, 64 * SP_SLOTS);
 }
 
 }  // namespace cadre

@@ -238,17 +238,24 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
 #endif
             uint4 o = make_uint4(0, 0, 0, 0);
             enc2_t* m2 = reinterpret_cast<enc2_t*>(&o);
-            for (int y = ylo; y <= oh; ++y) {
+            // fixed 3 x 3 trip count (fully unrolled: all nine 16-byte loads are in flight together); a window
+            // position outside the image re-reads a valid one, which leaves the maximum unchanged
+            uint4 u[9];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int y = (oh - dy >= ylo) ? oh - dy : oh;
               const uint8_t* yrow = row_s + (y % 3) * SP_ROW_BYTES;
 #pragma unroll
               for (int dx = -1; dx <= 1; ++dx) {
-                const int x = 2 * pw + dx;
-                if (x < 0) continue;
-                const uint4 u = *reinterpret_cast<const uint4*>(yrow + x * 128 + ((chunk ^ (x & 7)) << 4));
-                const enc2_t* h2 = reinterpret_cast<const enc2_t*>(&u);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) m2[i] = __hmax2(m2[i], h2[i]);
+                const int x = (2 * pw + dx >= 0) ? 2 * pw + dx : 0;
+                u[dy * 3 + dx + 1] = *reinterpret_cast<const uint4*>(yrow + x * 128 + ((chunk ^ (x & 7)) << 4));
               }
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              const enc2_t* h2 = reinterpret_cast<const enc2_t*>(&u[k]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) m2[i] = __hmax2(m2[i], h2[i]);
             }
             *reinterpret_cast<uint4*>(orow + pw * 64 + chunk * 8) = o;
           }

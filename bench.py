@@ -52,6 +52,7 @@ def encoder_flops_per_frame():
             f[f"layer{li}.{bi}.conv2"] = 2 * Ho * Wo * planes * planes * 9
             if s == 2:
                 f[f"layer{li}.0.downsample"] = 2 * Ho * Wo * planes * C
+                f[f"layer{li}.0.conv2+shortcut"] = f[f"layer{li}.0.conv2"] + f[f"layer{li}.0.downsample"]
             H, W, C = Ho, Wo, planes
     f["conv5a|conv5c"] = 2 * 40 * 256 * 512 * 9
     f["conv51"] = f["conv52+sum"] = 2 * 40 * 128 * 128 * 9

@@ -115,6 +115,7 @@ int cadre_conv2d_nhwc(const void* in, int B, int Hin, int Win, int Cin, const vo
 
 int cadre_debug_clk(long long* dev_counters) {
   cadre::g_dbg_clk = dev_counters;
+  cadre::g_dbg_persist_launch = 0;
   return 0;
 }
 

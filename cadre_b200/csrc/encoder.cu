@@ -36,6 +36,10 @@ struct Encoder {
   enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
   enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
   bool use_flat = true, fuse_stem = true;
+  // fused shortcuts (layer2.0 / 3.0 / 4.0): conv2 weights with the 1x1 downsample appended along K, summed bias
+  bool fuse_ds = true;
+  enc_t* fused_w[3] = {nullptr, nullptr, nullptr};
+  float* fused_b[3] = {nullptr, nullptr, nullptr};
   enc_t* head5 = nullptr;    // [Bmax][40][256]
   enc_t* pam_v = nullptr;    // [Bmax][40][128] PAM value projection
   enc_t* sa = nullptr;       // [Bmax][40][128]
@@ -84,6 +88,27 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
   e->use_flat = getenv("CADRE_NO_FLAT") == nullptr;
   e->fuse_stem = getenv("CADRE_NO_STEM_FUSION") == nullptr;
+  e->fuse_ds = getenv("CADRE_NO_SHORTCUT_FUSION") == nullptr && getenv("CADRE_CONV_V1") == nullptr;
+  if (e->fuse_ds) {
+    // conv indices follow execution order: layer1 = 0..3, then per stage (conv1, conv2, downsample, conv1, conv2)
+    const int planes[4] = {64, 128, 256, 512};
+    for (int li = 1; li < 4; ++li) {
+      const int conv2_idx = 4 + (li - 1) * 5 + 1, ds_idx = conv2_idx + 1;
+      const int Cout = planes[li], Cin = planes[li - 1], K2 = 9 * Cout, Kf = K2 + Cin;
+      enc_t* wf = dev_alloc<enc_t>(static_cast<size_t>(Cout) * Kf, false);
+      CADRE_CUDA_CHECK(cudaMemcpy2D(wf, Kf * sizeof(enc_t), w->conv_w[conv2_idx], K2 * sizeof(enc_t),
+                                    K2 * sizeof(enc_t), Cout, cudaMemcpyDeviceToDevice));
+      CADRE_CUDA_CHECK(cudaMemcpy2D(wf + K2, Kf * sizeof(enc_t), w->conv_w[ds_idx], Cin * sizeof(enc_t),
+                                    Cin * sizeof(enc_t), Cout, cudaMemcpyDeviceToDevice));
+      std::vector<float> b2(Cout), bd(Cout);
+      CADRE_CUDA_CHECK(cudaMemcpy(b2.data(), w->conv_b[conv2_idx], Cout * sizeof(float), cudaMemcpyDeviceToHost));
+      CADRE_CUDA_CHECK(cudaMemcpy(bd.data(), w->conv_b[ds_idx], Cout * sizeof(float), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < Cout; ++i) b2[i] += bd[i];
+      float* bf = dev_alloc<float>(Cout, false);
+      CADRE_CUDA_CHECK(cudaMemcpy(bf, b2.data(), Cout * sizeof(float), cudaMemcpyHostToDevice));
+      e->fused_w[li - 1] = wf, e->fused_b[li - 1] = bf;
+    }
+  }
   e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
   e->pam_v = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
@@ -103,6 +128,7 @@ static void encoder_destroy(Encoder* e) {
   for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
   cudaFree(e->head5), cudaFree(e->pam_v), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
   cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max);
+  for (int i = 0; i < 3; ++i) cudaFree(e->fused_w[i]), cudaFree(e->fused_b[i]);
   delete e;
 }
 
@@ -175,6 +201,22 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
       step(e, s, n, (std::string("layer") + std::to_string(li + 1) + "." + std::to_string(bi) + ".conv1").c_str());
       const enc_t* idn = x;
       const int conv2_idx = ci++;
+      if (stride == 2 && e->fuse_ds) {
+        // BasicBlock with downsample (resnet.py:47-53): relu(bn2(conv2(t)) + bn_d(conv1x1_s2(x))) as ONE
+        // implicit GEMM: the shortcut is Cin/64 extra k-blocks reading x on its stride-2 sub-lattice
+        ++ci;
+        ConvArgs a;
+        a.in = t, a.B = B, a.Hin = Ho, a.Win = Wo, a.Cin = Cout;
+        a.w = e->fused_w[li - 1], a.bias = e->fused_b[li - 1];
+        a.Cout = Cout, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1;
+        a.act = 1, a.out = o;
+        a.in2 = x, a.Cin2 = C, a.in2_pad = from_pad ? 1 : 0, a.Hin2 = H, a.Win2 = W;
+        launch_conv(a, s);
+        step(e, s, n, (std::string("layer") + std::to_string(li + 1) + ".0.conv2+shortcut").c_str());
+        cur = (cur + 3) & 3;
+        H = Ho, W = Wo, C = Cout;
+        continue;
+      }
       if (stride == 2) {
         conv(e, ci++, x, B, H, W, C, Cout, 1, 2, 0, nullptr, 0, ds, s, from_pad);
         step(e, s, n, (std::string("layer") + std::to_string(li + 1) + ".0.downsample").c_str());

@@ -130,6 +130,12 @@ struct ConvArgs {
   int act = 0;
   enc_t* out = nullptr;  // [B][Hout][Wout][Cout]
   int in_pad = 0;        // input tensor is [B][Hin+2][Win+2][Cin] with a zero border (Hin/Win stay logical)
+  // Optional fused shortcut (ResNet downsample, resnet.py:152-158): out += conv1x1/stride-2 of a SECOND input,
+  // executed as Cin2/64 extra k-blocks of the same implicit GEMM. `w` is then [Cout][KH*KW*Cin + Cin2] (the
+  // shortcut weights appended along K) and `bias` the sum of both biases; in2 is [B][Hin2 (+2)][Win2 (+2)][Cin2]
+  // with Hout = (Hin2 - 1) / 2 + 1.
+  const enc_t* in2 = nullptr;
+  int Cin2 = 0, in2_pad = 0, Hin2 = 0, Win2 = 0;
 };
 void launch_conv(const ConvArgs& a, cudaStream_t stream);
 
@@ -174,6 +180,7 @@ struct OptTables {
 // with the predecessor's tail. CADRE_NO_PDL=1 restores plain stream order (A/B switch).
 bool pdl_enabled();
 extern long long* g_dbg_clk;
+extern int g_dbg_persist_launch;
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg;

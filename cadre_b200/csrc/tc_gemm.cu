@@ -10,6 +10,15 @@
 
 namespace cadre {
 
+long long* g_dbg_clk = nullptr;   // cadre_debug_clk: per-CTA cycle counters of the flat / stem / persistent kernels
+int g_dbg_persist_launch = 0;     // region 3 + n for the n-th persistent launch since cadre_debug_clk()
+static PersistParams with_dbg(const PersistParams& p) {
+  PersistParams q = p;
+  q.dbg = g_dbg_clk ? g_dbg_clk + static_cast<long long>(3 + g_dbg_persist_launch++) * 148 * 16 : nullptr;
+  return q;
+}
+
+
 // ---------------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -101,8 +110,6 @@ static int num_sms() {
   }
   return n;
 }
-long long* g_dbg_clk = nullptr;   // cadre_debug_clk: per-CTA cycle counters of the flat / stem kernels
-
 bool pdl_enabled() {
   static const bool on = getenv("CADRE_NO_PDL") == nullptr;
   return on;
@@ -132,7 +139,7 @@ static void launch_persist2(const PersistParams& p, cudaStream_t stream) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, with_dbg(p)));
 }
 
 template <int BN, int STAGES, int MODE>
@@ -146,7 +153,7 @@ static void launch_persist(const PersistParams& p, cudaStream_t stream) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_k(kern, dim3(grid), dim3(320), smem, stream, p);
+  launch_k(kern, dim3(grid), dim3(320), smem, stream, with_dbg(p));
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -299,10 +306,27 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
     }
   p.ntaps = nt, p.cin_chunks = a.Cin / 64;
   p.num_kb = nt * p.cin_chunks;
+  const int kb_main = p.num_kb;
+  int Ktot = nt * a.Cin;
+  if (a.in2 != nullptr) {
+    // fused shortcut: output (h, w) reads in2 pixel (2h, 2w) -> parity sub-lattice map of the (bordered) tensor
+    CADRE_REQUIRE(!g_use_v1 && a.stride == 1 && a.Cin2 % 64 == 0 && a.Cin2 > 0 && nt < 12, "fused shortcut arguments");
+    CADRE_REQUIRE((a.Hin2 - 1) / 2 + 1 == Hout && (a.Win2 - 1) / 2 + 1 == Wout, "fused shortcut input size");
+    const int Hs2 = a.Hin2 + 2 * a.in2_pad, Ws2 = a.Win2 + 2 * a.in2_pad, par = a.in2_pad & 1;
+    const int Hq = (Hs2 - par + 1) / 2, Wq = (Ws2 - par + 1) / 2;
+    const uint64_t dims[4] = {(uint64_t)a.Cin2, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)a.B};
+    const uint64_t str[3] = {2 * a.Cin2 * es, 2 * (uint64_t)Ws2 * a.Cin2 * es, (uint64_t)Hs2 * Ws2 * a.Cin2 * es};
+    make_map(&p.tmA[1], 2, 4, a.in2 + ((long long)par * Ws2 + par) * a.Cin2, dims, str, box);
+    ConvTap t;
+    t.map = 1, t.dh = (short)((a.in2_pad - par) / 2), t.dw = (short)((a.in2_pad - par) / 2), t.pad_ = 0;
+    p.taps[nt] = t;
+    p.num_kb += a.Cin2 / 64;
+    Ktot += a.Cin2;
+  }
   p.Hout = Hout, p.Wout = Wout, p.TH = TH, p.TN = TN, p.Bimg = a.B;
   // weights: [Cout][K] K-major
   {
-    const int K = nt * a.Cin;
+    const int K = Ktot;
     make_operand_map(&p.tmB, 2, false, a.w, K, 0, a.Cout, K, 1, bn);
   }
   p.M = 0, p.N = a.Cout;
@@ -322,7 +346,7 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
                                (uint64_t)Hout * Wout * a.Cout * es};
       make_map(&q.tmOut, 2, 4, a.out, dims, str, box);
     }
-    q.num_kb = p.num_kb, q.ntaps = p.ntaps, q.cin_chunks = p.cin_chunks;
+    q.num_kb = p.num_kb, q.kb_main = kb_main, q.ntaps = p.ntaps, q.cin_chunks = p.cin_chunks;
     q.Hout = Hout, q.Wout = Wout, q.TH = TH, q.TN = TN, q.Bimg = a.B;
     for (int i = 0; i < 12; ++i) q.taps[i] = p.taps[i];
     q.tiles_m = grid.x, q.tiles_n = grid.y;
@@ -333,14 +357,14 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
       launch_persist<64, 6, MODE_CONV>(q, stream);
     else if (bn == 128) {
       if (use_pairs) {
-        make_operand_map(&q.tmB, 2, false, a.w, nt * a.Cin, 0, a.Cout, nt * a.Cin, 1, 64);  // half-tile B boxes
+        make_operand_map(&q.tmB, 2, false, a.w, Ktot, 0, a.Cout, Ktot, 1, 64);  // half-tile B boxes
         launch_persist2<128, 6, MODE_CONV>(q, stream);
       } else {
         launch_persist<128, 5, MODE_CONV>(q, stream);
       }
     } else {
       if (use_pairs) {
-        make_operand_map(&q.tmB, 2, false, a.w, nt * a.Cin, 0, a.Cout, nt * a.Cin, 1, 128);
+        make_operand_map(&q.tmB, 2, false, a.w, Ktot, 0, a.Cout, Ktot, 1, 128);
         launch_persist2<256, 4, MODE_CONV>(q, stream);
       } else {
         launch_persist<256, 3, MODE_CONV>(q, stream);  // 128x256 tiles: half the A-operand smem traffic per FLOP

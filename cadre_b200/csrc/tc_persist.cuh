@@ -16,6 +16,7 @@ struct PersistParams {
   CUtensorMap tmB;
   CUtensorMap tmOut;
   int num_kb;
+  int kb_main;              // k-blocks of the filter taps; k-blocks beyond belong to tap `ntaps` (fused shortcut)
   int ntaps, cin_chunks, Hout, Wout, TH, TN, Bimg;
   ConvTap taps[12];
   int tiles_m, tiles_n;
@@ -25,6 +26,7 @@ struct PersistParams {
   long long ldr;
   int res_after_act, act;
   int out_pad;              // output (and residual) tensors carry a 1-pixel zero border: [B][H+2][W+2][C]
+  long long* dbg;           // optional per-CTA cycle counters [16] (cadre_debug_clk), nullptr in production
 };
 
 template <int BLOCK_N, int STAGES, bool CTA2 = false>
@@ -207,7 +209,9 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(&empty[s], ph ^ 1);
+        if (p.dbg && lane == 0) p.dbg[blockIdx.x * 16 + 1] += clock64() - t0;
         uint8_t* a_s = smem + s * S::STAGE_BYTES;
         uint8_t* b_s = a_s + S::A_BYTES;
         if (elect_one()) {
@@ -217,7 +221,8 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           if constexpr (MODE == MODE_GEMM) {
             tma_load_3d_2sm(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
           } else if constexpr (MODE == MODE_CONV) {
-            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            if (kb >= p.kb_main) tap = p.ntaps, cc = kb - p.kb_main;   // fused 1x1 / stride-2 shortcut
             const ConvTap t = p.taps[tap];
             tma_load_4d_2sm(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
           } else {
@@ -229,7 +234,8 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           if constexpr (MODE == MODE_GEMM) {
             tma_load_3d(a_s, &p.tmA[0], &full[s], kb * BK, m_tile * 128, 0);
           } else if constexpr (MODE == MODE_CONV) {
-            const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+            if (kb >= p.kb_main) tap = p.ntaps, cc = kb - p.kb_main;   // fused 1x1 / stride-2 shortcut
             const ConvTap t = p.taps[tap];
             tma_load_4d(a_s, &p.tmA[t.map], &full[s], cc * 64, t.dw, h0 + t.dh, img0);
           } else {
@@ -247,16 +253,22 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
     // converged warp, elected lane)
     constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, CTA2 ? 256 : 128, BLOCK_N);
     int it = 0, lt = 0;
+    long long d_te = 0, d_wf = 0;
+    const long long tstart = p.dbg ? clock64() : 0;
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++lt) {
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
+      const long long t0 = p.dbg ? clock64() : 0;
       mbar_wait(&tempty[as], aph ^ 1);  // epilogue has drained this accumulator
+      if (p.dbg) d_te += clock64() - t0;
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * BLOCK_N;
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        const long long t1 = p.dbg ? clock64() : 0;
         mbar_wait(&full[s], ph);
+        if (p.dbg) d_wf += clock64() - t1;
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
@@ -277,6 +289,10 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         }
         __syncwarp();
       }
+    }
+    if (p.dbg && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 16;
+      d[2] += d_te, d[3] += d_wf, d[5] += clock64() - tstart, d[10] += lt;
     }
     }
   } else if (warp >= 2) {
@@ -321,16 +337,21 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
         for (int j = 0; j < HC / 8; ++j) rres[j] = row_ok ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
       // staging buffer must have been read by the previous tile's TMA store
+      const long long e0 = (p.dbg && leader) ? clock64() : 0;
       if (leader) tma_store_wait_read();
       epi_bar_sync256();
+      const long long e1 = (p.dbg && leader) ? clock64() : 0;
       mbar_wait(&tfull[as], aph);
+      const long long e2 = (p.dbg && leader) ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BLOCK_N + cbase + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < HC / 32; ++c) {
         uint32_t r[32];
+        const long long l0 = (p.dbg && leader) ? clock64() : 0;
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
+        if (p.dbg && leader) p.dbg[blockIdx.x * 16 + 11] += clock64() - l0;
         if (c == HC / 32 - 1) {  // this warp's part of the accumulator is in registers
           tc_fence_before();
           __syncwarp();
@@ -382,8 +403,10 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           *reinterpret_cast<uint4*>(out_s + g * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
         }
       }
+      const long long e3 = (p.dbg && leader) ? clock64() : 0;
       fence_proxy_async_smem();
       epi_bar_sync256();
+      if (p.dbg && leader) p.dbg[blockIdx.x * 16 + 12] += clock64() - e3;
       if (leader) {
 #pragma unroll
         for (int g = 0; g < NCH; ++g) {
@@ -395,6 +418,10 @@ __global__ void __launch_bounds__(320, 1) tc_persist_kernel(const __grid_constan
           }
         }
         tma_store_commit();
+        if (p.dbg) {
+          long long* d = p.dbg + blockIdx.x * 16;
+          d[6] += e1 - e0, d[7] += e2 - e1, d[8] += clock64() - e2;
+        }
       }
     }
     if (leader) tma_store_wait_all();

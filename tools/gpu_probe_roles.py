@@ -13,6 +13,22 @@ from cadre_b200.encoder import Encoder  # noqa: E402
 from oracle import restate as R  # noqa: E402  (fixture weights only; tools/ is not product code)
 
 
+def persist_table(d, names):
+    print("== persistent conv / linear launches in order (cycles per tile, mean over CTAs that worked; CTA pairs: leader CTAs only for the mma rows)")
+    print(f"{'launch':28s} {'tiles':>6s} {'prod.wait':>9s} {'mma.tmemE':>9s} {'mma.opsF':>9s} {'mma.loop':>9s} {'epi.bar':>8s} {'epi.tfull':>9s} {'epi.rest':>9s} {'(tmem ld':>9s} {'bar2)':>7s}")
+    for r in range(3, d.shape[0]):
+        n = d[r, :, 10]
+        act = n > 0
+        if not act.any():
+            continue
+        nt = n[act].mean()
+        # epilogue counters exist for every CTA; tiles per CTA taken from the mma thread of leader CTAs
+        ep = d[r, :, 8] > 0
+        per = lambda i, m: (d[r, m, i].sum() / max(n[act].sum(), 1)) * (act.sum() / max(m.sum(), 1))  # noqa: E731
+        print(f"{names[r-3] if r-3 < len(names) else r-3!s:28s} {nt:6.1f} {per(1, act):9.0f} {per(2, act):9.0f} {per(3, act):9.0f} {per(5, act):9.0f} "
+              f"{per(6, ep):8.0f} {per(7, ep):9.0f} {per(8, ep):9.0f} {per(11, ep):9.0f} {per(12, ep):7.0f}")
+
+
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 640
     dev = torch.device("cuda:0")
@@ -22,7 +38,7 @@ def main():
     for _ in range(3):
         enc.forward_f32(xb, out)
     torch.cuda.synchronize()
-    dbg = torch.zeros(3, 148, 16, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(3 + 24, 148, 16, dtype=torch.int64, device=dev)
     L = _lib.lib()
     L.cadre_debug_clk(ctypes.c_void_p(dbg.data_ptr()))
     enc.forward_f32(xb, out)
@@ -47,6 +63,11 @@ def main():
             print(f"  epilogue  store-read + barrier {per(6):8.0f}")
             print(f"  epilogue  wait tmem-full       {per(7):8.0f}")
             print(f"  epilogue  ld..store issue      {per(8):8.0f}")
+    names = ["layer2.0.conv1", "layer2.0.down", "layer2.0.conv2", "layer2.1.conv1", "layer2.1.conv2", "layer3.0.conv1",
+             "layer3.0.down", "layer3.0.conv2", "layer3.1.conv1", "layer3.1.conv2", "layer4.0.conv1", "layer4.0.down",
+             "layer4.0.conv2", "layer4.1.conv1", "layer4.1.conv2", "conv5a|5c", "pam.value", "conv51", "conv52+sum",
+             "fc1"]
+    persist_table(d, names)
 
 
 if __name__ == "__main__":

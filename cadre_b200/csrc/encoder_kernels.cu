@@ -39,18 +39,39 @@ __global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __r
   }
 }
 
-__global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ route,
-                                  const uint8_t* __restrict__ route_max, enc_t* __restrict__ out,
-                                  int B) {
+// One block = 32 pixels x 8 row pairs of one image. The route map is [n][x][y] (y contiguous) while the output is
+// x-major, so its 32 x 16 byte tile is transposed through shared memory (lanes along y when loading: whole
+// sectors; the direct x-strided byte reads fetched every sector 16 times). k / 255 comes from a 256-entry table
+// (same double division + float + fp16 roundings as the reference, computed once per block instead of three
+// FP64 divisions per pixel).
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ rgb,
+                                                         const uint8_t* __restrict__ route,
+                                                         const uint8_t* __restrict__ route_max,
+                                                         enc_t* __restrict__ out, int B) {
   pdl_trigger();
   pdl_wait();
-  // one thread per (image, row pair y2 in 1..73, pixel x in 0..255): writes 16 bytes
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * 73 * 256;
-  if (gid >= total) return;
-  const int x = static_cast<int>(gid % 256);
-  const int y2 = static_cast<int>((gid / 256) % 73) + 1;
-  const int n = static_cast<int>(gid / (256 * 73));
+  __shared__ enc_t lut[256];
+  __shared__ uint8_t s_route[32][20];   // [x][y - ybase], 16 rows used
+  const int tid = threadIdx.x;
+  // np.array(rgb / 255., dtype=float32): float64 division rounded to fp32, then to the encoder's 16-bit type
+  lut[tid] = enc_from_float(static_cast<float>(tid / 255.0));
+  const int x0 = blockIdx.x * 32;          // 8 tiles across
+  const int yb = blockIdx.y;               // 0..9: row pairs y2 = 1 + 8*yb .. (73 row pairs: the last block has one)
+  const int n = blockIdx.z;
+  const int ybase = 2 * (1 + 8 * yb) - 3;  // unpadded row of (y2 = first, r = 0)
+  {
+    const int ty = tid & 15, tx = tid >> 4;   // 16 lanes along y, 16 x rows per pass
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int x = tx + 16 * k, y = ybase + ty;
+      s_route[x][ty] = (y >= 0 && y < 144) ? route[(static_cast<long long>(n) * 256 + x0 + x) * 144 + y] : 0;
+    }
+  }
+  __syncthreads();
+  const int lx = tid & 31, ly = tid >> 5;   // pixel, row pair within the tile
+  const int y2 = 1 + 8 * yb + ly;
+  if (y2 > 73) return;
+  const int x = x0 + lx;
   const uint8_t mx = route_max[n];
   enc_t v[8];
 #pragma unroll
@@ -58,11 +79,10 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t
     const int y = 2 * y2 + r - 3;  // unpadded row
     if (y >= 0 && y < 144) {
       const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + y) * 256 + x) * 3;
-      // np.array(rgb / 255., dtype=float32): float64 division rounded to fp32, then to bf16 here
-      v[4 * r + 0] = enc_from_float(static_cast<float>(px[0] / 255.0));
-      v[4 * r + 1] = enc_from_float(static_cast<float>(px[1] / 255.0));
-      v[4 * r + 2] = enc_from_float(static_cast<float>(px[2] / 255.0));
-      const uint8_t rv = route[(static_cast<long long>(n) * 256 + x) * 144 + y];
+      v[4 * r + 0] = lut[px[0]];
+      v[4 * r + 1] = lut[px[1]];
+      v[4 * r + 2] = lut[px[2]];
+      const uint8_t rv = s_route[lx][y - ybase];
       v[4 * r + 3] = enc_from_float((mx > 0) ? ((rv == mx) ? 1.f : 0.f) : static_cast<float>(rv));
     } else {
       v[4 * r + 0] = v[4 * r + 1] = v[4 * r + 2] = v[4 * r + 3] = enc_from_float(0.f);
@@ -75,9 +95,7 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ rgb, const uint8_t
 void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
                        int B, cudaStream_t stream) {
   launch_k(route_max_kernel, dim3(B), dim3(256), 0, stream, route, route_max_ws);
-  const long long total = static_cast<long long>(B) * 73 * 256;
-  launch_k(preprocess_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, rgb, route, route_max_ws,
-                                                                                     out, B);
+  launch_k(preprocess_kernel, dim3(8, 10, B), dim3(256), 0, stream, rgb, route, route_max_ws, out, B);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

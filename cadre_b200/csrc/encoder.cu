@@ -14,7 +14,8 @@
 
 namespace cadre {
 
-void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
+void launch_f32_to_enc(const float* in, enc_t* out, int n, cudaStream_t stream);
+void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, const enc_t* lut, enc_t* out,
                        int B, cudaStream_t stream);
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
 void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
@@ -49,6 +50,7 @@ struct Encoder {
   enc_t* fc1 = nullptr;      // [Bmax][3072]
   float* qkv = nullptr;              // [6][Bmax][256]
   uint8_t* route_max = nullptr;      // [Bmax]
+  enc_t* lut255 = nullptr;           // k / 255 for k = 0..255, rounded like np.array(rgb / 255., dtype=float32)
   enc_t* l4 = nullptr;       // alias of the act buffer holding layer4's output after a forward
   int launches_per_forward = 0;
   // optional per-launch timing (cadre_encoder_profile)
@@ -118,6 +120,17 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   e->fc1 = dev_alloc<enc_t>(B * 3072, false);
   e->qkv = dev_alloc<float>(6 * B * 256, false);
   e->route_max = dev_alloc<uint8_t>(B, true);
+  {
+    // agent.py:46: float64 division, cast to float32 (then to the 16-bit operand type of the stem)
+    std::vector<float> lf(256);
+    for (int k = 0; k < 256; ++k) lf[k] = static_cast<float>(k / 255.0);
+    float* tmp = dev_alloc<float>(256, false);
+    CADRE_CUDA_CHECK(cudaMemcpy(tmp, lf.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+    e->lut255 = dev_alloc<enc_t>(256, false);
+    launch_f32_to_enc(tmp, e->lut255, 256, 0);
+    CADRE_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  }
   return e;
 }
 
@@ -127,7 +140,7 @@ static void encoder_destroy(Encoder* e) {
   for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
   for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
   cudaFree(e->head5), cudaFree(e->pam_v), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
-  cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max);
+  cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max), cudaFree(e->lut255);
   for (int i = 0; i < 3; ++i) cudaFree(e->fused_w[i]), cudaFree(e->fused_b[i]);
   delete e;
 }
@@ -321,7 +334,7 @@ int cadre_encoder_forward_u8(void* handle, const uint8_t* rgb, const uint8_t* ro
   CADRE_REQUIRE(B > 0 && B <= e->max_batch, "batch exceeds the encoder's max_batch");
   CADRE_REQUIRE(ld_out >= (measurements ? 530 : 512), "ld_out too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cadre::launch_preprocess(rgb, route_fig, e->route_max, e->padded, B, s);
+  cadre::launch_preprocess(rgb, route_fig, e->route_max, e->lut255, e->padded, B, s);
   cadre::encoder_trunk(e, B, measurements, out, ld_out, s);
   CADRE_API_END
 }

@@ -42,46 +42,59 @@ __global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __r
 // One block = 32 pixels x 8 row pairs of one image. The route map is [n][x][y] (y contiguous) while the output is
 // x-major, so its 32 x 16 byte tile is transposed through shared memory (lanes along y when loading: whole
 // sectors; the direct x-strided byte reads fetched every sector 16 times). k / 255 comes from a 256-entry table
-// (same double division + float + fp16 roundings as the reference, computed once per block instead of three
+// (same double division + float + fp16 roundings as the reference, done once on the host instead of three
 // FP64 divisions per pixel).
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ rgb,
                                                          const uint8_t* __restrict__ route,
                                                          const uint8_t* __restrict__ route_max,
+                                                         const enc_t* __restrict__ lut_g,
                                                          enc_t* __restrict__ out, int B) {
   pdl_trigger();
   pdl_wait();
   __shared__ enc_t lut[256];
   __shared__ uint8_t s_route[32][20];   // [x][y - ybase], 16 rows used
   const int tid = threadIdx.x;
-  // np.array(rgb / 255., dtype=float32): float64 division rounded to fp32, then to the encoder's 16-bit type
-  lut[tid] = enc_from_float(static_cast<float>(tid / 255.0));
   const int x0 = blockIdx.x * 32;          // 8 tiles across
   const int yb = blockIdx.y;               // 0..9: row pairs y2 = 1 + 8*yb .. (73 row pairs: the last block has one)
   const int n = blockIdx.z;
   const int ybase = 2 * (1 + 8 * yb) - 3;  // unpadded row of (y2 = first, r = 0)
+  const int lx = tid & 31, ly = tid >> 5;   // pixel, row pair within the tile
+  const int y2 = 1 + 8 * yb + ly;
+  const int x = x0 + lx;
+  // every global load of the block is issued before the first barrier (one memory round trip per block: the
+  // kernel is a chain of short blocks, 103 us with three dependent round trips against 46 us of HBM time)
+  const enc_t lut_v = lut_g[tid];
+  uint8_t rt[2];
   {
     const int ty = tid & 15, tx = tid >> 4;   // 16 lanes along y, 16 x rows per pass
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int x = tx + 16 * k, y = ybase + ty;
-      s_route[x][ty] = (y >= 0 && y < 144) ? route[(static_cast<long long>(n) * 256 + x0 + x) * 144 + y] : 0;
+      const int y = ybase + ty;
+      rt[k] = (y >= 0 && y < 144) ? route[(static_cast<long long>(n) * 256 + x0 + tx + 16 * k) * 144 + y] : 0;
     }
   }
-  __syncthreads();
-  const int lx = tid & 31, ly = tid >> 5;   // pixel, row pair within the tile
-  const int y2 = 1 + 8 * yb + ly;
-  if (y2 > 73) return;
-  const int x = x0 + lx;
+  uint8_t pb[2][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = 2 * y2 + r - 3;  // unpadded row
+    const bool ok = y2 <= 73 && y >= 0 && y < 144;
+    const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + (ok ? y : 0)) * 256 + x) * 3;
+    pb[r][0] = ok ? px[0] : 0, pb[r][1] = ok ? px[1] : 0, pb[r][2] = ok ? px[2] : 0;
+  }
   const uint8_t mx = route_max[n];
+  lut[tid] = lut_v;   // k / 255 as the reference rounds it (table built once on the host)
+  s_route[(tid >> 4)][tid & 15] = rt[0];
+  s_route[(tid >> 4) + 16][tid & 15] = rt[1];
+  __syncthreads();
+  if (y2 > 73) return;
   enc_t v[8];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int y = 2 * y2 + r - 3;  // unpadded row
     if (y >= 0 && y < 144) {
-      const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + y) * 256 + x) * 3;
-      v[4 * r + 0] = lut[px[0]];
-      v[4 * r + 1] = lut[px[1]];
-      v[4 * r + 2] = lut[px[2]];
+      v[4 * r + 0] = lut[pb[r][0]];
+      v[4 * r + 1] = lut[pb[r][1]];
+      v[4 * r + 2] = lut[pb[r][2]];
       const uint8_t rv = s_route[lx][y - ybase];
       v[4 * r + 3] = enc_from_float((mx > 0) ? ((rv == mx) ? 1.f : 0.f) : static_cast<float>(rv));
     } else {
@@ -92,10 +105,19 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
 }
 
-void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, enc_t* out,
-                       int B, cudaStream_t stream) {
+__global__ void f32_to_enc_kernel(const float* __restrict__ in, enc_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = enc_from_float(in[i]);   // same rounding as every other fp32 -> operand conversion
+}
+void launch_f32_to_enc(const float* in, enc_t* out, int n, cudaStream_t stream) {
+  f32_to_enc_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, out, n);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, const enc_t* lut,
+                       enc_t* out, int B, cudaStream_t stream) {
   launch_k(route_max_kernel, dim3(B), dim3(256), 0, stream, route, route_max_ws);
-  launch_k(preprocess_kernel, dim3(8, 10, B), dim3(256), 0, stream, rgb, route, route_max_ws, out, B);
+  launch_k(preprocess_kernel, dim3(8, 10, B), dim3(256), 0, stream, rgb, route, route_max_ws, lut, out, B);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

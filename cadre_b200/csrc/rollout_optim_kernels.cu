@@ -19,8 +19,15 @@ __device__ __forceinline__ int skew(int i) { return i + (i >> 5); }
 // ITERS = ceil(T / 32) when T <= 32 * ITERS is known at launch (8: T <= 256, 32: T <= 1024): every global load
 // of the sequence is issued before the first use (3 * ITERS independent loads per lane, ~12 KB per warp in
 // flight) and V stays in registers for the output pass. ITERS = 0 is the general loop (V re-read from L2).
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int ITERS>
-__global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+__global__ void __launch_bounds__(256, (ITERS > 16 ? 3 : 1)) gae_kernel(const float* __restrict__ rewards, float* __restrict__ values,
                                                   const float* __restrict__ masks,
                                                   const float* __restrict__ next_value,
                                                   float* __restrict__ returns, float* __restrict__ adv, int E,
@@ -39,35 +46,56 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
   const float gt = gamma * tau;
   constexpr int NV = ITERS > 0 ? ITERS : 1;
   float vreg[NV];
-  if constexpr (ITERS > 0) {
-    // batches of <= 16 iterations, LAST batch first (V_{i+1} of a batch's last element lives in the next batch):
-    // 48 loads per lane in flight, r / m registers are recycled, so ~20 warps per SM fit at T = 1024
-    constexpr int HB = ITERS > 16 ? 16 : ITERS;
+  if constexpr (ITERS > 16) {
+    // r and m travel global -> shared with cp.async (no registers held while in flight) straight into the
+    // arrays that become (delta, a); V goes to registers (it is needed again for the output pass). All 3*ITERS
+    // loads of the sequence are in flight at once: one memory round trip per sequence, ~60 registers.
 #pragma unroll
-    for (int h = ITERS / HB - 1; h >= 0; --h) {
-      float rreg[HB], mreg[HB];
-#pragma unroll
-      for (int kk = 0; kk < HB; ++kk) {
-        const int k = h * HB + kk;
-        const int i = lane + 32 * k;
-        const bool ok = i < T;
-        rreg[kk] = ok ? rewards[base + i] : 0.f;
-        vreg[k] = ok ? values[base + i] : 0.f;
-        mreg[kk] = ok ? masks[base + i] : 0.f;
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = lane + 32 * k;
+      if (i < T) {
+        cp_async_4(&sd[skew(i)], rewards + base + i);
+        cp_async_4(&sa_[skew(i)], masks + base + i);
       }
+      vreg[k] = i < T ? values[base + i] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncwarp();
 #pragma unroll
-      for (int kk = 0; kk < HB; ++kk) {
-        const int k = h * HB + kk;
-        const int i = lane + 32 * k;
-        // V_{i+1}: the next lane's element, lane 31 takes lane 0's next element, the last step takes next_value
-        const float dn = __shfl_down_sync(0xffffffffu, vreg[k], 1);
-        const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, vreg[k + 1 < ITERS ? k + 1 : k], 0) : nv;
-        float vn = lane < 31 ? dn : wrap;
-        if (i + 1 == T) vn = nv;
-        if (i < T) {
-          sd[skew(i)] = rreg[kk] + gamma * vn * mreg[kk] - vreg[k];
-          sa_[skew(i)] = gt * mreg[kk];
-        }
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = lane + 32 * k;
+      // V_{i+1}: the next lane's element, lane 31 takes lane 0's next element, the last step takes next_value
+      const float dn = __shfl_down_sync(0xffffffffu, vreg[k], 1);
+      const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, vreg[k + 1 < ITERS ? k + 1 : k], 0) : nv;
+      float vn = lane < 31 ? dn : wrap;
+      if (i + 1 == T) vn = nv;
+      if (i < T) {
+        const float r = sd[skew(i)], m = sa_[skew(i)];   // this lane's own elements: in-place update is safe
+        sd[skew(i)] = r + gamma * vn * m - vreg[k];
+        sa_[skew(i)] = gt * m;
+      }
+    }
+  } else if constexpr (ITERS > 0) {
+    // short sequences: plain register loads (many warps per SM hide the single round trip)
+    float rreg[ITERS], mreg[ITERS];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = lane + 32 * k;
+      const bool ok = i < T;
+      rreg[k] = ok ? rewards[base + i] : 0.f;
+      vreg[k] = ok ? values[base + i] : 0.f;
+      mreg[k] = ok ? masks[base + i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = lane + 32 * k;
+      const float dn = __shfl_down_sync(0xffffffffu, vreg[k], 1);
+      const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, vreg[k + 1 < ITERS ? k + 1 : k], 0) : nv;
+      float vn = lane < 31 ? dn : wrap;
+      if (i + 1 == T) vn = nv;
+      if (i < T) {
+        sd[skew(i)] = rreg[k] + gamma * vn * mreg[k] - vreg[k];
+        sa_[skew(i)] = gt * mreg[k];
       }
     }
   } else {
@@ -83,8 +111,11 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
   __syncwarp();
   const int cs = (T + 31) / 32;
   const int t0 = min(T, lane * cs), t1 = min(T, t0 + cs);
+  {
   // chunk map x -> a*x + b (x = gae entering the chunk from later time steps)
+  // (unrolled by 8: the shared-memory loads of eight steps are issued ahead of the dependent FMA chain)
   float a = 1.f, b = 0.f;
+#pragma unroll 8
   for (int t = t1 - 1; t >= t0; --t) {
     const float at = sa_[skew(t)];
     b = at * b + sd[skew(t)];   // F_t o F_chunk_so_far : later steps were composed first
@@ -103,9 +134,11 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
   }
   float gae = __shfl_down_sync(0xffffffffu, sb, 1);  // S_{l+1}(0)
   if (lane == 31) gae = 0.f;
+#pragma unroll 8
   for (int t = t1 - 1; t >= t0; --t) {   // replay the chunk
     gae = sd[skew(t)] + sa_[skew(t)] * gae;
     sd[skew(t)] = gae;
+  }
   }
   __syncwarp();
   // returns_t = gae_t + V_t (storage.py:75); advantage_t = returns_t - V_t (train.py:82: the rounding of the
@@ -273,7 +306,7 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   CADRE_REQUIRE(E > 0 && T > 1 && T <= 16384, "gae sizes (1 < T <= 16384)");
   const int L = T + (T >> 5) + 1;
   const size_t per_warp = 2 * static_cast<size_t>(L) * sizeof(float);
-  int warps = (T > 256 && T <= 1024) ? 4 : 8;   // the register-resident variant (146 registers) runs 3 x 4 warps per SM
+  int warps = 8;
   while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
   auto kern = T <= 256 ? cadre::gae_kernel<8> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>);

@@ -169,6 +169,27 @@ def cpu_reference_rate(n_frames, mb, threads):
                                           t_step_s=t_step)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU BEFORE the pinned staging buffers
+    are allocated (first-touch puts their pages on that NUMA node). With 8 ranks copying 944 MB per step each, the
+    host-to-device leg of `e2e` is bound by host memory / inter-socket bandwidth, not by the GPUs."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        orig = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in orig]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus), orig
+    except Exception:
+        pass
+    return None, None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -205,6 +226,7 @@ def run_cadre(args):
                          "CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa, full_affinity = bind_to_gpu_numa_node(local)
     dist = torch.distributed
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -386,6 +408,8 @@ def run_cadre(args):
                     "frac": round(ach / tf_peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src + " (sustained bf16)",
                     "share_of_encoder_ms": round(tot_ms / sum(k["ms"] for k in kernels), 3)}
         launches = (n // ENC_CHUNK) * enc.launches_per_forward + 1 + n_upd * (learner.engine.launches + 3)
+        if full_affinity:
+            os.sched_setaffinity(0, full_affinity)   # the CPU baseline uses every host core
         cpu_val, cpu_detail = cpu_reference_rate(64, 64, os.cpu_count() or 1)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -394,7 +418,8 @@ def run_cadre(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "workers_per_gpu": WORKERS, "num_steps": T, "seq_length": SEQ,
                        "mini_batch": mb, "ppo_epoch": PPO_EPOCH, "encoder_chunk": ENC_CHUNK,
-                       "l2": "inputs (944 MB of uint8 frames per step) and activations exceed the 126 MB L2"},
+                       "l2": "inputs (944 MB of uint8 frames per step) and activations exceed the 126 MB L2",
+                       "host_cpus_bound_per_rank": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},

@@ -155,7 +155,7 @@ struct HeadParams {
 };
 
 constexpr int HEAD_ROWS_PER_CTA = 64;
-constexpr int DGRAD_SPLIT = 4;  // split-K factor of the recurrent dgrad GEMMs (K = 2120)
+constexpr int DGRAD_SPLIT = 4;  // maximum split-K factor of the recurrent dgrad GEMMs (K = 2120); see PpoPlan::dgrad_split
 
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   pdl_trigger();
@@ -450,6 +450,7 @@ struct PpoPlan {
   StorageRef* refs_dev = nullptr;
   OptTables opt;
   int launches = 0;
+  int dgrad_split = DGRAD_SPLIT;
 };
 
 template <typename T>
@@ -478,6 +479,12 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->dZ1 = dalloc<float>(rows * 2 * HID);
   P->dZ2 = dalloc<float>(rows * 2 * HID);
   P->dH = dalloc<float>(rows * LDF * DGRAD_SPLIT);
+  {
+    // split 4 -> 160 working CTAs at cfg 3; measured on B200: PPO update 9.26 ms (split 4), 9.55 (3), 9.78 (2)
+    int ks = DGRAD_SPLIT;
+    if (const char* ev = getenv("CADRE_DGRAD_SPLIT")) ks = atoi(ev) < 1 ? 1 : (atoi(ev) > DGRAD_SPLIT ? DGRAD_SPLIT : atoi(ev));
+    P->dgrad_split = ks;
+  }
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->sc.action = dalloc<int>(rows);
@@ -686,7 +693,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
   for (int t = 7; t >= 0; --t) {
     launch_k(lstm_bwd_kernel, dim3(dim3(bwd_blocks, E)), dim3(256), 0, s, P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
-                                                        t == 7, t == 7 ? 1 : DGRAD_SPLIT, dh_split_stride),
+                                                        t == 7, t == 7 ? 1 : P->dgrad_split, dh_split_stride),
         ++n;
     if (t > 0) {  // dh_{t-1} = dG_t W_hh
       GemmArgs g = tf32_gemm(0, 1);
@@ -695,7 +702,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
       g.M = cap, g.N = F, g.K = G;
       g.out = P->dH, g.ldc = LDF, g.out_bs = static_cast<long long>(cap) * LDF;
       g.batch_rows = P->counts;
-      g.ksplit = DGRAD_SPLIT, g.split_out_stride = dh_split_stride;  // 40 -> 160 CTAs; lstm_bwd sums the partials
+      g.ksplit = P->dgrad_split, g.split_out_stride = dh_split_stride;  // lstm_bwd sums the partials
       launch_gemm(g, s), ++n;
     }
   }

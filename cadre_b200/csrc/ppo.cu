@@ -388,25 +388,29 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__
   const int e = blockIdx.y;
   const int count = counts[e];
   const int rows_pad = min(cap, (count + 31) & ~31);
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int slot = static_cast<int>(gid / F), u = static_cast<int>(gid - static_cast<long long>(slot) * F);
-  if (slot >= rows_pad) return;
-  const long long row = static_cast<long long>(e) * cap + slot;
-  float4* dg = reinterpret_cast<float4*>(dG9 + (row * 9 + t) * G) + u;
-  if (slot >= count) {
-    *dg = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
+  // grid.x blocks per expert stride over the (slot, unit) cells that exist: no block is launched for the
+  // unused part of the capacity (the grid used to cover cap rows: 8 480 blocks, most of them exiting at once)
+  const long long cells = static_cast<long long>(rows_pad) * F;
+  for (long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gid < cells;
+       gid += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int slot = static_cast<int>(gid / F), u = static_cast<int>(gid - static_cast<long long>(slot) * F);
+    const long long row = static_cast<long long>(e) * cap + slot;
+    float4* dg = reinterpret_cast<float4*>(dG9 + (row * 9 + t) * G) + u;
+    if (slot >= count) {
+      *dg = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float4 g = *(reinterpret_cast<const float4*>(G9 + (row * 9 + t) * G) + u);  // i, f, g, o
+    const float c_prev = C9[(row * 9 + t) * LDF + u], c_t = C9[(row * 9 + t + 1) * LDF + u];
+    float dh = dH[row * LDF + u];  // split-K partial sums of the previous step's dgrad GEMM
+    for (int k = 1; k < nsplit; ++k) dh += dH[k * split_stride + row * LDF + u];
+    const float tc = tanhf(c_t);
+    float dc = dh * g.w * (1.f - tc * tc);
+    if (!first) dc += dC[row * LDF + u];
+    *dg = make_float4(dc * g.z * g.x * (1.f - g.x), dc * c_prev * g.y * (1.f - g.y), dc * g.x * (1.f - g.z * g.z),
+                      dh * tc * g.w * (1.f - g.w));
+    dC[row * LDF + u] = dc * g.y;
   }
-  const float4 g = *(reinterpret_cast<const float4*>(G9 + (row * 9 + t) * G) + u);  // i, f, g, o
-  const float c_prev = C9[(row * 9 + t) * LDF + u], c_t = C9[(row * 9 + t + 1) * LDF + u];
-  float dh = dH[row * LDF + u];  // split-K partial sums of the previous step's dgrad GEMM
-  for (int k = 1; k < nsplit; ++k) dh += dH[k * split_stride + row * LDF + u];
-  const float tc = tanhf(c_t);
-  float dc = dh * g.w * (1.f - tc * tc);
-  if (!first) dc += dC[row * LDF + u];
-  *dg = make_float4(dc * g.z * g.x * (1.f - g.x), dc * c_prev * g.y * (1.f - g.y), dc * g.x * (1.f - g.z * g.z),
-                    dh * tc * g.w * (1.f - g.w));
-  dC[row * LDF + u] = dc * g.y;
 }
 
 // column sums over the valid rows of each expert (bias gradients); deterministic
@@ -689,7 +693,8 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.batch_rows = P->counts;
     launch_gemm(g, s), ++n;
   }
-  const unsigned bwd_blocks = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
+  const unsigned bwd_full = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
+  const unsigned bwd_blocks = bwd_full < 74u ? bwd_full : 74u;   // x 8 experts = 4 blocks per SM, grid-stride inside
   const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
   for (int t = 7; t >= 0; --t) {
     launch_k(lstm_bwd_kernel, dim3(dim3(bwd_blocks, E)), dim3(256), 0, s, P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,

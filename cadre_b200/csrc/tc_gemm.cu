@@ -88,16 +88,16 @@ static void make_operand_map(CUtensorMap* m, int es, bool mn_major, const void* 
   make_map(m, es, 3, base, dims, str, box, mn_major && es == 4);
 }
 
-template <int KIND, int A_MN, int B_MN, int BN, int STAGES, int MODE, int EPI, typename OutT>
+template <int KIND, int A_MN, int B_MN, int BN, int STAGES, int MODE, int EPI, typename OutT, int EW = 1>
 static void launch_inst(const TcGemmParams& p, dim3 grid, cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, STAGES, MODE, EPI, OutT>;
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, STAGES, MODE, EPI, OutT, EW>;
   constexpr int smem = TcGemmSmem<KIND, BN, STAGES>::TOTAL;
   static bool configured = false;  // per instantiation
   if (!configured) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  launch_k(kern, dim3(grid), dim3(192), smem, stream, p);
+  launch_k(kern, dim3(grid), dim3(64 + 128 * EW), smem, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -248,6 +248,11 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(1, 0, 1, 128, 3, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(1, 1, 1, 128, 3, EPI_LINEAR, 1, float)
+  static const bool lstm_ew1 = getenv("CADRE_LSTM_EW1") != nullptr;   // A/B: four epilogue warps for the LSTM cell
+  if (a.kind == 1 && !a.a_mn && !a.b_mn && bn == 128 && a.epi == EPI_LSTM && a.out_f32 == 1 && !lstm_ew1) {
+    launch_inst<1, 0, 0, 128, 4, MODE_GEMM, EPI_LSTM, float, 2>(p, grid, stream);   // 8 epilogue warps, 1 CTA / SM
+    return;
+  }
   CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LSTM, 1, float)
 #undef CADRE_GEMM_CASE
   throw Error(1, "launch_gemm: unsupported (kind, majors, block_n, epilogue, out dtype) combination");

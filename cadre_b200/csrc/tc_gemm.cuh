@@ -82,8 +82,10 @@ __device__ __forceinline__ float load_as_float(const void* base, long long idx) 
     return reinterpret_cast<const float*>(base)[idx];
 }
 
-template <int KIND, int A_MN, int B_MN, int BLOCK_N, int STAGES, int MODE, int EPI, typename OutT>
-__global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+// EW = epilogue warps per TMEM lane quarter (1: 192 threads; 2: 320 threads, the two warps of a quarter split the
+// columns while draining TMEM and the rows afterwards: used where the epilogue is long, i.e. the LSTM cell)
+template <int KIND, int A_MN, int B_MN, int BLOCK_N, int STAGES, int MODE, int EPI, typename OutT, int EW = 1>
+__global__ void __launch_bounds__(64 + 128 * EW) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   constexpr int ES = KIND ? 4 : 2;         // operand element bytes
   constexpr int BK = 128 / ES;             // K elements per stage (one 128-byte swizzle row)
   constexpr int CHUNK = 128 / ES;          // MN elements per 128-byte row of an MN-major operand
@@ -228,7 +230,10 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
     // per 128x128 fp32 tile on B200, measured with clock64 stamps.)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     constexpr int LDS = BLOCK_N + 4;
-    float* stg = reinterpret_cast<float*>(smem) + (q * 32) * LDS;  // this warp's 32 rows (aliases the stages)
+    float* stg = reinterpret_cast<float*>(smem) + (q * 32) * LDS;  // this quarter's 32 rows (aliases the stages)
+    const int hf = EW == 2 ? (warp - 2) >> 2 : 0;   // which of the quarter's warps
+    constexpr int CPW = BLOCK_N / 32 / EW;           // 32-column TMEM loads per warp
+    const int r_lo = hf * (32 / EW), r_hi = r_lo + 32 / EW;   // rows of the quarter this warp finishes
     if (num_kb > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
     if (clk && threadIdx.x == 64) clk[4] = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = hf * CPW; c < (hf + 1) * CPW; ++c) {
       uint32_t r[32];
       if (num_kb > 0 && p.dbg_epi != 3) {
         tmem_ld_32x32(taddr + c * 32, r);
@@ -252,7 +257,10 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                         __uint_as_float(r[4 * j + 3]));
     }
-    __syncwarp();
+    if constexpr (EW == 2)
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // both warps of the quarter have staged their columns
+    else
+      __syncwarp();
     if (clk && threadIdx.x == 64) clk[7] = clock64();
 
     // With one epilogue warp per scheduler nothing hides instruction latency, so phase 2 is written for few
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           if (!general && vec) {
             // fast path: plain GEMM rows, coalesced 16-byte stores
 #pragma unroll 1
-            for (int rr = 0; rr < 32; rr += 4) {
+            for (int rr = r_lo; rr < r_hi; rr += 4) {
               float4 a4[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           } else {
             // general path: residual / ReLU-backward mask / ragged N / conv row mapping
 #pragma unroll 1
-            for (int rr = 0; rr < 32; ++rr) {
+            for (int rr = r_lo; rr < r_hi; ++rr) {
               const int row = q * 32 + rr;
               long long out_row;
               bool row_ok;
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(192) tc_gemm_kernel(const __grid_constant__ Tc
           // epilogue 30 k cycles, longer than the GEMM main loop (in-situ clock64 stamps, B200).
           constexpr int RB = 16;
 #pragma unroll 1
-          for (int rr = 0; rr < 32; rr += RB) {
+          for (int rr = r_lo; rr < r_hi; rr += RB) {
             float4 x4[RB];
             float cp[RB];
 #pragma unroll

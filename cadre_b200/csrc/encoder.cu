@@ -20,6 +20,10 @@ void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
 void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
                     cudaStream_t stream);
+#if CADRE_ENC_FP16
+void launch_pam_mma(const enc_t* x, enc_t* out, const float* wqk, const float* bqk, const enc_t* wv, const float* bv,
+                    float gamma, int B, int ldin, int num_sms, cudaStream_t stream);
+#endif
 void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, const float* bqk, float gamma,
                 int B, int ldin, int num_sms, cudaStream_t stream);
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
@@ -251,15 +255,28 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     a.Cout = 256, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->head5;
     launch_conv(a, s), step(e, s, n, "conv5a|conv5c");
   }
-  {  // PAM value projection for the whole batch on the tensor cores: V[B*40,128] = feat1 Wv^T + bv
-    GemmArgs g;
-    g.kind = 0, g.A = e->head5, g.lda = 256, g.B = e->w.pam_wv, g.ldb = 128;
-    g.M = B * 40, g.N = 128, g.K = 128;
-    g.out = e->pam_v, g.ldc = 128, g.out_f32 = 0, g.bias = e->w.pam_bv;
-    launch_gemm(g, s), step(e, s, n, "pam.value_conv");
+#if CADRE_ENC_FP16
+  static const bool pam_fp32 = getenv("CADRE_PAM_FP32") != nullptr;   // A/B switch: value GEMM + fp32 CUDA-core kernel
+#else
+  const bool pam_fp32 = true;
+#endif
+  if (!pam_fp32) {
+#if CADRE_ENC_FP16
+    launch_pam_mma(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, static_cast<const enc_t*>(e->w.pam_wv), e->w.pam_bv,
+                   e->w.pam_gamma, B, 256, e->num_sms, s);
+    step(e, s, n, "pam (value conv fused)");
+#endif
+  } else {
+    {  // PAM value projection for the whole batch on the tensor cores: V[B*40,128] = feat1 Wv^T + bv
+      GemmArgs g;
+      g.kind = 0, g.A = e->head5, g.lda = 256, g.B = e->w.pam_wv, g.ldb = 128;
+      g.M = B * 40, g.N = 128, g.K = 128;
+      g.out = e->pam_v, g.ldc = 128, g.out_f32 = 0, g.bias = e->w.pam_bv;
+      launch_gemm(g, s), step(e, s, n, "pam.value_conv");
+    }
+    launch_pam(e->head5, e->pam_v, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_gamma, B, 256, e->num_sms, s);
+    step(e, s, n, "pam");
   }
-  launch_pam(e->head5, e->pam_v, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_gamma, B, 256, e->num_sms, s);
-  step(e, s, n, "pam");
   launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), step(e, s, n, "cam");
   {
     ConvArgs a;

@@ -580,6 +580,221 @@ __global__ void __launch_bounds__(256) cam_mma_kernel(const enc_t* __restrict__ 
 }
 #endif
 
+#if CADRE_ENC_FP16
+// ---------------------------------------------------------------------------------------------------------
+// PAM on tensor cores, value projection included (da_att.py:32-51). Per frame, eight warps:
+//   1. [q | k | V] = X [W_q | W_k | W_v]^T + b on mma.sync.m16n8k16. The query / key weights are fp32 split into
+//      fp16 (hi, lo) pairs and both halves accumulate into the same fragment, q and k are split the same way
+//      for the energy product (hh + hl + lh), so the 40x40 energies keep fp32-level accuracy: they sit in an
+//      exponent. X, W_v, V and the attention weights are fp16 with fp32 accumulation.
+//   2. warps (m, h), m = 16-row block of pixels, h = half of the channels: energy row block -> softmax in
+//      registers -> the accumulator fragments are the A fragments of P V -> 1/rowsum -> staged fp32.
+//   3. gamma * out + x, coalesced fp16 stores.
+// Replaces the value-projection GEMM launch + the fp32 CUDA-core kernel (14 + 45 us per 640 frames).
+struct PamMmaSmem {
+  __half x[48][136];     // X[p][c], rows 40..47 zero
+  __half v[48][136];     // V[p][c], rows 40..47 zero
+  __half wqh[32][136];   // [W_q ; W_k] high halves
+  __half wql[32][136];   // low halves
+  __half wv[128][136];
+  __half qh[48][40];     // q (cols 0..15) | k (cols 16..31), high halves
+  __half ql[48][40];
+  float bqk[32];
+  float bv[128];
+  float o[40][132];
+};
+
+__global__ void __launch_bounds__(256) pam_mma_kernel(const enc_t* __restrict__ xin, enc_t* __restrict__ out,
+                                                      const float* __restrict__ wqk, const float* __restrict__ bqk,
+                                                      const enc_t* __restrict__ wv, const float* __restrict__ bv,
+                                                      float gamma, int B, int ldin) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t pam_raw2[];
+  PamMmaSmem& s = *reinterpret_cast<PamMmaSmem*>(pam_raw2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- once per CTA: weights (fp32 -> hi/lo fp16), biases, zero padding rows
+  for (int i = tid; i < 32 * PAM_C; i += 256) {
+    const int r = i >> 7, c = i & 127;
+    const float w = wqk[i];
+    const __half hi = __float2half_rn(w);
+    s.wqh[r][c] = hi;
+    s.wql[r][c] = __float2half_rn(w - __half2float(hi));
+  }
+  for (int i = tid; i < PAM_C * PAM_C / 8; i += 256) {
+    const int r = i >> 4, c8 = (i & 15) * 8;
+    *reinterpret_cast<uint4*>(&s.wv[r][c8]) = __ldg(reinterpret_cast<const uint4*>(wv + r * PAM_C + c8));
+  }
+  if (tid < 32) s.bqk[tid] = bqk[tid];
+  if (tid < 128) {
+    s.bv[tid] = bv[tid];
+    *reinterpret_cast<uint4*>(&s.x[40 + (tid >> 4)][(tid & 15) * 8]) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(&s.v[40 + (tid >> 4)][(tid & 15) * 8]) = make_uint4(0, 0, 0, 0);
+  }
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    __syncthreads();
+    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
+      const int p = i >> 4, c8 = (i & 15) * 8;
+      *reinterpret_cast<uint4*>(&s.x[p][c8]) = __ldg(reinterpret_cast<const uint4*>(xf + p * ldin + c8));
+    }
+    __syncthreads();
+    {  // ---- 1. projections: every warp two 8-column tiles of V, warps 0..3 also one tile of [q | k]
+      float av[3][2][4], aq[3][4];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[m][0][i] = av[m][1][i] = aq[m][i] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        uint32_t bvf[4], bqf[4];
+        ldsm_x4(bvf, &s.wv[16 * warp + (lane & 7) + ((lane >> 4) & 1) * 8][16 * kk + ((lane >> 3) & 1) * 8]);
+        if (warp < 4) {
+          const int sel = lane >> 3;   // matrices: hi / k lo, hi / k hi, lo / k lo, lo / k hi
+          const __half* wrow = (sel & 2) ? &s.wql[8 * warp + (lane & 7)][0] : &s.wqh[8 * warp + (lane & 7)][0];
+          ldsm_x4(bqf, wrow + 16 * kk + (sel & 1) * 8);
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          uint32_t af[4];
+          ldsm_x4(af, &s.x[16 * m + (lane & 7) + ((lane >> 3) & 1) * 8][16 * kk + ((lane >> 4) & 1) * 8]);
+          mma_16816(av[m][0], af, bvf[0], bvf[1]);
+          mma_16816(av[m][1], af, bvf[2], bvf[3]);
+          if (warp < 4) {
+            mma_16816(aq[m], af, bqf[0], bqf[1]);
+            mma_16816(aq[m], af, bqf[2], bqf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int c = 16 * warp + 8 * n + 2 * t;
+          const float b0 = s.bv[c], b1 = s.bv[c + 1];
+          const int r0 = 16 * m + g, r1 = r0 + 8;
+          if (r0 < PAM_P) *reinterpret_cast<uint32_t*>(&s.v[r0][c]) = pack_h2(av[m][n][0] + b0, av[m][n][1] + b1);
+          if (r1 < PAM_P) *reinterpret_cast<uint32_t*>(&s.v[r1][c]) = pack_h2(av[m][n][2] + b0, av[m][n][3] + b1);
+        }
+        if (warp < 4) {
+          const int c = 8 * warp + 2 * t;
+          const float b0 = s.bqk[c], b1 = s.bqk[c + 1];
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+            const int r = 16 * m + g + 8 * hrow;
+            const float v0 = aq[m][2 * hrow] + b0, v1 = aq[m][2 * hrow + 1] + b1;
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            *reinterpret_cast<__half2*>(&s.qh[r][c]) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(&s.ql[r][c]) =
+                __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < 6) {  // ---- 2. attention for pixel rows [16m, 16m+16), channels [64h, 64h+64)
+      const int m = warp % 3, h = warp / 3;
+      float e[6][4];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) e[j][0] = e[j][1] = e[j][2] = e[j][3] = 0.f;
+      uint32_t aqh[4], aql[4];
+      ldsm_x4(aqh, &s.qh[16 * m + (lane & 7) + ((lane >> 3) & 1) * 8][((lane >> 4) & 1) * 8]);
+      ldsm_x4(aql, &s.ql[16 * m + (lane & 7) + ((lane >> 3) & 1) * 8][((lane >> 4) & 1) * 8]);
+#pragma unroll
+      for (int jp = 0; jp < 3; ++jp) {
+        uint32_t bkh[4], bkl[4];
+        ldsm_x4(bkh, &s.qh[16 * jp + (lane & 7) + ((lane >> 4) & 1) * 8][16 + ((lane >> 3) & 1) * 8]);
+        ldsm_x4(bkl, &s.ql[16 * jp + (lane & 7) + ((lane >> 4) & 1) * 8][16 + ((lane >> 3) & 1) * 8]);
+        mma_16816(e[2 * jp], aqh, bkh[0], bkh[1]);
+        mma_16816(e[2 * jp], aqh, bkl[0], bkl[1]);
+        mma_16816(e[2 * jp], aql, bkh[0], bkh[1]);
+        mma_16816(e[2 * jp + 1], aqh, bkh[2], bkh[3]);
+        mma_16816(e[2 * jp + 1], aqh, bkl[2], bkl[3]);
+        mma_16816(e[2 * jp + 1], aql, bkh[2], bkh[3]);
+      }
+      e[5][0] = e[5][1] = e[5][2] = e[5][3] = -INFINITY;   // key positions 40..47 do not exist
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        mx[0] = fmaxf(mx[0], fmaxf(e[j][0], e[j][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(e[j][2], e[j][3]));
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
+        mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o));
+      }
+      float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        e[j][0] = __expf(e[j][0] - mx[0]), e[j][1] = __expf(e[j][1] - mx[0]);
+        e[j][2] = __expf(e[j][2] - mx[1]), e[j][3] = __expf(e[j][3] - mx[1]);
+        sum[0] += e[j][0] + e[j][1], sum[1] += e[j][2] + e[j][3];
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+      }
+      float oacc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        uint32_t af[4];
+        af[0] = pack_h2(e[2 * kk][0], e[2 * kk][1]), af[1] = pack_h2(e[2 * kk][2], e[2 * kk][3]);
+        af[2] = pack_h2(e[2 * kk + 1][0], e[2 * kk + 1][1]), af[3] = pack_h2(e[2 * kk + 1][2], e[2 * kk + 1][3]);
+#pragma unroll
+        for (int cp = 0; cp < 4; ++cp) {
+          uint32_t bf[4];
+          ldsm_x4_trans(bf, &s.v[16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8][64 * h + 16 * cp + ((lane >> 4) & 1) * 8]);
+          mma_16816(oacc[2 * cp], af, bf[0], bf[1]);
+          mma_16816(oacc[2 * cp + 1], af, bf[2], bf[3]);
+        }
+      }
+      const float inv[2] = {1.f / sum[0], 1.f / sum[1]};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 64 * h + 8 * j + 2 * t;
+        const int r0 = 16 * m + g, r1 = r0 + 8;
+        if (r0 < PAM_P) *reinterpret_cast<float2*>(&s.o[r0][c]) = make_float2(oacc[j][0] * inv[0], oacc[j][1] * inv[0]);
+        if (r1 < PAM_P) *reinterpret_cast<float2*>(&s.o[r1][c]) = make_float2(oacc[j][2] * inv[1], oacc[j][3] * inv[1]);
+      }
+    }
+    __syncthreads();
+    enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
+    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
+      const int p = i >> 4, c8 = (i & 15) * 8;
+      const float4 o_lo = *reinterpret_cast<const float4*>(&s.o[p][c8]);
+      const float4 o_hi = *reinterpret_cast<const float4*>(&s.o[p][c8 + 4]);
+      const uint4 ux = *reinterpret_cast<const uint4*>(&s.x[p][c8]);
+      const __half* hx = reinterpret_cast<const __half*>(&ux);
+      uint4 u;
+      u.x = enc_pack2(gamma * o_lo.x + __half2float(hx[0]), gamma * o_lo.y + __half2float(hx[1]));
+      u.y = enc_pack2(gamma * o_lo.z + __half2float(hx[2]), gamma * o_lo.w + __half2float(hx[3]));
+      u.z = enc_pack2(gamma * o_hi.x + __half2float(hx[4]), gamma * o_hi.y + __half2float(hx[5]));
+      u.w = enc_pack2(gamma * o_hi.z + __half2float(hx[6]), gamma * o_hi.w + __half2float(hx[7]));
+      *reinterpret_cast<uint4*>(of + p * PAM_C + c8) = u;
+    }
+  }
+}
+
+void launch_pam_mma(const enc_t* x, enc_t* out, const float* wqk, const float* bqk, const enc_t* wv, const float* bv,
+                    float gamma, int B, int ldin, int num_sms, cudaStream_t stream) {
+  static bool cfg = false;
+  if (!cfg) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(pam_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(sizeof(PamMmaSmem))));
+    cfg = true;
+  }
+  const int grid = B < 2 * num_sms ? B : 2 * num_sms;
+  launch_k(pam_mma_kernel, dim3(grid), dim3(256), sizeof(PamMmaSmem), stream, x, out, wqk, bqk, wv, bv, gamma, B, ldin);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+#endif
+
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
                 cudaStream_t stream) {
   static bool cfg = false;

@@ -39,7 +39,7 @@ __global__ void route_max_kernel(const uint8_t* __restrict__ route, uint8_t* __r
   }
 }
 
-// One block = 32 pixels x 8 row pairs of one image. The route map is [n][x][y] (y contiguous) while the output is
+// One block = 4 x 32 pixels x 8 row pairs of one image. The route map is [n][x][y] (y contiguous) while the output is
 // x-major, so its 32 x 16 byte tile is transposed through shared memory (lanes along y when loading: whole
 // sectors; the direct x-strided byte reads fetched every sector 16 times). k / 255 comes from a 256-entry table
 // (same double division + float + fp16 roundings as the reference, done once on the host instead of three
@@ -51,58 +51,64 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
                                                          enc_t* __restrict__ out, int B) {
   pdl_trigger();
   pdl_wait();
+  constexpr int XT = 4;                     // 32-pixel tiles per block (fewer, fatter blocks: block launch rate
+                                            // bounded the one-tile version)
   __shared__ enc_t lut[256];
-  __shared__ uint8_t s_route[32][20];   // [x][y - ybase], 16 rows used
+  __shared__ uint8_t s_route[32 * XT][20];  // [x][y - ybase], 16 rows used
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * 32;          // 8 tiles across
-  const int yb = blockIdx.y;               // 0..9: row pairs y2 = 1 + 8*yb .. (73 row pairs: the last block has one)
+  const int x0 = blockIdx.x * 32 * XT;      // 256 / (32 * XT) blocks across
+  const int yb = blockIdx.y;                // 0..9: row pairs y2 = 1 + 8*yb .. (73 row pairs: the last block has one)
   const int n = blockIdx.z;
-  const int ybase = 2 * (1 + 8 * yb) - 3;  // unpadded row of (y2 = first, r = 0)
+  const int ybase = 2 * (1 + 8 * yb) - 3;   // unpadded row of (y2 = first, r = 0)
   const int lx = tid & 31, ly = tid >> 5;   // pixel, row pair within the tile
   const int y2 = 1 + 8 * yb + ly;
-  const int x = x0 + lx;
-  // every global load of the block is issued before the first barrier (one memory round trip per block: the
-  // kernel is a chain of short blocks, 103 us with three dependent round trips against 46 us of HBM time)
+  // every global load of the block is issued before the barrier: one memory round trip per block
   const enc_t lut_v = lut_g[tid];
-  uint8_t rt[2];
+  uint8_t rt[XT][2];
   {
     const int ty = tid & 15, tx = tid >> 4;   // 16 lanes along y, 16 x rows per pass
+    const int y = ybase + ty;
+    const bool yok = y >= 0 && y < 144;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int y = ybase + ty;
-      rt[k] = (y >= 0 && y < 144) ? route[(static_cast<long long>(n) * 256 + x0 + tx + 16 * k) * 144 + y] : 0;
-    }
+    for (int k = 0; k < 2 * XT; ++k)
+      rt[k >> 1][k & 1] = yok ? route[(static_cast<long long>(n) * 256 + x0 + tx + 16 * k) * 144 + y] : 0;
   }
-  uint8_t pb[2][3];
+  uint8_t pb[XT][2][3];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int y = 2 * y2 + r - 3;  // unpadded row
-    const bool ok = y2 <= 73 && y >= 0 && y < 144;
-    const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + (ok ? y : 0)) * 256 + x) * 3;
-    pb[r][0] = ok ? px[0] : 0, pb[r][1] = ok ? px[1] : 0, pb[r][2] = ok ? px[2] : 0;
+  for (int xt = 0; xt < XT; ++xt) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int y = 2 * y2 + r - 3;  // unpadded row
+      const bool ok = y2 <= 73 && y >= 0 && y < 144;
+      const uint8_t* px = rgb + ((static_cast<long long>(n) * 144 + (ok ? y : 0)) * 256 + x0 + 32 * xt + lx) * 3;
+      pb[xt][r][0] = ok ? px[0] : 0, pb[xt][r][1] = ok ? px[1] : 0, pb[xt][r][2] = ok ? px[2] : 0;
+    }
   }
   const uint8_t mx = route_max[n];
   lut[tid] = lut_v;   // k / 255 as the reference rounds it (table built once on the host)
-  s_route[(tid >> 4)][tid & 15] = rt[0];
-  s_route[(tid >> 4) + 16][tid & 15] = rt[1];
+#pragma unroll
+  for (int k = 0; k < 2 * XT; ++k) s_route[(tid >> 4) + 16 * k][tid & 15] = rt[k >> 1][k & 1];
   __syncthreads();
   if (y2 > 73) return;
-  enc_t v[8];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int y = 2 * y2 + r - 3;  // unpadded row
-    if (y >= 0 && y < 144) {
-      v[4 * r + 0] = lut[pb[r][0]];
-      v[4 * r + 1] = lut[pb[r][1]];
-      v[4 * r + 2] = lut[pb[r][2]];
-      const uint8_t rv = s_route[lx][y - ybase];
-      v[4 * r + 3] = enc_from_float((mx > 0) ? ((rv == mx) ? 1.f : 0.f) : static_cast<float>(rv));
-    } else {
-      v[4 * r + 0] = v[4 * r + 1] = v[4 * r + 2] = v[4 * r + 3] = enc_from_float(0.f);
+  for (int xt = 0; xt < XT; ++xt) {
+    enc_t v[8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int y = 2 * y2 + r - 3;  // unpadded row
+      if (y >= 0 && y < 144) {
+        v[4 * r + 0] = lut[pb[xt][r][0]];
+        v[4 * r + 1] = lut[pb[xt][r][1]];
+        v[4 * r + 2] = lut[pb[xt][r][2]];
+        const uint8_t rv = s_route[32 * xt + lx][y - ybase];
+        v[4 * r + 3] = enc_from_float((mx > 0) ? ((rv == mx) ? 1.f : 0.f) : static_cast<float>(rv));
+      } else {
+        v[4 * r + 0] = v[4 * r + 1] = v[4 * r + 2] = v[4 * r + 3] = enc_from_float(0.f);
+      }
     }
+    enc_t* dst = out + ((static_cast<long long>(n) * 75 + y2) * 262 + (x0 + 32 * xt + lx + 3)) * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
   }
-  enc_t* dst = out + ((static_cast<long long>(n) * 75 + y2) * 262 + (x + 3)) * 8;
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
 }
 
 __global__ void f32_to_enc_kernel(const float* __restrict__ in, enc_t* __restrict__ out, int n) {
@@ -117,7 +123,7 @@ void launch_f32_to_enc(const float* in, enc_t* out, int n, cudaStream_t stream) 
 void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, const enc_t* lut,
                        enc_t* out, int B, cudaStream_t stream) {
   launch_k(route_max_kernel, dim3(B), dim3(256), 0, stream, route, route_max_ws);
-  launch_k(preprocess_kernel, dim3(8, 10, B), dim3(256), 0, stream, rgb, route, route_max_ws, lut, out, B);
+  launch_k(preprocess_kernel, dim3(2, 10, B), dim3(256), 0, stream, rgb, route, route_max_ws, lut, out, B);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -100,3 +100,48 @@ def test_attention_stages_match_oracle(encoders, tag):
     assert rel_l2(nhwc(3, 128), sa) < REL_FEATURE
     assert rel_l2(nhwc(4, 128), sc) < 5e-3
     assert rel_l2(nhwc(1, 128), fs) < REL_FEATURE
+
+
+def test_fused_shortcut_matches_separate_downsample_launches():
+    """layer2.0 / 3.0 / 4.0: the 1x1/stride-2 shortcut as extra k-blocks of conv2 (default) against the separate
+    downsample conv + residual add (CADRE_NO_SHORTCUT_FUSION=1, read when the encoder is created)."""
+    from cadre_b200.encoder import Encoder
+    sd = R.danet_fixture_state(0)
+    x = torch.from_numpy(np.random.RandomState(5).rand(7, 4, 144, 256).astype(np.float32)).cuda()
+    fused_enc = Encoder(sd, "cuda:0", max_batch=8)
+    fused = fused_enc.forward_f32(x).cpu()
+    os.environ["CADRE_NO_SHORTCUT_FUSION"] = "1"
+    try:
+        plain_enc = Encoder(sd, "cuda:0", max_batch=8)
+    finally:
+        del os.environ["CADRE_NO_SHORTCUT_FUSION"]
+    plain = plain_enc.forward_f32(x).cpu()
+    assert plain_enc.launches_per_forward == fused_enc.launches_per_forward + 3   # counted during a forward
+    assert rel_l2(fused, plain) < 2e-3          # the fused form keeps the shortcut in fp32 instead of rounding it to fp16
+    with torch.no_grad():
+        ref = R.encoder_latent(x.cpu(), sd)
+    assert rel_l2(fused, ref) < REL_FEATURE and rel_l2(plain, ref) < REL_FEATURE
+
+
+def test_two_encoders_on_two_streams_match_sequential(encoders):
+    """bench.py's scheduling: independent chunks on two encoder instances / two streams give the results of one
+    encoder on one stream, bit for bit."""
+    from cadre_b200.encoder import Encoder
+    sd = R.danet_fixture_state(0)
+    enc_a, enc_b = encoders["base"], Encoder(sd, "cuda:0", max_batch=32)
+    g = torch.Generator().manual_seed(11)
+    rgb = torch.randint(0, 256, (64, 144, 256, 3), dtype=torch.uint8, generator=g).cuda()
+    route = (torch.rand(64, 256, 144, generator=g) < 0.1).to(torch.uint8).mul(255).cuda()
+    meas = torch.rand(64, 3, dtype=torch.float64, generator=g).cuda()
+    ref = torch.cat([enc_a.forward_u8(rgb[s:s + 32], route[s:s + 32], meas[s:s + 32]) for s in (0, 32)])
+    torch.cuda.synchronize()
+    out = torch.empty_like(ref)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):
+        out.zero_()
+        torch.cuda.synchronize()
+        for k, (e, s) in enumerate(((enc_a, 0), (enc_b, 32))):
+            with torch.cuda.stream(streams[k]):
+                e.forward_u8(rgb[s:s + 32], route[s:s + 32], meas[s:s + 32], out[s:s + 32])
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)

@@ -411,6 +411,33 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
     CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
     configured = true;
   }
+  // opt-in: measured SLOWER on B200 (layer1 conv 160 us against 129 us: a 256x64x16 cta_group::2 MMA does not beat two
+  // independent 128x64x16 MMAs, and the pair advances in lock step)
+  static const bool flat_pairs = getenv("CADRE_FLAT_PAIRS") != nullptr;
+  if (flat_pairs) {
+    // cta_group::2 variant: each CTA of a pair loads 32 of the 64 weight rows of every tap
+    const uint32_t wbox2[2] = {64, 32};
+    make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox2);
+    static bool configured2 = false;
+    if (!configured2) {
+      CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
+      configured2 = true;
+    }
+    const int pair_tiles = (p.num_tiles + 1) / 2;
+    int pairs = num_sms() / 2;
+    if (pair_tiles < pairs) pairs = pair_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = FLAT_SMEM, cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_flat3x3_pair_kernel, p));
+    return;
+  }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   launch_k(tc_flat3x3_kernel, dim3(grid), dim3(320), FLAT_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());

@@ -153,3 +153,18 @@ def test_config_and_synthetic_env_contract():
     assert t["route_fig"].shape == (8, 256, 144) and t["measurements"].shape == (8, 3) and 0 <= t["command"] < 4
     t2, r, done, info = env.step([0.0, 0.6, 0.0])
     assert np.array_equal(t2["rgb"][:7], t["rgb"][1:]) and r.shape == (2,) and len(info["action_done"]) == 2
+
+
+def test_sync_primitive_shims_keep_the_reference_interface():
+    """ppo_agent/utils.py:31-70, 108-126: Counter / TrafficLight as used by train.py:101-110 and chief.py:12-24."""
+    from cadre_b200.utils import Counter, TrafficLight
+    c, light = Counter(), TrafficLight()
+    assert c.get() == 0 and light.get() is False
+    c.increment(), c.increment()
+    assert c.get() == 2
+    c.reset()
+    assert c.get() == 0
+    light.switch()
+    assert light.get() is True
+    light.switch()
+    assert light.get() is False

@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKERS, T, SEQ, MB_NUM, PPO_EPOCH = 4, 200, 8, 2, 4
 FRAMES_PER_STEP = WORKERS * T * SEQ           # per rank
-ENC_CHUNK = 640                               # frames per encoder call (10 chunks per step)
+ENC_CHUNK = int(os.environ.get("CADRE_BENCH_CHUNK", "640"))   # frames per encoder call (divides 6400)
 METRIC = "encoder+PPO-update frames/sec"
 WORKLOAD = ("cfg3 learner iteration per GPU: 4 workers x T=200 x 8 frames encoder fwd (6400 u8 frames 144x256) + "
             "GAE + 4 epochs x 2 minibatches x 400 rows PPO update (fwd+bwd, allreduce, clip+Adam)")
@@ -324,8 +324,11 @@ def run_cadre(args):
 
     # e2e chunk schedule: the encoder cannot start before its first chunk has landed, so the first chunks are
     # small (128 frames = 19 MB = 0.35 ms of PCIe time instead of 1.7 ms for 640 frames)
-    e2e_sizes = [128, 512] + [ENC_CHUNK] * ((n - 640) // ENC_CHUNK) if n >= 1280 and ENC_CHUNK == 640 else \
-        [ENC_CHUNK] * (n // ENC_CHUNK)
+    if ENC_CHUNK % 640 == 0 and n % ENC_CHUNK == 0 and n > ENC_CHUNK:
+        ramp = [128, 512] + [640 * 2 ** i for i in range(8) if 640 * 2 ** (i + 1) <= ENC_CHUNK]   # 128, 512, 640, 1280, ...
+        e2e_sizes = ramp + [ENC_CHUNK] * ((n - sum(ramp)) // ENC_CHUNK)
+    else:
+        e2e_sizes = [ENC_CHUNK] * (n // ENC_CHUNK)
     assert sum(e2e_sizes) == n
     e2e_starts = [sum(e2e_sizes[:i]) for i in range(len(e2e_sizes))]
 

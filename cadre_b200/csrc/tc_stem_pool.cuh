@@ -183,10 +183,14 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
     __syncwarp();
     if (lane == 0)
       for (int sl = 0; sl < SP_SLOTS; ++sl) mbar_arrive(&tempty[sl]);
-    int lt = 0;
+    int lt = 0, npool = 0;
+    uint32_t prev[16], vm[16];          // packed pairs: the odd conv row above, the running vertical maximum
+#pragma unroll
+    for (int i = 0; i < 16; ++i) prev[i] = vm[i] = 0u;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int img, r0, c0, c1;
       unit_rows(unit, img, r0, c0, c1);
+      bool have_prev = false;
       for (int oh = c0; oh <= c1; ++oh, ++lt) {
         const int as = lt % SP_SLOTS;
         const uint32_t aph = (lt / SP_SLOTS) & 1;
@@ -204,62 +208,73 @@ __global__ void __launch_bounds__(320, 1) tc_stem_pool_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
-        // bias + ReLU + fp16 into the conv-row ring: pixel px = 128 B, 16-byte chunk index XOR (px & 7)
-        uint8_t* rowp = row_s + (oh % 3) * SP_ROW_BYTES + px * 128;
+        // bias + ReLU + fp16 pack in registers. The 3x3/s2 max-pool is separable and this thread sees the SAME pixel
+        // column in every conv row, so the vertical max (rows 2r-1, 2r, 2r+1) stays in registers; only the vertically
+        // reduced row goes to shared memory (once per pooled row) for the horizontal 3-max + stride-2 pick:
+        // 41 KB of shared-memory traffic per pooled row instead of 106 KB (the kernel was bound by that traffic).
+#if CADRE_ENC_FP16
+        typedef __half2 enc2_t;
+#else
+        typedef __nv_bfloat162 enc2_t;
+#endif
+        uint32_t cur[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + bias_r[8 * j + i];
-          uint4 u;
-          u.x = enc_pack2_relu(v[0], v[1]), u.y = enc_pack2_relu(v[2], v[3]);
-          u.z = enc_pack2_relu(v[4], v[5]), u.w = enc_pack2_relu(v[6], v[7]);
-          const int chunk = half * 4 + j;
-          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (px & 7)) << 4)) = u;
-        }
-        sp_epi_bar();
+        for (int i = 0; i < 16; ++i)
+          cur[i] = enc_pack2_relu(__uint_as_float(r[2 * i]) + bias_r[2 * i], __uint_as_float(r[2 * i + 1]) + bias_r[2 * i + 1]);
         const long long e2 = dbgl ? clock64() : 0;
         if (dbgl) p.dbg[blockIdx.x * 16 + 7] += e1 - e0, p.dbg[blockIdx.x * 16 + 8] += e2 - e1;
-        if ((oh & 1) && ((oh - 1) >> 1) >= r0) {  // (the unit's halo row above r0 only feeds pooled row r0)
-          // pooled row r = (oh-1)/2 from conv rows oh-2 (absent for r == 0), oh-1, oh; 64 px x 8 chunks
+        bool emit = false;
+        if ((oh & 1) == 0) {   // row 2r: start the pooled row from the kept odd row above it (absent for r == 0)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            enc2_t m = *reinterpret_cast<enc2_t*>(&cur[i]);
+            if (have_prev) m = __hmax2(m, *reinterpret_cast<enc2_t*>(&prev[i]));
+            vm[i] = *reinterpret_cast<uint32_t*>(&m);
+          }
+        } else if (((oh - 1) >> 1) >= r0) {   // row 2r+1 completes pooled row r
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            enc2_t m = __hmax2(*reinterpret_cast<enc2_t*>(&vm[i]), *reinterpret_cast<enc2_t*>(&cur[i]));
+            vm[i] = *reinterpret_cast<uint32_t*>(&m);
+          }
+          emit = true;
+        }
+        if (oh & 1) {   // an odd row is also row 2(r+1)-1 of the next pooled row (the unit's halo row only that)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) prev[i] = cur[i];
+          have_prev = true;
+        }
+        if (emit) {
           const int r = (oh - 1) >> 1;
-          const int ylo = (oh >= 2) ? oh - 2 : oh - 1;
+          uint8_t* vrow = row_s + (npool & 1) * SP_ROW_BYTES;   // double buffered: one barrier per pooled row
+          ++npool;
+          uint8_t* rowp = vrow + px * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = half * 4 + j;
+            *reinterpret_cast<uint4*>(rowp + ((chunk ^ (px & 7)) << 4)) =
+                make_uint4(vm[4 * j], vm[4 * j + 1], vm[4 * j + 2], vm[4 * j + 3]);
+          }
+          sp_epi_bar();
           enc_t* orow = p.out + ((static_cast<long long>(img) * 38 + r + 1) * 66 + 1) * 64;
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
-            const int item = et + it * 256;      // 0..511
+            const int item = et + it * 256;      // 0..511: pooled pixel pw, 16-byte channel chunk
             const int pw = item >> 3, chunk = item & 7;
-            // max over the 3x3 window on packed pairs (4 HMNMX2 per 16 bytes); post-ReLU values are >= 0,
-            // so 0 acts as the -inf padding
-#if CADRE_ENC_FP16
-            typedef __half2 enc2_t;
-#else
-            typedef __nv_bfloat162 enc2_t;
-#endif
-            uint4 o = make_uint4(0, 0, 0, 0);
+            uint4 u[3];
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {   // column -1 is padding: re-reading column 0 leaves the max unchanged
+              const int x = (2 * pw + dx >= 0) ? 2 * pw + dx : 0;
+              u[dx + 1] = *reinterpret_cast<const uint4*>(vrow + x * 128 + ((chunk ^ (x & 7)) << 4));
+            }
+            uint4 o;
             enc2_t* m2 = reinterpret_cast<enc2_t*>(&o);
-            // fixed 3 x 3 trip count (fully unrolled: all nine 16-byte loads are in flight together); a window
-            // position outside the image re-reads a valid one, which leaves the maximum unchanged
-            uint4 u[9];
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const int y = (oh - dy >= ylo) ? oh - dy : oh;
-              const uint8_t* yrow = row_s + (y % 3) * SP_ROW_BYTES;
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                const int x = (2 * pw + dx >= 0) ? 2 * pw + dx : 0;
-                u[dy * 3 + dx + 1] = *reinterpret_cast<const uint4*>(yrow + x * 128 + ((chunk ^ (x & 7)) << 4));
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              const enc2_t* h2 = reinterpret_cast<const enc2_t*>(&u[k]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) m2[i] = __hmax2(m2[i], h2[i]);
-            }
+            for (int i = 0; i < 4; ++i)
+              m2[i] = __hmax2(__hmax2(reinterpret_cast<const enc2_t*>(&u[0])[i], reinterpret_cast<const enc2_t*>(&u[1])[i]),
+                              reinterpret_cast<const enc2_t*>(&u[2])[i]);
             *reinterpret_cast<uint4*>(orow + pw * 64 + chunk * 8) = o;
           }
-          sp_epi_bar();  // the ring slot of row oh-2 is overwritten by conv row oh+1
           if (dbgl) p.dbg[blockIdx.x * 16 + 9] += clock64() - e2;
         }
       }

@@ -455,6 +455,10 @@ struct PpoPlan {
   OptTables opt;
   int launches = 0;
   int dgrad_split = DGRAD_SPLIT;
+  // side stream for the gradient kernels that are off the critical path (dW2, dW1, bias column sums)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_bptt = nullptr, ev_join = nullptr;
+  bool use_side = true;
 };
 
 template <typename T>
@@ -489,6 +493,11 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
     if (const char* ev = getenv("CADRE_DGRAD_SPLIT")) ks = atoi(ev) < 1 ? 1 : (atoi(ev) > DGRAD_SPLIT ? DGRAD_SPLIT : atoi(ev));
     P->dgrad_split = ks;
   }
+  P->use_side = getenv("CADRE_PPO_NO_SIDE_STREAM") == nullptr;
+  CADRE_CUDA_CHECK(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_bptt, cudaEventDisableTiming));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->sc.action = dalloc<int>(rows);
@@ -561,6 +570,10 @@ static void ppo_destroy(PpoPlan* P) {
                   P->row_expert, P->counts, P->counts9, P->idx_dev, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
                   P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
   for (void* p : ptrs) cudaFree(p);
+  if (P->side) cudaStreamDestroy(P->side);
+  if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  if (P->ev_bptt) cudaEventDestroy(P->ev_bptt);
+  if (P->ev_join) cudaEventDestroy(P->ev_join);
   delete P;
 }
 
@@ -648,18 +661,11 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     CADRE_CUDA_CHECK(cudaGetLastError());
   }
 
-  // ---- backward
+  // ---- backward. Critical path: head -> dZ1 -> dh_8 -> 8 x (LSTM cell backward, dgrad) -> LSTM weight gradients.
+  // The second-layer / first-layer weight gradients and the bias column sums only consume finished tensors, so
+  // they run on a side stream next to the BPTT chain (whose kernels leave most SMs idle).
   const long long bs256 = static_cast<long long>(cap) * 2 * HID;
   for (int br = 0; br < 2; ++br) {
-    {  // dW2 = dZ2^T Y1
-      GemmArgs g = tf32_gemm(1, 1);
-      g.A = P->dZ2 + br * HID, g.lda = 2 * HID, g.a_bs = bs256;
-      g.B = P->Y1 + br * HID, g.ldb = 2 * HID, g.b_bs = bs256;
-      g.M = HID, g.N = HID, g.K = cap;
-      g.out = grads + OFF_W2 + br * HID * HID, g.ldc = HID, g.out_bs = 2LL * HID * HID;
-      g.batch_rows = P->counts, g.rows_is_k = 1;
-      launch_gemm(g, s), ++n;
-    }
     {  // dZ1 = (dZ2 W2) * relu'(Y1)
       GemmArgs g = tf32_gemm(0, 1);
       g.A = P->dZ2 + br * HID, g.lda = 2 * HID, g.a_bs = bs256;
@@ -671,9 +677,25 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
       launch_gemm(g, s), ++n;
     }
   }
-  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s, P->dZ2, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B2, 2 * HID,
+  cudaStream_t s2 = P->use_side ? P->side : s;
+  if (P->use_side) {
+    CADRE_CUDA_CHECK(cudaEventRecord(P->ev_fork, s));
+    CADRE_CUDA_CHECK(cudaStreamWaitEvent(s2, P->ev_fork, 0));
+  }
+  for (int br = 0; br < 2; ++br) {
+    {  // dW2 = dZ2^T Y1
+      GemmArgs g = tf32_gemm(1, 1);
+      g.A = P->dZ2 + br * HID, g.lda = 2 * HID, g.a_bs = bs256;
+      g.B = P->Y1 + br * HID, g.ldb = 2 * HID, g.b_bs = bs256;
+      g.M = HID, g.N = HID, g.K = cap;
+      g.out = grads + OFF_W2 + br * HID * HID, g.ldc = HID, g.out_bs = 2LL * HID * HID;
+      g.batch_rows = P->counts, g.rows_is_k = 1;
+      launch_gemm(g, s2), ++n;
+    }
+  }
+  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s2, P->dZ2, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B2, 2 * HID,
                                            nullptr), ++n;
-  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s, P->dZ1, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B1, 2 * HID,
+  launch_k(colsum_kernel, dim3(dim3(8, E)), dim3(256), 0, s2, P->dZ1, 2 * HID, bs256, P->counts, 2 * HID, grads + OFF_B1, 2 * HID,
                                            nullptr), ++n;
   {  // dW1 = dZ1^T h_8
     GemmArgs g = tf32_gemm(1, 1);
@@ -682,7 +704,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.M = 2 * HID, g.N = F, g.K = cap;
     g.out = grads + OFF_W1, g.ldc = LDF, g.out_bs = 2LL * HID * LDF;
     g.batch_rows = P->counts, g.rows_is_k = 1;
-    launch_gemm(g, s), ++n;
+    launch_gemm(g, s2), ++n;
   }
   {  // dh_8 = dZ1 W1
     GemmArgs g = tf32_gemm(0, 1);
@@ -712,6 +734,13 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     }
   }
   CADRE_CUDA_CHECK(cudaGetLastError());
+  if (P->use_side) {   // dG9 is complete: its column sums (LSTM bias gradients) run next to the weight-gradient GEMMs
+    CADRE_CUDA_CHECK(cudaEventRecord(P->ev_bptt, s));
+    CADRE_CUDA_CHECK(cudaStreamWaitEvent(s2, P->ev_bptt, 0));
+  }
+  launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s2, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
+                                                       grads + OFF_BHH), ++n;
+  if (P->use_side) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_join, s2));
   for (int which = 0; which < 2; ++which) {  // dW_ih = dG9^T X9, dW_hh = dG9^T H9 (K = 9 * rows)
     GemmArgs g = tf32_gemm(1, 1);
     g.A = P->dG9, g.lda = G, g.a_bs = rs9G;
@@ -721,8 +750,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.batch_rows = P->counts9, g.rows_is_k = 1;
     launch_gemm(g, s), ++n;
   }
-  launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
-                                                       grads + OFF_BHH), ++n;
+  if (P->use_side) CADRE_CUDA_CHECK(cudaStreamWaitEvent(s, P->ev_join, 0));
   CADRE_CUDA_CHECK(cudaGetLastError());
   P->launches = n;
 }

@@ -237,7 +237,7 @@ def run_cadre(args):
         dist.barrier()
     from cadre_b200.encoder import Encoder
     from cadre_b200.learner import Learner, RolloutPool
-    from oracle import restate as R   # fixture weights only (name-keyed seeded tensors); nothing is computed with it
+    from cadre_b200 import fixtures as R   # seeded synthetic weights (no checkpoint on the box)
 
     enc = Encoder(R.danet_fixture_state(0), dev, max_batch=ENC_CHUNK)
     mb = T // MB_NUM

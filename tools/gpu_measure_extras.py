@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cadre_b200 import ppo, ppo_params
 from cadre_b200.encoder import Encoder
 from cadre_b200.learner import Learner, RolloutPool
-from oracle import restate as R
+from cadre_b200 import fixtures as R
 dev = "cuda:0"
 peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6453.1, "bf16_tflops_sustained": 1417.3}

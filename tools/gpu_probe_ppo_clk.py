@@ -7,7 +7,7 @@ torch.zeros(1, device=dev)
 clk = torch.zeros(4 * 17 * 8 * 8 * 4, dtype=torch.int64, device=dev)
 os.environ["CADRE_DBG_CLK_EPI"] = f"{sys.argv[1] if len(sys.argv) > 1 else 1}:{clk.data_ptr()}"
 from cadre_b200.learner import Learner, RolloutPool
-from oracle import restate as R
+from cadre_b200 import fixtures as R
 W = 4
 learner = Learner(W, 100, R.ppo_fixture_state(0), dev, seeds=list(range(W)))
 pool = RolloutPool(W, dict(num_steps=200, mini_batch_num=2, feature_dims=530, seq_length=8, use_gae=True, gamma=0.99, tau=0.95), dev)

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cadre_b200 import _lib  # noqa: E402
 from cadre_b200.encoder import Encoder  # noqa: E402
-from oracle import restate as R  # noqa: E402  (fixture weights only; tools/ is not product code)
+from cadre_b200 import fixtures as R
 
 
 def persist_table(d, names):

@@ -2,7 +2,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cadre_b200.encoder import Encoder
-from oracle import restate as R
+from cadre_b200 import fixtures as R
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 640
 enc = Encoder(R.danet_fixture_state(0), "cuda:0", max_batch=B)
 x = torch.rand(B, 4, 144, 256, device="cuda")

@@ -3,7 +3,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cadre_b200.learner import Learner, RolloutPool
-from oracle import restate as R
+from cadre_b200 import fixtures as R
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = "cuda:0"
 learner = Learner(W, 100, R.ppo_fixture_state(0), dev, seeds=list(range(W)))

@@ -143,3 +143,37 @@ def test_learner_two_steps_match_chief_contract():
     a = torch.cat([post[m][n].flatten() for m in post for n in post[m]])
     b = torch.cat([pref[m][n].flatten() for m in post for n in post[m]])
     assert rel(a, b) < 2e-3          # theta after one step (TF32 gradients, Adam sign sensitivity)
+
+
+def test_batched_actor_with_frame_cache_equals_single_env_act(agent):
+    """E environments acted on in one batch, only the newest frame of each sliding 8-frame window
+    encoded; features and values equal CadreAgent.act on the full windows (same kernels, row-independent math)."""
+    from cadre_b200.actor import BatchedActor
+    E, ticks_n = 3, 4
+    rs = np.random.RandomState(7)
+    streams = []
+    for e in range(E):   # per env: 8 + ticks_n - 1 frames; tick t sees frames [t, t+8)
+        n = 8 + ticks_n - 1
+        streams.append(dict(rgb=rs.randint(0, 256, size=(n, 144, 256, 3)).astype(np.uint8),
+                            route_fig=(rs.rand(n, 256, 144) < 0.1).astype(np.uint8) * 255,
+                            measurements=rs.rand(n, 3)))
+    actor = BatchedActor(agent, E)
+    for t in range(ticks_n):
+        ticks = [dict(rgb=s["rgb"][t:t + 8], route_fig=s["route_fig"][t:t + 8], measurements=s["measurements"][t:t + 8],
+                      command=int((t + e) % 4)) for e, s in enumerate(streams)]
+        before = actor.frames_encoded
+        res = actor.act([{k: (v.copy() if hasattr(v, "copy") else v) for k, v in tk.items()} for tk in ticks])
+        assert actor.frames_encoded - before == (8 * E if t == 0 else E)       # only the newest frames after tick 0
+        for e in range(E):
+            feat_b, act_b, lp_b, val_b, _ = res[e]
+            tk = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in ticks[e].items()}
+            feat_s, _, _, val_s, _ = agent.act(tk)
+            assert torch.equal(feat_b, feat_s)
+            for h in range(2):
+                assert abs(val_b[h].item() - val_s[h].item()) < 1e-6
+                assert 0 <= int(act_b[h]) < (33, 3)[h] and lp_b[h].shape == (1, 1)
+    # a reset environment (its window does not continue the previous one) is re-encoded in full
+    actor.reset(1)
+    before = actor.frames_encoded
+    actor.encode(ticks)
+    assert actor.frames_encoded - before == 8 * E     # same ticks again: no window slid, everything re-encoded

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import torch
 
+from .actor import BatchedActor
 from .agent import CadreAgent
 from .config import load_config
 from .learner import Learner, RolloutPool
@@ -15,8 +16,10 @@ from .synthetic_env import SyntheticEnv
 
 
 def train(rank, train_cfg, agent_cfg, env_cfg, rollout_cfg, danet_state, ppo_state=None, workers=1, max_episode=None,
-          process_group=None, log=print):
-    """One rank: `workers` logical workers (env + rollout pair each) sharing one agent replica."""
+          process_group=None, log=print, batched_acting=True):
+    """One rank: `workers` logical workers (env + rollout pair each) sharing one agent replica. With
+    `batched_acting` the rank's workers are stepped together through `BatchedActor` (one encoder batch of the newest
+    frames + one routed LSTM / head evaluation per tick) instead of one `agent.act` call per worker."""
     device = torch.device("cuda:" + str(agent_cfg.model_cfg.device_num))
     envs = [SyntheticEnv(dict(env_cfg, rank=rank * workers + w, seq_length=rollout_cfg.seq_length))
             for w in range(workers)]
@@ -33,17 +36,21 @@ def train(rank, train_cfg, agent_cfg, env_cfg, rollout_cfg, danet_state, ppo_sta
     obs = [e.reset() for e in envs]
     done = [False] * workers
     history = []
+    actor = BatchedActor(agent, workers) if batched_acting else None
     for episode in range(max_episode if max_episode is not None else train_cfg.max_episode):
         for _ in range(num_steps):                                        # train.py:55-74
+            acted = actor.act(obs) if actor is not None else None
             for w, env in enumerate(envs):
                 command = obs[w]["command"]
-                feat, action, logp, value, hidden = agent.act(obs[w])
+                feat, action, logp, value, hidden = acted[w] if acted is not None else agent.act(obs[w])
                 obs[w], reward, done[w], info = env.step(agent.convert_action(action))
                 for h in range(2):
                     mask = torch.tensor([[0.0] if info["action_done"][h] else [1.0]])
                     pool.storages[w][h].insert(feat, action[h], logp[h], value[h], reward[h], mask, hidden, command)
                 if done[w]:
                     obs[w] = env.reset()
+                    if actor is not None:
+                        actor.reset(w)
         nv = torch.zeros(workers, 2)
         for w in range(workers):                                          # train.py:76-79
             vs, vt = agent.get_value(done[w], pool.storages[w][0].get_last(), pool.storages[w][1].get_last())

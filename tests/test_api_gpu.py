@@ -177,3 +177,24 @@ def test_batched_actor_with_frame_cache_equals_single_env_act(agent):
     before = actor.frames_encoded
     actor.encode(ticks)
     assert actor.frames_encoded - before == 8 * E     # same ticks again: no window slid, everything re-encoded
+
+
+@pytest.mark.parametrize("batched", [True, False])
+def test_train_loop_runs_against_the_synthetic_env(batched):
+    """cadre_b200.train.train (ppo_agent/train.py:53-110 + chief.py) for two short episodes with two logical workers:
+    rollouts through BatchedActor or per-worker agent.act, GAE, 4 epochs x 2 minibatches of update_step."""
+    from cadre_b200.config import load_config
+    from cadre_b200.train import train
+    cfg = load_config()
+    cfg.rollout_cfg.num_steps = 8
+    cfg.rollout_cfg.mini_batch_num = 2
+    cfg.train_cfg.log_interval = 1000
+    cfg.env_cfg["done_prob"] = 0.1          # exercise env resets / actor.reset inside the 16 ticks
+    ppo0 = R.ppo_fixture_state(0)
+    learner, hist = train(0, cfg.train_cfg, cfg.agent_cfg, cfg.env_cfg, cfg.rollout_cfg, R.danet_fixture_state(0),
+                          ppo_state=ppo0, workers=2, max_episode=2, batched_acting=batched, log=lambda *a: None)
+    assert len(hist) == 2 and all(np.isfinite(v) for ep in hist for v in ep)
+    assert learner.step_count == 2 * cfg.train_cfg.ppo_epoch * 2
+    new = learner.state()
+    moved = (new["steer_lstm_0"]["rnn.weight_ih"].cpu() - ppo0["steer_lstm_0"]["rnn.weight_ih"]).abs().max().item()
+    assert 0 < moved < 0.1                  # Adam moved the parameters by ~lr per step

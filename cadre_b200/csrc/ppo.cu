@@ -458,6 +458,7 @@ struct PpoPlan {
   // side stream for the gradient kernels that are off the critical path (dW2, dW1, bias column sums)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_bptt = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_wih = nullptr;   // recorded when the W_ih block of the gradient (the first 36 MB) is final
   bool use_side = true;
 };
 
@@ -498,6 +499,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_bptt, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wih, cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->sc.action = dalloc<int>(rows);
@@ -574,6 +576,7 @@ static void ppo_destroy(PpoPlan* P) {
   if (P->ev_fork) cudaEventDestroy(P->ev_fork);
   if (P->ev_bptt) cudaEventDestroy(P->ev_bptt);
   if (P->ev_join) cudaEventDestroy(P->ev_join);
+  if (P->ev_wih) cudaEventDestroy(P->ev_wih);
   delete P;
 }
 
@@ -749,6 +752,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.out = grads + (which ? OFF_WHH : OFF_WIH), g.ldc = LDF, g.out_bs = static_cast<long long>(G) * LDF;
     g.batch_rows = P->counts9, g.rows_is_k = 1;
     launch_gemm(g, s), ++n;
+    if (which == 0) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wih, s));   // lets the caller start reducing that block
   }
   if (P->use_side) CADRE_CUDA_CHECK(cudaStreamWaitEvent(s, P->ev_join, 0));
   CADRE_CUDA_CHECK(cudaGetLastError());
@@ -828,6 +832,14 @@ int cadre_ppo_module_norms(void* handle, float* norms16_host) {
   PpoPlan* P = static_cast<PpoPlan*>(handle);
   CADRE_REQUIRE(P && norms16_host, "module_norms arguments");
   CADRE_CUDA_CHECK(cudaMemcpy(norms16_host, P->opt.norms, 16 * sizeof(float), cudaMemcpyDeviceToHost));
+  CADRE_API_END
+}
+
+int cadre_ppo_wait_wih(void* handle, void* stream) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P != nullptr, "ppo handle");
+  CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), P->ev_wih, 0));
   CADRE_API_END
 }
 

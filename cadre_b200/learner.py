@@ -79,6 +79,8 @@ class Learner:
         self.step_count = 0
         self.l2_persist = os.environ.get("CADRE_L2_PERSIST", "0") == "1"   # measured: no gain on B200, costs the encoder L2
         self.pg = process_group
+        self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
+        self._comm_stream = self._comm_done = None
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -122,7 +124,21 @@ class Learner:
         advs = [(s.advantages, t.advantages) for s, t in storages]
         self.engine.update(storages, advs, indices, self.params, self.grads, self.losses)
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            if self.overlap_allreduce:
+                # the W_ih block (36 of the 78 MB) is final before the last GEMM of the backward pass starts: reduce it
+                # on a second stream while that GEMM runs, the rest afterwards; same sums, one collective more
+                n1 = ppo_params.OFF["WHH"]
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device=self.device)
+                    self._comm_done = torch.cuda.Event()
+                with torch.cuda.stream(self._comm_stream):
+                    self.engine.wait_wih(self._comm_stream)
+                    torch.distributed.all_reduce(self.grads[:n1], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                    self._comm_done.record(self._comm_stream)
+                torch.distributed.all_reduce(self.grads[n1:], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                torch.cuda.current_stream().wait_event(self._comm_done)
+            else:
+                torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         self.step_count += 1
         self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
                               self.max_grad_norm, self.lr)

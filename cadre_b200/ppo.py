@@ -117,6 +117,10 @@ class PpoEngine:
             out[f"{head}_ppo_{c}"] = buf[8 + e]
         return out
 
+    def wait_wih(self, stream):
+        """`stream` (torch.cuda.Stream) waits until the last update() has finished the W_ih block of the gradient."""
+        _lib.check(self._lib.cadre_ppo_wait_wih(self._h, ctypes.c_void_p(stream.cuda_stream)))
+
     @property
     def launches(self):
         return int(self._lib.cadre_ppo_launches(self._h))

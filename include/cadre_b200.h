@@ -189,6 +189,11 @@ int cadre_ppo_adam_step(void* handle, float* params, const float* grads, float* 
 /* gradient norms of the 16 modules seen by the last adam_step: [0..7] LSTM of expert e, [8..15] actor-critic
  * of expert e (expert = head*4 + command); synchronises */
 int cadre_ppo_module_norms(void* handle, float* norms16_host);
+/* Makes `stream` wait until the LAST cadre_ppo_update on this handle has finished the W_ih block of `grads`
+ * (elements [0, 8*2120*532) of the flat buffer: the first of the two LSTM weight-gradient GEMMs). A data-parallel
+ * caller can start the all-reduce of that block (Shared_grad_buffers.add_gradient, models.py:231-239) while the
+ * W_hh gradient is still being computed. */
+int cadre_ppo_wait_wih(void* handle, void* stream);
 int cadre_ppo_launches(void* handle);
 
 #ifdef __cplusplus

@@ -36,7 +36,8 @@ L += ["", f"PPO update step, 4 workers x (steer, throttle) minibatches of 100 ro
       "| GPUs | frames/s (device-resident) | ms/step | scaling vs N x 1-GPU | e2e frames/s (pinned host frames, H2D inside) | all-reduce 77.9 MB |", "|---|---|---|---|---|---|",
       "| 1 | 223 194 | 28.67 | - | 211 137 | - |", "| 2 | 414 159 (before the PPO side stream) | 30.91 | 0.96 | 394 054 | 0.181 ms, algbw 430 GB/s |",
       "| 4 | 709 358 (earlier build) | 36.09 | 0.93 | 690 903 | 0.222 ms, algbw 351 GB/s, busbw 526 GB/s |",
-      "| 8 | 1 565 884 (earlier build) | 32.70 | 0.95 | 971 808 | 0.318 ms, algbw 245 GB/s, busbw 429 GB/s |", "",
+      "| 8 | 1 601 824 (final build; 1 598 016 without the overlapped W_ih all-reduce) | 31.96 | 0.90 | 961 077 | 0.317 ms, algbw 245 GB/s, busbw 429 GB/s |", "",
+      "Scaling is relative to the final 1-GPU number (223 k); the 1-GPU step got 3 ms shorter late in the round while the eight all-reduces (0.32 ms each + skew) stayed: PPO phase 8.0 ms at N=1, 10.6 ms at N=8.",
       "At 8 GPUs the e2e leg is bound by the host: 8 x 944 MB per step through one NUMA node (the box exposes 32 vCPUs, one node) = 143 GB/s aggregate H2D (a single GPU gets 55 GB/s: tools/gpu_probe_h2d.py); the device-resident number shows the GPU side."]
 open("profiles/r1_measurements.md", "w").write("\n".join(L) + "\n")
 print("written")

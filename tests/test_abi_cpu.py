@@ -168,3 +168,30 @@ def test_sync_primitive_shims_keep_the_reference_interface():
     assert light.get() is True
     light.switch()
     assert light.get() is False
+
+
+def test_batched_actor_window_check_on_the_synthetic_env():
+    """cadre_b200.actor.BatchedActor host logic (no GPU): the one-frame check recognises a window that slid by one
+    (env_wrapper.py:900-904 semantics of SyntheticEnv.step) and rejects a reset / repeated / foreign window."""
+    import numpy as np
+    from cadre_b200.actor import BatchedActor
+    from cadre_b200.synthetic_env import SyntheticEnv
+    env, other = SyntheticEnv(dict(rank=0)), SyntheticEnv(dict(rank=1))
+    actor = BatchedActor.__new__(BatchedActor)          # host-side state only
+    actor.E, actor.verify_window, actor._last = 1, True, [None]
+
+    def remember(t):
+        actor._last[0] = (np.array(t["rgb"][-1], copy=True), np.array(t["route_fig"][-1], copy=True),
+                          np.array(t["measurements"][-1], copy=True))
+    t0 = env.reset()
+    assert not actor._slid_by_one(0, t0)                # nothing seen yet
+    remember(t0)
+    t1, *_ = env.step([0.0, 0.0, 0.0])
+    assert actor._slid_by_one(0, t1)                    # newest frame of t0 is now the second newest
+    assert not actor._slid_by_one(0, t0) or np.array_equal(t0["rgb"][-2], t0["rgb"][-1])   # (reset primes 8 equal frames)
+    remember(t1)
+    t2, *_ = env.step([0.0, 0.0, 0.0])
+    assert actor._slid_by_one(0, t2) and not actor._slid_by_one(0, t1)
+    assert not actor._slid_by_one(0, other.reset())     # a different environment's window
+    actor.reset(0)
+    assert not actor._slid_by_one(0, t2)

@@ -131,6 +131,21 @@ class Learner:
                 if self._comm_stream is None:
                     self._comm_stream = torch.cuda.Stream(device=self.device)
                     self._comm_done = torch.cuda.Event()
+                groups = self.engine.grad_groups
+                if groups > 1:   # experimental (CADRE_GRAD_GROUPS): one collective per group of experts, pipelined
+                    chunk = n1 // groups
+                    with torch.cuda.stream(self._comm_stream):
+                        for k in range(2 * groups):
+                            self.engine.wait_grad_group(k, self._comm_stream)
+                            torch.distributed.all_reduce(self.grads[k * chunk:(k + 1) * chunk],
+                                                         op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                        self._comm_done.record(self._comm_stream)
+                    torch.distributed.all_reduce(self.grads[2 * n1:], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                    torch.cuda.current_stream().wait_event(self._comm_done)
+                    self.step_count += 1
+                    self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                          self.max_grad_norm, self.lr)
+                    return self.losses if async_losses else self.scaled_losses()
                 with torch.cuda.stream(self._comm_stream):
                     self.engine.wait_wih(self._comm_stream)
                     torch.distributed.all_reduce(self.grads[:n1], op=torch.distributed.ReduceOp.SUM, group=self.pg)

@@ -117,6 +117,13 @@ class PpoEngine:
             out[f"{head}_ppo_{c}"] = buf[8 + e]
         return out
 
+    @property
+    def grad_groups(self):
+        return int(self._lib.cadre_ppo_grad_groups(self._h))
+
+    def wait_grad_group(self, index, stream):
+        _lib.check(self._lib.cadre_ppo_wait_grad_group(self._h, int(index), ctypes.c_void_p(stream.cuda_stream)))
+
     def wait_wih(self, stream):
         """`stream` (torch.cuda.Stream) waits until the last update() has finished the W_ih block of the gradient."""
         _lib.check(self._lib.cadre_ppo_wait_wih(self._h, ctypes.c_void_p(stream.cuda_stream)))

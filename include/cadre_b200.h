@@ -194,6 +194,11 @@ int cadre_ppo_module_norms(void* handle, float* norms16_host);
  * caller can start the all-reduce of that block (Shared_grad_buffers.add_gradient, models.py:231-239) while the
  * W_hh gradient is still being computed. */
 int cadre_ppo_wait_wih(void* handle, void* stream);
+/* Experimental finer pipeline (environment CADRE_GRAD_GROUPS = 2 / 4 / 8 when the plan is created; default 1 = off):
+ * the W_ih and W_hh gradient blocks are produced per group of 8/groups experts; group index k = which * groups + g
+ * (which 0 = W_ih, 1 = W_hh) covers elements [k, k+1) * (8*2120*532 / groups) of the flat buffer. */
+int cadre_ppo_grad_groups(void* handle);
+int cadre_ppo_wait_grad_group(void* handle, int index, void* stream);
 int cadre_ppo_launches(void* handle);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from . import ppo as _ppo
 from . import ppo_params
 from ._lib import CadreError
-from .models import create_model, get_vae_output
+from .models import create_model, get_vae_output, load_model_dict, save_model_dict
 from .storage import MiniBatch
 
 
@@ -153,18 +153,32 @@ class CadreAgent(object):
         return control
 
     def save_snapshot(self, model_path):
-        """State dicts of all 16 modules (the reference pickles nn.Modules and forgets `throttle_lstm_*`,
-        agent.py:248-258; both omissions are fixed here)."""
-        torch.save({name: m.state_dict() for name, m in self.model_dict.items()}, model_path)
+        """agent.py:245-260; all 16 modules (the reference forgets `throttle_lstm_*`), see models.save_model_dict."""
+        save_model_dict(self.model_dict, model_path)
 
     def load_snapshot(self, model_path, device=None):
-        try:
-            snap = torch.load(model_path, map_location="cpu")
-            for name in snap:
-                sd = snap[name].state_dict() if hasattr(snap[name], "state_dict") else snap[name]
-                self.model_dict[name].load_state_dict(sd)
-        except Exception as e:  # agent.py:270-271
-            raise ImportError("load snapshot error due to {}".format(e))
+        """agent.py:262-271; reads this package's snapshots and the reference's pickled-module files."""
+        load_model_dict(self.model_dict, model_path, device)
+
+    def pre_process(self, tick_data):
+        """agent.py:43-75 for callers that want the network input itself: fp32 [S,4,144,256] on `vae_device`.
+        The hot path does NOT use this: `get_latent_feature` ingests the uint8 arrays directly (the same arithmetic is
+        fused into the encoder's first kernel). Unlike the reference the caller's `route_fig` array is left
+        unmodified (the in-place write-back of agent.py:51-54 is idempotent, so later ticks see the same values)."""
+        return pre_process_tensors(torch.from_numpy(np.ascontiguousarray(tick_data["rgb"])).to(self.vae_device),
+                                   torch.from_numpy(np.ascontiguousarray(tick_data["route_fig"])).to(self.vae_device))
+
+
+def pre_process_tensors(rgb, route):
+    """agent.py:43-75 on torch tensors of any device: rgb u8 [S,H,W,3] -> rgb/255 computed in float64 and cast to
+    float32 (agent.py:46); route u8 [S,W,H] max-normalised per frame THROUGH uint8 (agent.py:51-54 writes the
+    quotient back into the uint8 array, truncating it to {0,1}; frames whose max is 0 stay as they are), then
+    transposed to [S,1,H,W] and concatenated as the fourth channel."""
+    img = (rgb.double() / 255.0).float().permute(0, 3, 1, 2)
+    mx = route.flatten(1).max(1).values.view(-1, 1, 1)
+    norm = (route.double() / mx.double().clamp_min(1.0)).to(torch.uint8)     # float64 -> uint8 truncates
+    route = torch.where(mx > 0, norm, route)
+    return torch.cat([img, route.float().transpose(1, 2).unsqueeze(1)], 1).contiguous()
 
 
 __all__ = ["CadreAgent", "ppo_params"]

@@ -36,44 +36,6 @@ int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream) {
   CADRE_API_END
 }
 
-int cadre_l2_persist(const void* ptr, int64_t nbytes, void* stream) {
-  CADRE_API_BEGIN
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int dev = 0;
-  CADRE_CUDA_CHECK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  static bool have = false;
-  static size_t max_persist = 0, max_window = 0;
-  if (!have) {
-    CADRE_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    max_persist = prop.persistingL2CacheMaxSize, max_window = prop.accessPolicyMaxWindowSize;
-    have = true;
-  }
-  cudaStreamAttrValue attr;
-  memset(&attr, 0, sizeof(attr));
-  if (ptr != nullptr && nbytes > 0 && max_persist > 0) {
-    const size_t want = static_cast<size_t>(nbytes) < max_persist ? static_cast<size_t>(nbytes) : max_persist;
-    static size_t limit_set = 0;
-    if (limit_set != want) {
-      CADRE_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-      limit_set = want;
-    }
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
-    attr.accessPolicyWindow.num_bytes = static_cast<size_t>(nbytes) < max_window ? static_cast<size_t>(nbytes) : max_window;
-    attr.accessPolicyWindow.hitRatio = static_cast<float>(want) / static_cast<float>(attr.accessPolicyWindow.num_bytes);
-    if (attr.accessPolicyWindow.hitRatio > 1.f) attr.accessPolicyWindow.hitRatio = 1.f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  } else {
-    attr.accessPolicyWindow.num_bytes = 0;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-  }
-  CADRE_CUDA_CHECK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
-  if (ptr == nullptr || nbytes <= 0) CADRE_CUDA_CHECK(cudaCtxResetPersistingL2Cache());
-  CADRE_API_END
-}
-
 int cadre_gemm(const cadre_gemm_args* s, void* stream) {
   CADRE_API_BEGIN
   CADRE_REQUIRE(s != nullptr, "args");
@@ -127,19 +89,6 @@ int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, con
   a.w = static_cast<const cadre::enc_t*>(w), a.bias = bias, a.res = static_cast<const cadre::enc_t*>(res);
   a.act = act, a.out = static_cast<cadre::enc_t*>(out);
   cadre::launch_flat3x3(a, static_cast<cudaStream_t>(stream));
-  CADRE_API_END
-}
-
-int cadre_stem_conv(const void* in_padded, int B, const void* w256, const float* bias, void* out,
-                    void* stream) {
-  CADRE_API_BEGIN
-  cadre::StemArgs a;
-  a.in = static_cast<const cadre::enc_t*>(in_padded);
-  a.B = B;
-  a.w = static_cast<const cadre::enc_t*>(w256);
-  a.bias = bias;
-  a.out = static_cast<cadre::enc_t*>(out);
-  cadre::launch_stem(a, static_cast<cudaStream_t>(stream));
   CADRE_API_END
 }
 

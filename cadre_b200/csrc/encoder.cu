@@ -1,6 +1,6 @@
 // Perception encoder forward plan: DANet.get_latent_feature (carla_perception/Networks/danet.py:216-238) as a
 // fixed sequence of kernel launches over NHWC bf16 activations held in library-owned HBM workspaces.
-//   ingest -> stem (tcgen05) -> maxpool -> 8 BasicBlocks (tcgen05 implicit GEMM, BN folded, residual + ReLU in
+//   ingest -> stem + ReLU + maxpool (one tcgen05 kernel) -> 8 BasicBlocks (tcgen05 implicit GEMM, BN folded, residual + ReLU in
 //   the epilogue) -> conv5a|conv5c as one N=256 conv -> fused PAM / fused CAM -> conv51, conv52 (+sum) ->
 //   [conv8 o visual/bc 1x1 o Linear(20480,512)] folded into one [B,5120]x[5120,3072] GEMM + LeakyReLU ->
 //   six Linear(512,256) as one batched GEMM -> inter-task attention (+ measurement concat).
@@ -18,14 +18,9 @@ void launch_f32_to_enc(const float* in, enc_t* out, int n, cudaStream_t stream);
 void launch_preprocess(const uint8_t* rgb, const uint8_t* route, uint8_t* route_max_ws, const enc_t* lut, enc_t* out,
                        int B, cudaStream_t stream);
 void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream);
-void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
-                    cudaStream_t stream);
-#if CADRE_ENC_FP16
+static_assert(CADRE_ENC_FP16 == 1, "the fused PAM / CAM kernels are written for IEEE fp16 operands");
 void launch_pam_mma(const enc_t* x, enc_t* out, const float* wqk, const float* bqk, const enc_t* wv, const float* bv,
                     float gamma, int B, int ldin, int num_sms, cudaStream_t stream);
-#endif
-void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, const float* bqk, float gamma,
-                int B, int ldin, int num_sms, cudaStream_t stream);
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
                 cudaStream_t stream);
 void launch_intertask(const float* qkv, float* out, const double* meas, int B, int ld_out,
@@ -37,16 +32,13 @@ struct Encoder {
   int num_sms = 148;
   // workspaces (device)
   enc_t* padded = nullptr;   // [Bmax][75][262][8]
-  enc_t* stem = nullptr;     // [Bmax][72][128][64]
   enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
   enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
-  bool use_flat = true, fuse_stem = true;
   // fused shortcuts (layer2.0 / 3.0 / 4.0): conv2 weights with the 1x1 downsample appended along K, summed bias
   bool fuse_ds = true;
   enc_t* fused_w[3] = {nullptr, nullptr, nullptr};
   float* fused_b[3] = {nullptr, nullptr, nullptr};
   enc_t* head5 = nullptr;    // [Bmax][40][256]
-  enc_t* pam_v = nullptr;    // [Bmax][40][128] PAM value projection
   enc_t* sa = nullptr;       // [Bmax][40][128]
   enc_t* sc = nullptr;
   enc_t* sa_conv = nullptr;
@@ -89,12 +81,9 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t B = max_batch;
   e->padded = dev_alloc<enc_t>(B * 75 * 262 * 8, true);  // zero borders = conv padding
-  e->stem = dev_alloc<enc_t>(B * 72 * 128 * 64, false);
   for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
-  e->use_flat = getenv("CADRE_NO_FLAT") == nullptr;
-  e->fuse_stem = getenv("CADRE_NO_STEM_FUSION") == nullptr;
-  e->fuse_ds = getenv("CADRE_NO_SHORTCUT_FUSION") == nullptr && getenv("CADRE_CONV_V1") == nullptr;
+  e->fuse_ds = getenv("CADRE_NO_SHORTCUT_FUSION") == nullptr;   // A/B switch kept for the fused-shortcut parity test
   if (e->fuse_ds) {
     // conv indices follow execution order: layer1 = 0..3, then per stage (conv1, conv2, downsample, conv1, conv2)
     const int planes[4] = {64, 128, 256, 512};
@@ -116,7 +105,6 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
     }
   }
   e->head5 = dev_alloc<enc_t>(B * 40 * 256, false);
-  e->pam_v = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sc = dev_alloc<enc_t>(B * 40 * 128, false);
   e->sa_conv = dev_alloc<enc_t>(B * 40 * 128, false);
@@ -140,10 +128,10 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
 
 static void encoder_destroy(Encoder* e) {
   if (!e) return;
-  cudaFree(e->padded), cudaFree(e->stem);
+  cudaFree(e->padded);
   for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
   for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
-  cudaFree(e->head5), cudaFree(e->pam_v), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
+  cudaFree(e->head5), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
   cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max), cudaFree(e->lut255);
   for (int i = 0; i < 3; ++i) cudaFree(e->fused_w[i]), cudaFree(e->fused_b[i]);
   delete e;
@@ -171,21 +159,14 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
   }
   StemArgs st;
   st.in = e->padded, st.B = B, st.w = static_cast<const enc_t*>(e->w.stem_w), st.bias = e->w.stem_b;
-  st.out = e->stem;
-  if (e->use_flat && e->fuse_stem) {
-    st.out = e->padact[0];
-    launch_stem_pool(st, s), step(e, s, n, "stem+pool");
-  } else {
-    launch_stem(st, s), step(e, s, n, "stem");
-    launch_maxpool(e->stem, e->use_flat ? e->padact[0] : e->act[0], B, 72, 128, 64, e->use_flat ? 1 : 0, s);
-    step(e, s, n, "maxpool");
-  }
+  st.out = e->padact[0];   // the pooled map lands in layer1's zero-bordered input; the stem activation never reaches HBM
+  launch_stem_pool(st, s), step(e, s, n, "stem+pool");
 
   // ResNet-18 BasicBlocks (resnet.py:39-55, 116-119); conv indices follow execution order
   int cur = 0, ci = 0, H = 36, W = 64, C = 64;
   const int planes[4] = {64, 128, 256, 512};
   const enc_t* padded_in = nullptr;  // layer1 output in zero-bordered layout (input of layer2.0)
-  if (e->use_flat) {
+  {
     // layer1 (4 convs 64->64, 3x3/s1) through the halo-reuse kernel on zero-bordered buffers
     enc_t* x = e->padact[0];
     enc_t* t = e->padact[1];
@@ -204,7 +185,7 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     }
     padded_in = x;
   }
-  for (int li = e->use_flat ? 1 : 0; li < 4; ++li) {
+  for (int li = 1; li < 4; ++li) {
     for (int bi = 0; bi < 2; ++bi) {
       const int stride = (li > 0 && bi == 0) ? 2 : 1;
       const int Cout = planes[li];
@@ -255,28 +236,9 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     a.Cout = 256, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1, a.act = 1, a.out = e->head5;
     launch_conv(a, s), step(e, s, n, "conv5a|conv5c");
   }
-#if CADRE_ENC_FP16
-  static const bool pam_fp32 = getenv("CADRE_PAM_FP32") != nullptr;   // A/B switch: value GEMM + fp32 CUDA-core kernel
-#else
-  const bool pam_fp32 = true;
-#endif
-  if (!pam_fp32) {
-#if CADRE_ENC_FP16
-    launch_pam_mma(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, static_cast<const enc_t*>(e->w.pam_wv), e->w.pam_bv,
-                   e->w.pam_gamma, B, 256, e->num_sms, s);
-    step(e, s, n, "pam (value conv fused)");
-#endif
-  } else {
-    {  // PAM value projection for the whole batch on the tensor cores: V[B*40,128] = feat1 Wv^T + bv
-      GemmArgs g;
-      g.kind = 0, g.A = e->head5, g.lda = 256, g.B = e->w.pam_wv, g.ldb = 128;
-      g.M = B * 40, g.N = 128, g.K = 128;
-      g.out = e->pam_v, g.ldc = 128, g.out_f32 = 0, g.bias = e->w.pam_bv;
-      launch_gemm(g, s), step(e, s, n, "pam.value_conv");
-    }
-    launch_pam(e->head5, e->pam_v, e->sa, e->w.pam_wqk, e->w.pam_bqk, e->w.pam_gamma, B, 256, e->num_sms, s);
-    step(e, s, n, "pam");
-  }
+  launch_pam_mma(e->head5, e->sa, e->w.pam_wqk, e->w.pam_bqk, static_cast<const enc_t*>(e->w.pam_wv), e->w.pam_bv,
+                 e->w.pam_gamma, B, 256, e->num_sms, s);
+  step(e, s, n, "pam (value conv fused)");
   launch_cam(e->head5 + 128, e->sc, e->w.cam_gamma, B, 256, e->num_sms, s), step(e, s, n, "cam");
   {
     ConvArgs a;
@@ -378,7 +340,7 @@ int cadre_encoder_buffer(void* handle, int which, void** ptr, int64_t* elems_per
     case 2: *ptr = e->head5, *elems_per_frame = 40 * 256; break;       // conv5a|conv5c output
     case 3: *ptr = e->sa, *elems_per_frame = 40 * 128; break;          // PAM output
     case 4: *ptr = e->sc, *elems_per_frame = 40 * 128; break;          // CAM output
-    case 5: *ptr = e->stem, *elems_per_frame = 72 * 128 * 64; break;   // stem output
+    case 5: *ptr = e->fc1, *elems_per_frame = 3072; break;             // six folded Linear(20480,512) + LeakyReLU
     default: throw cadre::Error(1, "encoder_buffer: unknown buffer id");
   }
   CADRE_API_END

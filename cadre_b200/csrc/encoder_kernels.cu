@@ -159,290 +159,8 @@ void launch_pack_f32(const float* x, enc_t* out, int B, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// MaxPool2d(3, stride 2, padding 1) on NHWC bf16 (resnet.py:172): [B,72,128,64] -> [B,36,64,64].
-// One thread = one output pixel x 8 channels (16 B); inputs are post-ReLU so padding never wins.
-__global__ void maxpool_kernel(const enc_t* __restrict__ in, enc_t* __restrict__ out, int B,
-                               int Hin, int Win, int C, int out_pad) {
-  pdl_trigger();
-  pdl_wait();
-  const int Hout = Hin / 2, Wout = Win / 2, CV = C / 8;
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hout * Wout * CV;
-  if (gid >= total) return;
-  const int cv = static_cast<int>(gid % CV);
-  const int ow = static_cast<int>((gid / CV) % Wout);
-  const int oh = static_cast<int>((gid / (CV * Wout)) % Hout);
-  const int n = static_cast<int>(gid / (static_cast<long long>(CV) * Wout * Hout));
-  float m[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int y = 2 * oh + dy;
-    if (y < 0 || y >= Hin) continue;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int x = 2 * ow + dx;
-      if (x < 0 || x >= Win) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * Hin + y) * Win + x) * C +
-                                                      cv * 8);
-      const enc_t* h = reinterpret_cast<const enc_t*>(&v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], enc_to_float(h[i]));
-    }
-  }
-  enc_t o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = enc_from_float(m[i]);
-  // out_pad: the output carries a 1-pixel zero border ([B][Hout+2][Wout+2][C]) for the halo-reuse convs
-  const long long opix = (static_cast<long long>(n) * (Hout + 2 * out_pad) + oh + out_pad) * (Wout + 2 * out_pad) +
-                         ow + out_pad;
-  *reinterpret_cast<uint4*>(out + opix * C + cv * 8) = *reinterpret_cast<const uint4*>(o);
-}
-
-void launch_maxpool(const enc_t* in, enc_t* out, int B, int Hin, int Win, int C, int out_pad,
-                    cudaStream_t stream) {
-  const long long total = static_cast<long long>(B) * (Hin / 2) * (Win / 2) * (C / 8);
-  launch_k(maxpool_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, in, out, B, Hin, Win, C, out_pad);
-  CADRE_CUDA_CHECK(cudaGetLastError());
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// PAM_Module.forward (danet_blocks/da_att.py:32-51) fused per frame: q,k = 1x1 conv 128->16 (fp32), energy =
-// q^T k [40x40] (no scale), softmax over keys, out = v att^T, gamma*out + x. The value projection
-// v = Wv x + bv (80 % of the module's FLOPs, linear in the output) is done beforehand by the tcgen05 tile kernel
-// for the whole batch; q, k, the 40x40 map and the softmax stay in fp32 on CUDA cores and never leave the SM.
-// x: NHWC enc16 rows of `ldin` elements (first 128 channels used), v / out: enc16 [B][40][128].
-constexpr int PAM_P = 40, PAM_C = 128, PAM_LD = 132;
-struct PamSmem {
-  float wqk[32][PAM_LD];
-  float bqk[32];
-  float x[PAM_P][PAM_LD];
-  float v[PAM_P][PAM_LD];
-  float qk[PAM_P][33];
-  float att[PAM_P][PAM_P + 1];
-};
-
-__global__ void __launch_bounds__(256) pam_kernel(const enc_t* __restrict__ xin, const enc_t* __restrict__ vin,
-                                                  enc_t* __restrict__ out, const float* __restrict__ wqk,
-                                                  const float* __restrict__ bqk, float gamma, int B, int ldin) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ uint8_t pam_raw[];
-  PamSmem& s = *reinterpret_cast<PamSmem*>(pam_raw);
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 32 * PAM_C; i += 256) s.wqk[i / PAM_C][i % PAM_C] = wqk[i];
-  if (tid < 32) s.bqk[tid] = bqk[tid];
-  for (int f = blockIdx.x; f < B; f += gridDim.x) {
-    __syncthreads();
-    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
-    const enc_t* vf = vin + static_cast<long long>(f) * PAM_P * PAM_C;
-    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {  // 16-byte loads: 8 channels
-      const int p = i / (PAM_C / 8), c8 = (i % (PAM_C / 8)) * 8;
-      const uint4 ux = *reinterpret_cast<const uint4*>(xf + p * ldin + c8);
-      const uint4 uv = *reinterpret_cast<const uint4*>(vf + p * PAM_C + c8);
-      const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
-      const enc_t* hv = reinterpret_cast<const enc_t*>(&uv);
-      *reinterpret_cast<float4*>(&s.x[p][c8]) = make_float4(enc_to_float(hx[0]), enc_to_float(hx[1]), enc_to_float(hx[2]), enc_to_float(hx[3]));
-      *reinterpret_cast<float4*>(&s.x[p][c8 + 4]) = make_float4(enc_to_float(hx[4]), enc_to_float(hx[5]), enc_to_float(hx[6]), enc_to_float(hx[7]));
-      *reinterpret_cast<float4*>(&s.v[p][c8]) = make_float4(enc_to_float(hv[0]), enc_to_float(hv[1]), enc_to_float(hv[2]), enc_to_float(hv[3]));
-      *reinterpret_cast<float4*>(&s.v[p][c8 + 4]) = make_float4(enc_to_float(hv[4]), enc_to_float(hv[5]), enc_to_float(hv[6]), enc_to_float(hv[7]));
-    }
-    __syncthreads();
-    {  // qk[p][j]: thread = (j, group of 5 pixels), float4 along the 128 input channels
-      const int j = tid & 31, p0 = (tid >> 5) * 5;
-      float acc[5];
-#pragma unroll
-      for (int r = 0; r < 5; ++r) acc[r] = s.bqk[j];
-      for (int k = 0; k < PAM_C; k += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(&s.wqk[j][k]);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const float4 xv = *reinterpret_cast<const float4*>(&s.x[p0 + r][k]);
-          acc[r] = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, fmaf(xv.w, w.w, acc[r]))));
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 5; ++r) s.qk[p0 + r][j] = acc[r];
-    }
-    __syncthreads();
-    for (int o = tid; o < PAM_P * PAM_P; o += 256) {  // energy[i][j] = q_i . k_j
-      const int i = o / PAM_P, j = o % PAM_P;
-      float acc = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) acc = fmaf(s.qk[i][d], s.qk[j][16 + d], acc);
-      s.att[i][j] = acc;
-    }
-    __syncthreads();
-    for (int i = tid >> 5; i < PAM_P; i += 8) {  // row softmax: one warp per row
-      const int l = tid & 31;
-      const float e0 = s.att[i][l], e1 = (l + 32 < PAM_P) ? s.att[i][l + 32] : -INFINITY;
-      float m = fmaxf(e0, e1);
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float p0 = expf(e0 - m), p1 = (l + 32 < PAM_P) ? expf(e1 - m) : 0.f;
-      float sum = p0 + p1;
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      s.att[i][l] = p0 / sum;
-      if (l + 32 < PAM_P) s.att[i][l + 32] = p1 / sum;
-    }
-    __syncthreads();
-    {  // out[i][c] = gamma * sum_j att[i][j] v[j][c] + x[i][c]: thread = (4 channels, 5 pixels)
-      const int c0 = (tid & 31) * 4, i0 = (tid >> 5) * 5;
-      float acc[5][4];
-#pragma unroll
-      for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-      for (int j = 0; j < PAM_P; ++j) {
-        const float4 vv = *reinterpret_cast<const float4*>(&s.v[j][c0]);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const float a = s.att[i0 + r][j];
-          acc[r][0] = fmaf(a, vv.x, acc[r][0]);
-          acc[r][1] = fmaf(a, vv.y, acc[r][1]);
-          acc[r][2] = fmaf(a, vv.z, acc[r][2]);
-          acc[r][3] = fmaf(a, vv.w, acc[r][3]);
-        }
-      }
-      enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        uint2 u;
-        u.x = enc_pack2(gamma * acc[r][0] + s.x[i0 + r][c0], gamma * acc[r][1] + s.x[i0 + r][c0 + 1]);
-        u.y = enc_pack2(gamma * acc[r][2] + s.x[i0 + r][c0 + 2], gamma * acc[r][3] + s.x[i0 + r][c0 + 3]);
-        *reinterpret_cast<uint2*>(of + (i0 + r) * PAM_C + c0) = u;
-      }
-    }
-  }
-}
-
-// CAM_Module.forward (da_att.py:63-83) fused per frame: energy = X X^T [128x128] over the 40 positions,
-// softmax(rowmax - energy), out = att X, gamma*out + x. Register-tiled fp32 (8x8 gram tiles, 4x5 output tiles).
-struct CamSmem {
-  float x[PAM_P][PAM_LD];   // x[p][c]
-  float att[PAM_C][PAM_LD];
-};
-
-__global__ void __launch_bounds__(256) cam_kernel(const enc_t* __restrict__ xin, enc_t* __restrict__ out,
-                                                  float gamma, int B, int ldin) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ uint8_t cam_raw[];
-  CamSmem& s = *reinterpret_cast<CamSmem*>(cam_raw);
-  const int tid = threadIdx.x;
-  for (int f = blockIdx.x; f < B; f += gridDim.x) {
-    __syncthreads();
-    const enc_t* xf = xin + static_cast<long long>(f) * PAM_P * ldin;
-    for (int i = tid; i < PAM_P * PAM_C / 8; i += 256) {
-      const int p = i / (PAM_C / 8), c8 = (i % (PAM_C / 8)) * 8;
-      const uint4 ux = *reinterpret_cast<const uint4*>(xf + p * ldin + c8);
-      const enc_t* hx = reinterpret_cast<const enc_t*>(&ux);
-      *reinterpret_cast<float4*>(&s.x[p][c8]) = make_float4(enc_to_float(hx[0]), enc_to_float(hx[1]), enc_to_float(hx[2]), enc_to_float(hx[3]));
-      *reinterpret_cast<float4*>(&s.x[p][c8 + 4]) = make_float4(enc_to_float(hx[4]), enc_to_float(hx[5]), enc_to_float(hx[6]), enc_to_float(hx[7]));
-    }
-    __syncthreads();
-    {  // gram: thread owns rows a0..a0+7 x columns {b0..b0+3, 64+b0..64+b0+3}: the 16 lanes that differ in b0
-       // read consecutive float4 (conflict-free), the two a0 values of a warp are broadcasts
-      const int a0 = (tid >> 4) * 8, b0 = (tid & 15) * 4;
-      float acc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-      for (int p = 0; p < PAM_P; ++p) {
-        const float4 a_lo = *reinterpret_cast<const float4*>(&s.x[p][a0]);
-        const float4 a_hi = *reinterpret_cast<const float4*>(&s.x[p][a0 + 4]);
-        const float4 b_lo = *reinterpret_cast<const float4*>(&s.x[p][b0]);
-        const float4 b_hi = *reinterpret_cast<const float4*>(&s.x[p][64 + b0]);
-        const float av[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
-        const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        *reinterpret_cast<float4*>(&s.att[a0 + i][b0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        *reinterpret_cast<float4*>(&s.att[a0 + i][64 + b0]) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-      }
-    }
-    __syncthreads();
-    // softmax(rowmax - e): one warp per channel row, 4 values per lane
-    for (int a = tid >> 5; a < PAM_C; a += 8) {
-      const int l = tid & 31;
-      float e[4], mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        e[k] = s.att[a][l + 32 * k];
-        mx = fmaxf(mx, e[k]);
-      }
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float en[4], m2 = -INFINITY;  // energy_new = mx - e, then a regular stable softmax over energy_new
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        en[k] = mx - e[k];
-        m2 = fmaxf(m2, en[k]);
-      }
-      for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        en[k] = expf(en[k] - m2);
-        sum += en[k];
-      }
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s.att[a][l + 32 * k] = en[k] / sum;
-    }
-    __syncthreads();
-    {  // out[p][a] = gamma * sum_b att[a][b] x[p][b] + x[p][a]: thread = channels {lane + 32q}, 5 pixels p.
-       // Lanes read CONSECUTIVE att rows (row stride 132 words = 4 banks: conflict-free float4 loads; the former
-       // lane*4 mapping put every other lane on the same bank and made this loop 8x slower); x reads are broadcasts.
-      const int lane = tid & 31, p0 = (tid >> 5) * 5;
-      float acc[5][4];
-#pragma unroll
-      for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-#pragma unroll 2
-      for (int b = 0; b < PAM_C; b += 4) {
-        float4 at[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) at[q] = *reinterpret_cast<const float4*>(&s.att[lane + 32 * q][b]);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const float4 xv = *reinterpret_cast<const float4*>(&s.x[p0 + r][b]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            acc[r][q] = fmaf(at[q].x, xv.x, fmaf(at[q].y, xv.y, fmaf(at[q].z, xv.z, fmaf(at[q].w, xv.w, acc[r][q]))));
-        }
-      }
-      enc_t* of = out + static_cast<long long>(f) * PAM_P * PAM_C;
-#pragma unroll
-      for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = lane + 32 * q;
-          of[(p0 + r) * PAM_C + a] = enc_from_float(gamma * acc[r][q] + s.x[p0 + r][a]);
-        }
-    }
-  }
-}
-
-void launch_pam(const enc_t* x, const enc_t* v, enc_t* out, const float* wqk, const float* bqk, float gamma,
-                int B, int ldin, int num_sms, cudaStream_t stream) {
-  static bool cfg = false;
-  if (!cfg) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(pam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(PamSmem))));
-    cfg = true;
-  }
-  const int grid = B < 3 * num_sms ? B : 3 * num_sms;
-  launch_k(pam_kernel, dim3(grid), dim3(256), sizeof(PamSmem), stream, x, v, out, wqk, bqk, gamma, B, ldin);
-  CADRE_CUDA_CHECK(cudaGetLastError());
-}
+// Position / channel attention (danet_blocks/da_att.py:32-83): 40 positions x 128 channels per frame.
+constexpr int PAM_P = 40, PAM_C = 128;
 
 #if CADRE_ENC_FP16
 // ---------------------------------------------------------------------------------------------------------
@@ -789,12 +507,8 @@ __global__ void __launch_bounds__(256) pam_mma_kernel(const enc_t* __restrict__ 
 
 void launch_pam_mma(const enc_t* x, enc_t* out, const float* wqk, const float* bqk, const enc_t* wv, const float* bv,
                     float gamma, int B, int ldin, int num_sms, cudaStream_t stream) {
-  static bool cfg = false;
-  if (!cfg) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(pam_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(PamMmaSmem))));
-    cfg = true;
-  }
+  static size_t cfg[CADRE_MAX_DEVICES] = {};
+  ensure_dynamic_smem(pam_mma_kernel, sizeof(PamMmaSmem), cfg);
   const int grid = B < 2 * num_sms ? B : 2 * num_sms;
   launch_k(pam_mma_kernel, dim3(grid), dim3(256), sizeof(PamMmaSmem), stream, x, out, wqk, bqk, wv, bv, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());
@@ -803,23 +517,10 @@ void launch_pam_mma(const enc_t* x, enc_t* out, const float* wqk, const float* b
 
 void launch_cam(const enc_t* x, enc_t* out, float gamma, int B, int ldin, int num_sms,
                 cudaStream_t stream) {
-  static bool cfg = false;
-  if (!cfg) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(cam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(sizeof(CamSmem))));
-    cfg = true;
-  }
-#if CADRE_ENC_FP16
-  static const bool fp32_path = getenv("CADRE_CAM_FP32") != nullptr;   // A/B switch: CUDA-core fp32 kernel
-  if (!fp32_path) {
-    const int grid2 = B < 6 * num_sms ? B : 6 * num_sms;
-    launch_k(cam_mma_kernel, dim3(grid2), dim3(256), sizeof(CamMmaSmem), stream, x, out, gamma, B, ldin);
-    CADRE_CUDA_CHECK(cudaGetLastError());
-    return;
-  }
-#endif
-  const int grid = B < 2 * num_sms ? B : 2 * num_sms;
-  launch_k(cam_kernel, dim3(grid), dim3(256), sizeof(CamSmem), stream, x, out, gamma, B, ldin);
+  static size_t cfg[CADRE_MAX_DEVICES] = {};
+  ensure_dynamic_smem(cam_mma_kernel, sizeof(CamMmaSmem), cfg);
+  const int grid = B < 6 * num_sms ? B : 6 * num_sms;
+  launch_k(cam_mma_kernel, dim3(grid), dim3(256), sizeof(CamMmaSmem), stream, x, out, gamma, B, ldin);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -193,6 +193,25 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per (call site, device) which
+// devices have been configured, so that a process driving several GPUs (vae_device != device_num, agent.py:21-31)
+// configures each of them. `flags` is a caller-owned static array of CADRE_MAX_DEVICES entries.
+constexpr int CADRE_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  CADRE_CUDA_CHECK(cudaGetDevice(&dev));
+  CADRE_REQUIRE(dev >= 0 && dev < CADRE_MAX_DEVICES, "device ordinal");
+  return dev;
+}
+template <typename Kern>
+inline void ensure_dynamic_smem(Kern kern, size_t smem, size_t* flags) {
+  const int dev = current_device();
+  if (smem > flags[dev]) {
+    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    flags[dev] = smem;
+  }
+}
+
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
                       float lr, float beta1, float beta2, float eps, int step, cudaStream_t s);
 

@@ -459,11 +459,6 @@ struct PpoPlan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_bptt = nullptr, ev_join = nullptr;
   cudaEvent_t ev_wih = nullptr;   // recorded when the W_ih block of the gradient (the first 36 MB) is final
-  // optional finer pipeline (CADRE_GRAD_GROUPS = 2 / 4 / 8, default 1 = off; NOT yet validated on hardware): the two
-  // LSTM weight-gradient GEMMs run per group of experts and record one event per group, so that a data-parallel
-  // caller can all-reduce group k while group k+1 is still being computed
-  int grad_groups = 1;
-  cudaEvent_t ev_grp[16] = {};
   bool use_side = true;
 };
 
@@ -505,12 +500,6 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_bptt, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wih, cudaEventDisableTiming));
-  if (const char* gg = getenv("CADRE_GRAD_GROUPS")) {
-    const int v = atoi(gg);
-    if (v == 2 || v == 4 || v == 8) P->grad_groups = v;
-  }
-  for (int i = 0; i < 2 * P->grad_groups && P->grad_groups > 1; ++i)
-    CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_grp[i], cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->sc.action = dalloc<int>(rows);
@@ -588,8 +577,6 @@ static void ppo_destroy(PpoPlan* P) {
   if (P->ev_bptt) cudaEventDestroy(P->ev_bptt);
   if (P->ev_join) cudaEventDestroy(P->ev_join);
   if (P->ev_wih) cudaEventDestroy(P->ev_wih);
-  for (cudaEvent_t ev : P->ev_grp)
-    if (ev) cudaEventDestroy(ev);
   delete P;
 }
 
@@ -757,24 +744,6 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s2, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
                                                        grads + OFF_BHH), ++n;
   if (P->use_side) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_join, s2));
-  if (P->grad_groups > 1) {   // per group of experts, one event per group (see PpoPlan::grad_groups)
-    const int eg = E / P->grad_groups;
-    for (int which = 0; which < 2; ++which)
-      for (int grp = 0; grp < P->grad_groups; ++grp) {
-        const long long e0 = static_cast<long long>(grp) * eg;
-        GemmArgs g = tf32_gemm(1, 1);
-        g.batch = eg;
-        g.A = P->dG9 + e0 * rs9G, g.lda = G, g.a_bs = rs9G;
-        g.B = (which ? P->H9 : P->X9) + e0 * rs9F, g.ldb = LDF, g.b_bs = rs9F;
-        g.M = G, g.N = F, g.K = 9 * cap;
-        g.out_bs = static_cast<long long>(G) * LDF;
-        g.out = grads + (which ? OFF_WHH : OFF_WIH) + e0 * g.out_bs, g.ldc = LDF;
-        g.batch_rows = P->counts9 + e0, g.rows_is_k = 1;
-        launch_gemm(g, s), ++n;
-        CADRE_CUDA_CHECK(cudaEventRecord(P->ev_grp[which * P->grad_groups + grp], s));
-        if (which == 0 && grp == P->grad_groups - 1) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wih, s));
-      }
-  } else
   for (int which = 0; which < 2; ++which) {  // dW_ih = dG9^T X9, dW_hh = dG9^T H9 (K = 9 * rows)
     GemmArgs g = tf32_gemm(1, 1);
     g.A = P->dG9, g.lda = G, g.a_bs = rs9G;
@@ -871,19 +840,6 @@ int cadre_ppo_wait_wih(void* handle, void* stream) {
   PpoPlan* P = static_cast<PpoPlan*>(handle);
   CADRE_REQUIRE(P != nullptr, "ppo handle");
   CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), P->ev_wih, 0));
-  CADRE_API_END
-}
-
-int cadre_ppo_grad_groups(void* handle) {
-  PpoPlan* P = static_cast<PpoPlan*>(handle);
-  return P ? P->grad_groups : 0;
-}
-
-int cadre_ppo_wait_grad_group(void* handle, int index, void* stream) {
-  CADRE_API_BEGIN
-  PpoPlan* P = static_cast<PpoPlan*>(handle);
-  CADRE_REQUIRE(P != nullptr && P->grad_groups > 1 && index >= 0 && index < 2 * P->grad_groups, "grad group index");
-  CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), P->ev_grp[index], 0));
   CADRE_API_END
 }
 

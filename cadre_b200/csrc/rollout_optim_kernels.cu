@@ -310,12 +310,9 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
   auto kern = T <= 256 ? cadre::gae_kernel<8> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>);
-  static size_t configured[3] = {0, 0, 0};
+  static size_t configured[3][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
   const int which = T <= 256 ? 0 : (T <= 1024 ? 1 : 2);
-  if (smem > 48 * 1024 && smem > configured[which]) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[which] = smem;
-  }
+  if (smem > 48 * 1024) cadre::ensure_dynamic_smem(kern, smem, configured[which]);
   cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
                   rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
   CADRE_CUDA_CHECK(cudaGetLastError());

@@ -92,41 +92,30 @@ template <int KIND, int A_MN, int B_MN, int BN, int STAGES, int MODE, int EPI, t
 static void launch_inst(const TcGemmParams& p, dim3 grid, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, STAGES, MODE, EPI, OutT, EW>;
   constexpr int smem = TcGemmSmem<KIND, BN, STAGES>::TOTAL;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(kern, smem, configured);
   launch_k(kern, dim3(grid), dim3(64 + 128 * EW), smem, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    CADRE_CUDA_CHECK(cudaGetDevice(&dev));
-    CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return n;
+  static int n[CADRE_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!n[dev]) CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev];
 }
 bool pdl_enabled() {
   static const bool on = getenv("CADRE_NO_PDL") == nullptr;
   return on;
 }
 
-static const bool g_use_v1 = getenv("CADRE_CONV_V1") != nullptr;  // A/B switch: non-persistent encoder kernels
-
 // CTA-pair variant (cta_group::2): clusters of two CTAs, one 256 x BN tile per pair
 template <int BN, int STAGES, int MODE>
 static void launch_persist2(const PersistParams& p, cudaStream_t stream) {
   auto kern = tc_persist_kernel<BN, STAGES, MODE, true>;
   constexpr int smem = PersistSmem<BN, STAGES, true>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(kern, smem, configured);
   const int pairs_needed = ((p.tiles_m + 1) / 2) * p.tiles_n;
   int pairs = num_sms() / 2;
   if (pairs_needed < pairs) pairs = pairs_needed;
@@ -146,11 +135,8 @@ template <int BN, int STAGES, int MODE>
 static void launch_persist(const PersistParams& p, cudaStream_t stream) {
   auto kern = tc_persist_kernel<BN, STAGES, MODE>;
   constexpr int smem = PersistSmem<BN, STAGES>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(kern, smem, configured);
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   launch_k(kern, dim3(grid), dim3(320), smem, stream, with_dbg(p));
@@ -176,7 +162,7 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const int es = a.kind ? 4 : 2;
   const int bk = 128 / es;
   int bn = a.block_n ? a.block_n : (a.N <= 64 ? 64 : 128);
-  if (!g_use_v1 && a.K > 0 && a.kind == 0 && !a.a_mn && !a.b_mn && a.batch == 1 && !a.out_f32 && a.epi == 0 && !a.mask &&
+  if (a.K > 0 && a.kind == 0 && !a.a_mn && !a.b_mn && a.batch == 1 && !a.out_f32 && a.epi == 0 && !a.mask &&
       !a.batch_rows && a.alpha == 1.f && a.N % 8 == 0) {
     PersistParams q;
     memset(&q, 0, sizeof(q));
@@ -273,7 +259,7 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   while (TH * 2 <= rows_per_tile && Hout % (TH * 2) == 0) TH *= 2;
   const int TN = rows_per_tile / TH;
   static const bool allow_bn256 = getenv("CADRE_NO_BN256") == nullptr;
-  const int bn = a.Cout <= 64 ? 64 : ((a.Cout % 256 == 0 && allow_bn256 && !g_use_v1) ? 256 : 128);
+  const int bn = a.Cout <= 64 ? 64 : ((a.Cout % 256 == 0 && allow_bn256) ? 256 : 128);
 
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -315,7 +301,7 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   int Ktot = nt * a.Cin;
   if (a.in2 != nullptr) {
     // fused shortcut: output (h, w) reads in2 pixel (2h, 2w) -> parity sub-lattice map of the (bordered) tensor
-    CADRE_REQUIRE(!g_use_v1 && a.stride == 1 && a.Cin2 % 64 == 0 && a.Cin2 > 0 && nt < 12, "fused shortcut arguments");
+    CADRE_REQUIRE(a.stride == 1 && a.Cin2 % 64 == 0 && a.Cin2 > 0 && nt < 12, "fused shortcut arguments");
     CADRE_REQUIRE((a.Hin2 - 1) / 2 + 1 == Hout && (a.Win2 - 1) / 2 + 1 == Wout, "fused shortcut input size");
     const int Hs2 = a.Hin2 + 2 * a.in2_pad, Ws2 = a.Win2 + 2 * a.in2_pad, par = a.in2_pad & 1;
     const int Hq = (Hs2 - par + 1) / 2, Wq = (Ws2 - par + 1) / 2;
@@ -340,7 +326,7 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
   p.res = a.res, p.ldr = a.Cout, p.res_after_act = a.res_after_act;
   p.act = a.act, p.alpha = 1.f;
   dim3 grid((Hout / TH) * ((a.B + TN - 1) / TN), (a.Cout + bn - 1) / bn, 1);
-  if (!g_use_v1) {
+  {
     PersistParams q;
     memset(&q, 0, sizeof(q));
     for (int i = 0; i < 4; ++i) q.tmA[i] = p.tmA[i];
@@ -377,10 +363,6 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
     }
     return;
   }
-  if (bn == 64)
-    launch_inst<0, 0, 0, 64, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
-  else
-    launch_inst<0, 0, 0, 128, 4, MODE_CONV, EPI_LINEAR, enc_t>(p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -406,83 +388,18 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
   p.num_tiles = static_cast<int>((P + 127) / 128);
   p.bias = a.bias, p.res = a.res, p.act = a.act;
   p.dbg = g_dbg_clk ? g_dbg_clk + (a.res ? 2 : 1) * 148 * 16 : nullptr;  // region 0: stem, 1: conv, 2: conv + residual
-  static bool configured = false;
-  if (!configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
-    configured = true;
-  }
-  // opt-in: measured SLOWER on B200 (layer1 conv 160 us against 129 us: a 256x64x16 cta_group::2 MMA does not beat two
-  // independent 128x64x16 MMAs, and the pair advances in lock step)
-  static const bool flat_pairs = getenv("CADRE_FLAT_PAIRS") != nullptr;
-  if (flat_pairs) {
-    // cta_group::2 variant: each CTA of a pair loads 32 of the 64 weight rows of every tap
-    const uint32_t wbox2[2] = {64, 32};
-    make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox2);
-    static bool configured2 = false;
-    if (!configured2) {
-      CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_flat3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLAT_SMEM));
-      configured2 = true;
-    }
-    const int pair_tiles = (p.num_tiles + 1) / 2;
-    int pairs = num_sms() / 2;
-    if (pair_tiles < pairs) pairs = pair_tiles;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = FLAT_SMEM, cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_flat3x3_pair_kernel, p));
-    return;
-  }
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(tc_flat3x3_kernel, FLAT_SMEM, configured);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   launch_k(tc_flat3x3_kernel, dim3(grid), dim3(320), FLAT_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------------------
-void launch_stem(const StemArgs& a, cudaStream_t stream) {
-  // Input layout (written by the preprocess kernel): row-pair interleaved, padded by 3 pixels on every side:
-  //   P[n][y2 = 0..74][x = 0..261][r = 0..1][c = 0..3]  (padded row 2*y2 + r), 16 bytes per (y2, x).
-  // Output pixel (oh, ow), filter-row pair j (kh = 2j, 2j+1) reads P[n][oh + j][2ow .. 2ow+7] = 128 contiguous
-  // bytes, so k-block j of the implicit GEMM is one 4-D TMA box whose ow-stride (32 B) overlaps its rows.
-  TcGemmParams p;
-  memset(&p, 0, sizeof(p));
-  const uint64_t pitch = 262 * 16;  // bytes per row pair
-  const uint64_t dims[4] = {64, 128, 75, (uint64_t)a.B};
-  const uint64_t str[3] = {32, pitch, 75 * pitch};
-  const uint32_t box[4] = {64, 128, 1, 1};
-  make_map(&p.tmA[0], 2, 4, a.in, dims, str, box);
-  make_operand_map(&p.tmB, 2, false, a.w, 256, 0, 64, 256, 1, 64);
-  p.num_kb = 4;
-  p.Hout = 72, p.Wout = 128, p.TH = 1, p.TN = 1, p.Bimg = a.B;
-  p.N = 64;
-  p.out = a.out, p.ldc = 64;
-  p.bias = a.bias;
-  p.act = ACT_RELU, p.alpha = 1.f;
-  dim3 grid(72 * a.B, 1, 1);
-  if (!g_use_v1) {
-    PersistParams q;
-    memset(&q, 0, sizeof(q));
-    q.tmA[0] = p.tmA[0], q.tmB = p.tmB;
-    {
-      const uint64_t odims[4] = {64, 128, 72, (uint64_t)a.B};
-      const uint64_t ostr[3] = {64 * 2, 128 * 64 * 2, 72 * 128 * 64 * 2};
-      const uint32_t obox[4] = {64, 128, 1, 1};
-      make_map(&q.tmOut, 2, 4, a.out, odims, ostr, obox);
-    }
-    q.num_kb = 4, q.Hout = 72, q.Wout = 128, q.TH = 1, q.TN = 1, q.Bimg = a.B;
-    q.tiles_m = grid.x, q.tiles_n = 1, q.N = 64;
-    q.bias = a.bias, q.act = ACT_RELU;
-    launch_persist<64, 6, MODE_STEM>(q, stream);
-    return;
-  }
-  launch_inst<0, 0, 0, 64, 4, MODE_STEM, EPI_LINEAR, enc_t>(p, grid, stream);
-}
-
+// Input layout of the stem (written by the preprocess kernel): row-pair interleaved, padded by 3 pixels on every
+// side: P[n][y2 = 0..74][x = 0..261][r = 0..1][c = 0..3] (padded row 2*y2 + r), 16 bytes per (y2, x). Output pixel
+// (oh, ow), filter-row pair j (kh = 2j, 2j+1) reads P[n][oh + j][2ow .. 2ow+7] = 128 contiguous bytes, so k-block j of
+// the implicit GEMM is one 4-D TMA box whose ow-stride (32 B) overlaps its rows.
 void launch_stem_pool(const StemArgs& a, cudaStream_t stream) {
   StemPoolParams p;
   memset(&p, 0, sizeof(p));
@@ -499,11 +416,8 @@ void launch_stem_pool(const StemArgs& a, cudaStream_t stream) {
   p.pool_rows = 12;
   p.num_units = a.B * (36 / p.pool_rows);
   p.dbg = g_dbg_clk;
-  static bool configured = false;
-  if (!configured) {
-    CADRE_CUDA_CHECK(cudaFuncSetAttribute(tc_stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    configured = true;
-  }
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(tc_stem_pool_kernel, SP_SMEM, configured);
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
   launch_k(tc_stem_pool_kernel, dim3(grid), dim3(320), SP_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());

@@ -142,7 +142,11 @@ class Encoder:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            self._lib.cadre_encoder_destroy(h)
+            try:
+                with torch.cuda.device(self.device):
+                    self._lib.cadre_encoder_destroy(h)
+            except Exception:
+                pass
             self._h = None
 
     def forward_u8(self, rgb, route_fig, measurements=None, out=None):
@@ -156,12 +160,13 @@ class Encoder:
         assert route_fig.is_contiguous() and out.stride(1) == 1
         if measurements is not None:
             assert measurements.dtype == torch.float64 and measurements.is_contiguous()
-        for s in range(0, B, self.max_batch):
-            n = min(self.max_batch, B - s)
-            _lib.check(self._lib.cadre_encoder_forward_u8(
-                self._h, _lib.ptr(rgb[s:]), _lib.ptr(route_fig[s:]),
-                _lib.ptr(measurements[s:]) if measurements is not None else None, n, _lib.ptr(out[s:]),
-                out.stride(0), _lib.stream_ptr()))
+        with torch.cuda.device(self.device):     # the library launches on the CURRENT device (vae_device may differ)
+            for s in range(0, B, self.max_batch):
+                n = min(self.max_batch, B - s)
+                _lib.check(self._lib.cadre_encoder_forward_u8(
+                    self._h, _lib.ptr(rgb[s:]), _lib.ptr(route_fig[s:]),
+                    _lib.ptr(measurements[s:]) if measurements is not None else None, n, _lib.ptr(out[s:]),
+                    out.stride(0), _lib.stream_ptr(self.device)))
         return out
 
     def forward_f32(self, x, out=None):
@@ -171,10 +176,11 @@ class Encoder:
         x = x.contiguous()
         if out is None:
             out = torch.empty(B, 512, device=self.device, dtype=torch.float32)
-        for s in range(0, B, self.max_batch):
-            n = min(self.max_batch, B - s)
-            _lib.check(self._lib.cadre_encoder_forward_f32(self._h, _lib.ptr(x[s:]), n, _lib.ptr(out[s:]),
-                                                           out.stride(0), _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            for s in range(0, B, self.max_batch):
+                n = min(self.max_batch, B - s)
+                _lib.check(self._lib.cadre_encoder_forward_f32(self._h, _lib.ptr(x[s:]), n, _lib.ptr(out[s:]),
+                                                               out.stride(0), _lib.stream_ptr(self.device)))
         return out
 
     def debug_buffer(self, which, B):
@@ -183,8 +189,16 @@ class Encoder:
         n = ctypes.c_int64()
         _lib.check(self._lib.cadre_encoder_buffer(self._h, which, ctypes.byref(p), ctypes.byref(n)))
         t = torch.empty(B * n.value, device=self.device, dtype=self.enc16)
-        _lib.check(self._lib.cadre_memcpy_d2d(_lib.ptr(t), p, ctypes.c_int64(B * n.value * 2), _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_memcpy_d2d(_lib.ptr(t), p, ctypes.c_int64(B * n.value * 2),
+                                                  _lib.stream_ptr(self.device)))
         return t
+
+    def activation_absmax(self, B):
+        """max |activation| of the first B frames in the debug-visible buffers of the last forward (layer4, conv5a|5c,
+        PAM, CAM, head sum, fc1). 16-bit stores SATURATE at 65504 (fp16), so a value at the limit means the checkpoint
+        drives activations out of the fp16 range."""
+        return max(float(self.debug_buffer(w, B).float().abs().max()) for w in range(6))
 
     def profile(self, B):
         """[(launch name, ms)] for the trunk re-run on the B frames ingested by the previous forward call."""
@@ -192,8 +206,9 @@ class Encoder:
         ms = (ctypes.c_float * 64)()
         names = ctypes.create_string_buffer(4096)
         n = ctypes.c_int()
-        _lib.check(self._lib.cadre_encoder_profile(self._h, B, _lib.ptr(out), 512, ms, names, 4096, ctypes.byref(n),
-                                                   _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_encoder_profile(self._h, B, _lib.ptr(out), 512, ms, names, 4096,
+                                                       ctypes.byref(n), _lib.stream_ptr(self.device)))
         return list(zip(names.value.decode().split(";"), [ms[i] for i in range(n.value)]))
 
     @property

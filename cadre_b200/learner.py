@@ -11,14 +11,13 @@ replicas hold identical parameters afterwards. How it is done here:
   * every rank then runs the same deterministic clip + Adam kernel, so no parameter broadcast
     (agent.py:239-243) is needed and replicas stay bit-identical.
 """
-import ctypes
 import os
 
 import numpy as np
 import torch
 
-from . import _lib
 from . import ppo as _ppo
+from ._lib import CadreError
 from . import ppo_params
 from .storage import RolloutStorage
 
@@ -75,9 +74,10 @@ class Learner:
         self.grads = torch.zeros_like(self.params)
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
-        self.losses = torch.zeros(workers, 2, 3, device=self.device)
+        self.losses = torch.zeros(workers, 2, 3, device=self.device)       # last update step
+        self.loss_sum = torch.zeros(workers, 2, 3, device=self.device)     # summed over the update steps of learn()
+        self.loss_steps = 0
         self.step_count = 0
-        self.l2_persist = os.environ.get("CADRE_L2_PERSIST", "0") == "1"   # measured: no gain on B200, costs the encoder L2
         self.pg = process_group
         self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
         self._comm_stream = self._comm_done = None
@@ -109,12 +109,20 @@ class Learner:
             per_worker.append((s_chunks, t_chunks))
         if keep is not None:
             torch.set_rng_state(keep)
-        n_mb = min(len(per_worker[0][0]), len(per_worker[0][1]))
+        n_mb = min(min(len(s), len(t)) for s, t in per_worker)     # zip() of the two generators (train.py:94)
         out = np.empty((n_mb, len(storages), 2, self.mini_batch), dtype=np.int32)
         for w, (s_chunks, t_chunks) in enumerate(per_worker):
             for k in range(n_mb):
-                out[k, w, 0] = s_chunks[k]
-                out[k, w, 1] = t_chunks[k]
+                for h, chunk in enumerate((s_chunks[k], t_chunks[k])):
+                    if len(chunk) != self.mini_batch:
+                        # BatchSampler(drop_last=False) yields a short last chunk when num_steps is not a multiple of
+                        # num_steps // mini_batch_num (storage.py:93-97); the batched engine is sized for ONE
+                        # minibatch length. CadreAgent.update_policy handles such tails (one engine per length).
+                        raise CadreError(
+                            f"ragged minibatch: chunk {k} of worker {w} has {len(chunk)} rows, the learner was built "
+                            f"for mini_batch={self.mini_batch}; choose num_steps divisible by num_steps // "
+                            "mini_batch_num or drive CadreAgent.update_policy per worker")
+                    out[k, w, h] = chunk
         return out
 
     # ---------------------------------------------------------------- one synchronous update step
@@ -131,21 +139,6 @@ class Learner:
                 if self._comm_stream is None:
                     self._comm_stream = torch.cuda.Stream(device=self.device)
                     self._comm_done = torch.cuda.Event()
-                groups = self.engine.grad_groups
-                if groups > 1:   # experimental (CADRE_GRAD_GROUPS): one collective per group of experts, pipelined
-                    chunk = n1 // groups
-                    with torch.cuda.stream(self._comm_stream):
-                        for k in range(2 * groups):
-                            self.engine.wait_grad_group(k, self._comm_stream)
-                            torch.distributed.all_reduce(self.grads[k * chunk:(k + 1) * chunk],
-                                                         op=torch.distributed.ReduceOp.SUM, group=self.pg)
-                        self._comm_done.record(self._comm_stream)
-                    torch.distributed.all_reduce(self.grads[2 * n1:], op=torch.distributed.ReduceOp.SUM, group=self.pg)
-                    torch.cuda.current_stream().wait_event(self._comm_done)
-                    self.step_count += 1
-                    self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
-                                          self.max_grad_norm, self.lr)
-                    return self.losses if async_losses else self.scaled_losses()
                 with torch.cuda.stream(self._comm_stream):
                     self.engine.wait_wih(self._comm_stream)
                     torch.distributed.all_reduce(self.grads[:n1], op=torch.distributed.ReduceOp.SUM, group=self.pg)
@@ -157,26 +150,27 @@ class Learner:
         self.step_count += 1
         self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
                               self.max_grad_norm, self.lr)
+        self.loss_sum += self.losses
+        self.loss_steps += 1
         return self.losses if async_losses else self.scaled_losses()
 
-    def scaled_losses(self):
-        """[W,3] = (value_loss*coeff, action_loss*coeff, entropy*coeff) per worker, like update_policy's return."""
-        L = self.losses.sum(1).cpu()
+    def scaled_losses(self, mean=False):
+        """[W,3] = (value_loss*coeff, action_loss*coeff, entropy*coeff) per worker, like update_policy's return:
+        of the LAST update step, or with `mean=True` averaged over the update steps since the last `learn()` began
+        (what train.py:98-100, 112-116 logs)."""
+        L = (self.loss_sum / max(1, self.loss_steps) if mean else self.losses).sum(1).cpu()
         return L * torch.tensor([self.value_coeff, self.clip_coeff, self.ent_coeff])
 
     def learn(self, pool_or_storages, ppo_epoch=4):
         """ppo_epoch x minibatches of update_step over already computed returns/advantages (train.py:93-110)."""
         storages = pool_or_storages.storages if hasattr(pool_or_storages, "storages") else pool_or_storages
+        self.loss_sum.zero_()
+        self.loss_steps = 0
         n = 0
-        if self.l2_persist:   # keep W_ih / W_hh (the first 72 MB of the flat buffer) L2-resident during the update
-            nbytes = 2 * ppo_params.E * ppo_params.G * ppo_params.LDF * 4
-            _lib.check(_lib.lib().cadre_l2_persist(_lib.ptr(self.params), ctypes.c_int64(nbytes), _lib.stream_ptr()))
         for _ in range(ppo_epoch):
             for idx in self.sample_epoch_indices(storages):
                 self.update_step(storages, idx)
                 n += 1
-        if self.l2_persist:
-            _lib.check(_lib.lib().cadre_l2_persist(None, ctypes.c_int64(0), _lib.stream_ptr()))
         return n
 
     def state(self):

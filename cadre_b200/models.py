@@ -8,25 +8,70 @@ zero_grad` surface that `train.py`, `chief.py` and snapshot code touch, implemen
 the flat buffer.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
 
 from . import ppo_params
+from ._lib import CadreError
 
 Z_DIMS = 256            # carla_perception/Config/auto_danet.py:145
 LATENT_CHANNELS = 4     # RGB + route (auto_danet.py:111-119)
 
+# carla_perception/Config/auto_danet.py:14,24,41,46-56: load_epoch 90, input_mode 9, output_mode 12, version "danet",
+# train_town "nocrash_IL_n10_k1234_r40", exp_suffix "34"
+_LOAD_EPOCH = 90
+_EXP_SUFFIX = "34"
+_EXP_DIR = "danet912_nocrash_IL_n10_k1234_r40"
+# tensors of the checkpoint that `get_latent_feature(x, "concate")` reads (danet.py:216-238); everything else in the
+# file (decoder heads, speed fc, ...) is off the path and ignored
+ON_PATH_PREFIXES = ("backbone.", "da_head.", "visual_conv.", "bc_conv.", "inter_task_att.")
+
+
+class DanetParams:
+    """The two fields of `danet_config()` (auto_danet.py:7-171) that the PPO side reads through
+    `get_vae_output(...)[1]`: `.networks['autoencoder']['z_dims']` and `['pretrained_path']`."""
+
+    def __init__(self, pretrained_path=None):
+        self.load_epoch = _LOAD_EPOCH
+        self.networks = {"autoencoder": {"z_dims": Z_DIMS, "pretrained": True, "pretrained_path": pretrained_path}}
+
+
+def default_pretrained_path():
+    """auto_danet.py:161-171: $CHALLENGE_DIR/carla_perception/Experiments34/danet912_nocrash_IL_n10_k1234_r40/
+    net_epoch90. Like the reference, a missing CHALLENGE_DIR is a KeyError."""
+    return os.path.join(os.environ["CHALLENGE_DIR"], "carla_perception/Experiments" + _EXP_SUFFIX, _EXP_DIR,
+                        "net_epoch" + str(_LOAD_EPOCH))
+
 
 def get_vae_output(model_cfg):
-    """models.py:33-42: observation width = 2*z_dims (+ measurement_dim) for the CoPM encoders."""
+    """models.py:33-42: observation width = 2*z_dims (+ measurement_dim) for the CoPM encoders, and the
+    perception config. `model_cfg['pretrained_path']` (an extension: the reference config has no such key)
+    overrides the $CHALLENGE_DIR-derived checkpoint path."""
     vae_params_cfg = model_cfg["vae_params"]
     measurement_dim = model_cfg["measurement_dim"]
+    path = model_cfg.get("pretrained_path") if hasattr(model_cfg, "get") else None
+    if path is None and "CHALLENGE_DIR" in os.environ:
+        path = default_pretrained_path()
+    vae_params = DanetParams(path)
     if vae_params_cfg in ("CoPM", "CoPM w/o att"):
         obs_dim = 2 * Z_DIMS + measurement_dim
     else:
         obs_dim = Z_DIMS + measurement_dim
-    return obs_dim, None
+    return obs_dim, vae_params
+
+
+def load_danet_checkpoint(path):
+    """models.py:55-63: the perception checkpoint is `{'epoch', 'metric', 'autoencoder': state_dict}` written by
+    experiments_builder.py:442-...; returns the `'autoencoder'` state dict restricted to the on-path tensors.
+    Unlike the reference (which prints 'VAE model load fail' and keeps RANDOM weights when keys do not match,
+    models.py:68-74) a checkpoint that lacks an on-path tensor is an error."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    if "autoencoder" not in ckpt:
+        raise CadreError(f"{path}: no 'autoencoder' entry (keys: {list(ckpt.keys())[:8]})")
+    sd = ckpt["autoencoder"]
+    return {k: v for k, v in sd.items() if k.startswith(ON_PATH_PREFIXES)}
 
 
 class FlatParameter:
@@ -151,24 +196,64 @@ def create_model(model_cfg, load_vae=False, danet_state=None, ppo_state=None, ma
     when load_vae is False, as in main.py:38); `model_dict` maps the 16 reference module names to FlatModule
     windows of one shared `FlatParams` (reachable as `model_dict.owner`).
 
-    `danet_state`: the `'autoencoder'` state dict of the reference checkpoint (models.py:55-63). When omitted
-    the checkpoint at `model_cfg['pretrained_path']` is read with torch.load (same file format)."""
+    `danet_state`: the `'autoencoder'` state dict of the reference checkpoint (models.py:55-63), for callers that
+    hold the weights in memory. When omitted the checkpoint is read from the path the reference uses:
+    `danet_config().networks['autoencoder']['pretrained_path']` = $CHALLENGE_DIR/carla_perception/Experiments34/
+    danet912_nocrash_IL_n10_k1234_r40/net_epoch90 (auto_danet.py:161-171), so `CadreAgent(**agent_cfg)` works
+    with the reference's unmodified config."""
     dev = model_cfg["device_num"]
     if dev == -1:
-        from ._lib import CadreError
         raise CadreError("device_num = -1 (CPU) is not supported: cadre_b200 has no CPU path")
     device = torch.device("cuda:" + str(dev))
     vae_model = None
     if load_vae:
         from .encoder import Encoder
+        if model_cfg["vae_device"] == -1:
+            raise CadreError("vae_device = -1 (CPU) is not supported: cadre_b200 has no CPU path")
         if danet_state is None:
-            ckpt = torch.load(model_cfg["pretrained_path"], map_location="cpu")
-            danet_state = ckpt["autoencoder"]
+            _, vae_params = get_vae_output(model_cfg)
+            path = vae_params.networks["autoencoder"]["pretrained_path"]
+            if path is None:
+                path = default_pretrained_path()      # KeyError('CHALLENGE_DIR') like auto_danet.py:168
+            danet_state = load_danet_checkpoint(path)
         vae_dev = torch.device("cuda:" + str(model_cfg["vae_device"]))
         vae_model = Encoder(danet_state, vae_dev, max_batch=max_batch)
     owner = FlatParams(device, ppo_state if ppo_state is not None else init_state())
     model_dict = ModelDict(owner)
     return vae_model, model_dict
+
+
+class ModuleState(OrderedDict):
+    """Picklable snapshot entry: a state dict that also answers `.state_dict()`, which is all the reference's
+    `load_snapshot` asks of an entry (agent.py:266-267: `model_dict[name].state_dict()`)."""
+
+    def state_dict(self):
+        return OrderedDict(self)
+
+
+def save_model_dict(model_dict, model_path):
+    """agent.py:245-260 `save_snapshot`. The reference pickles the nn.Modules themselves and forgets the four
+    `throttle_lstm_*` modules (it stores `steer_ppo_*` twice); here all 16 entries are written as `ModuleState`
+    objects: readable by this package, and by the reference's `load_snapshot` whenever `cadre_b200` is importable
+    in that process (it only calls `.state_dict()` on each entry)."""
+    torch.save({name: ModuleState((k, v.cpu()) for k, v in m.state_dict().items()) for name, m in model_dict.items()},
+               model_path)
+
+
+def load_model_dict(model_dict, model_path, device=None):
+    """agent.py:262-271 `load_snapshot`: accepts snapshots written by `save_model_dict`, plain dicts of state
+    dicts, and the reference's own files (pickled `Model` / `LSTM` nn.Modules: unpickling those needs the
+    reference's `ppo_agent.models` importable, as in any process that ran the reference). `device` is accepted for
+    signature compatibility; tensors are copied into the flat parameter buffer wherever that lives.
+    Errors are re-raised as ImportError like the reference."""
+    try:
+        snap = torch.load(model_path, map_location="cpu", weights_only=False)
+        for name in snap:
+            entry = snap[name]
+            sd = entry.state_dict() if hasattr(entry, "state_dict") else entry
+            model_dict[name].load_state_dict(sd)
+    except Exception as e:  # agent.py:270-271
+        raise ImportError("load snapshot error due to {}".format(e))
 
 
 class ModelDict(OrderedDict):

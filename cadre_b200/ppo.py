@@ -86,25 +86,28 @@ class PpoEngine:
         idx = self._marshal(storages, advantages, indices)
         if losses is None:
             losses = torch.empty(self.workers, 2, 3, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.cadre_ppo_update(self._h, self._refs, idx.ctypes.data_as(ctypes.c_void_p),
-                                              _lib.ptr(params), _lib.ptr(grads), _lib.ptr(losses),
-                                              _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_update(self._h, self._refs, idx.ctypes.data_as(ctypes.c_void_p),
+                                                  _lib.ptr(params), _lib.ptr(grads), _lib.ptr(losses),
+                                                  _lib.stream_ptr(self.device)))
         return losses
 
     def evaluate(self, storages, advantages, indices, params):
         """Forward only: returns [2, W*mb, 36] = value, log-prob(action), entropy, 33 normalised logits."""
         idx = self._marshal(storages, advantages, indices)
         out = torch.zeros(2, self.workers * self.mini_batch, ROW_OUT, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.cadre_ppo_evaluate(self._h, self._refs, idx.ctypes.data_as(ctypes.c_void_p),
-                                                _lib.ptr(params), _lib.ptr(out), _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_evaluate(self._h, self._refs, idx.ctypes.data_as(ctypes.c_void_p),
+                                                    _lib.ptr(params), _lib.ptr(out), _lib.stream_ptr(self.device)))
         return out
 
     def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, max_grad_norm=250.0, lr=3e-4, betas=(0.9, 0.999),
                   eps=1e-8):
-        _lib.check(self._lib.cadre_ppo_adam_step(
-            self._h, _lib.ptr(params), _lib.ptr(grads), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
-            ctypes.c_float(max_grad_norm), ctypes.c_float(lr), ctypes.c_float(betas[0]), ctypes.c_float(betas[1]),
-            ctypes.c_float(eps), int(step), _lib.stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_adam_step(
+                self._h, _lib.ptr(params), _lib.ptr(grads), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                ctypes.c_float(max_grad_norm), ctypes.c_float(lr), ctypes.c_float(betas[0]), ctypes.c_float(betas[1]),
+                ctypes.c_float(eps), int(step), _lib.stream_ptr(self.device)))
 
     def module_norms(self):
         """{module name: gradient norm seen by the last adam_step} (16 entries, reference module names)."""
@@ -116,13 +119,6 @@ class PpoEngine:
             out[f"{head}_lstm_{c}"] = buf[e]
             out[f"{head}_ppo_{c}"] = buf[8 + e]
         return out
-
-    @property
-    def grad_groups(self):
-        return int(self._lib.cadre_ppo_grad_groups(self._h))
-
-    def wait_grad_group(self, index, stream):
-        _lib.check(self._lib.cadre_ppo_wait_grad_group(self._h, int(index), ctypes.c_void_p(stream.cuda_stream)))
 
     def wait_wih(self, stream):
         """`stream` (torch.cuda.Stream) waits until the last update() has finished the W_ih block of the gradient."""
@@ -138,7 +134,8 @@ def gae(rewards, values, masks, next_value, returns, adv, gamma=0.99, tau=0.95, 
     E, T1 = rewards.shape
     for t in (rewards, values, masks, next_value, returns, adv):
         _check_tensor(t, torch.float32, "gae input")
-    _lib.check(_lib.lib().cadre_gae(_lib.ptr(rewards), _lib.ptr(values), _lib.ptr(masks), _lib.ptr(next_value),
-                                    _lib.ptr(returns), _lib.ptr(adv), E, T1 - 1, ctypes.c_float(gamma),
-                                    ctypes.c_float(tau), int(bool(normalize)), _lib.stream_ptr()))
+    with torch.cuda.device(rewards.device):
+        _lib.check(_lib.lib().cadre_gae(_lib.ptr(rewards), _lib.ptr(values), _lib.ptr(masks), _lib.ptr(next_value),
+                                        _lib.ptr(returns), _lib.ptr(adv), E, T1 - 1, ctypes.c_float(gamma),
+                                        ctypes.c_float(tau), int(bool(normalize)), _lib.stream_ptr(rewards.device)))
     return returns, adv

@@ -57,7 +57,7 @@ def train(rank, train_cfg, agent_cfg, env_cfg, rollout_cfg, danet_state, ppo_sta
             nv[w, 0], nv[w, 1] = float(vs.reshape(-1)[0]), float(vt.reshape(-1)[0])
         pool.compute_returns(nv, normalize=train_cfg.use_adv_norm)        # train.py:81-88
         learner.learn(pool, train_cfg.ppo_epoch)                          # train.py:93-110
-        L = learner.scaled_losses().mean(0)
+        L = learner.scaled_losses(mean=True).mean(0)     # mean over update steps and workers
         history.append(L.tolist())
         if episode % train_cfg.log_interval == 0 and rank == 0:
             log("Episode: {}, value loss: {:.4f}, policy loss: {:.4f}, entropy loss: {:.4f}".format(episode, *L))
@@ -77,7 +77,12 @@ def main():
     if not ckpt:
         raise SystemExit("set CADRE_ENCODER_CKPT to the reference perception checkpoint ({'autoencoder': state_dict})")
     danet_state = torch.load(ckpt, map_location="cpu")["autoencoder"]
-    workers = max(1, cfg.env_cfg.num_processes // world)
+    # env_cfg.num_processes logical workers in total (main.py:41-60), split evenly over the ranks. Gradients are SUMMED
+    # over workers like the reference (models.py:231-239), so the effective step (clip at max_grad_norm, Adam's eps)
+    # depends on the total worker count: it must match the configured one, not grow with the number of GPUs.
+    if cfg.env_cfg.num_processes % world:
+        raise SystemExit(f"env_cfg.num_processes={cfg.env_cfg.num_processes} is not divisible by WORLD_SIZE={world}")
+    workers = cfg.env_cfg.num_processes // world
     train(rank, cfg.train_cfg, cfg.agent_cfg, cfg.env_cfg, cfg.rollout_cfg, danet_state, workers=workers)
 
 

@@ -26,10 +26,6 @@ const char* cadre_version(void);
 /* 16-bit storage / tensor-core operand type of the encoder path: 1 = IEEE fp16 (default build), 0 = bf16.
  * Every "enc16" buffer below (activations, conv / linear weights) uses this type. */
 int cadre_enc_dtype(void);
-/* Pin [ptr, ptr+nbytes) in the persisting part of L2 for kernels subsequently launched on `stream`
- * (cudaAccessPolicyWindow); ptr = NULL or nbytes = 0 removes the window. Used by the learner to keep the LSTM
- * weights (72 MB fp32) L2-resident across the 8 recurrent steps and 7 dgrad GEMMs of an update. */
-int cadre_l2_persist(const void* ptr, int64_t nbytes, void* stream);
 /* stream-ordered device-to-device copy (test / debug helper) */
 int cadre_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream);
 
@@ -83,11 +79,6 @@ int cadre_debug_clk(long long* dev_counters);
 
 int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
                          int act, void* out, void* stream);
-
-/* ResNet stem conv7x7/s2/p3 + folded BN + ReLU over the padded 4-channel image written by
- * cadre_preprocess (resnet.py:169-171). */
-int cadre_stem_conv(const void* in_padded, int B, const void* w256, const float* bias, void* out,
-                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Perception encoder forward = DANet.get_latent_feature(x, "concate")
@@ -194,11 +185,6 @@ int cadre_ppo_module_norms(void* handle, float* norms16_host);
  * caller can start the all-reduce of that block (Shared_grad_buffers.add_gradient, models.py:231-239) while the
  * W_hh gradient is still being computed. */
 int cadre_ppo_wait_wih(void* handle, void* stream);
-/* Experimental finer pipeline (environment CADRE_GRAD_GROUPS = 2 / 4 / 8 when the plan is created; default 1 = off):
- * the W_ih and W_hh gradient blocks are produced per group of 8/groups experts; group index k = which * groups + g
- * (which 0 = W_ih, 1 = W_hh) covers elements [k, k+1) * (8*2120*532 / groups) of the flat buffer. */
-int cadre_ppo_grad_groups(void* handle);
-int cadre_ppo_wait_grad_group(void* handle, int index, void* stream);
 int cadre_ppo_launches(void* handle);
 
 #ifdef __cplusplus

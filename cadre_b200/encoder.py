@@ -43,13 +43,61 @@ def _khwc(w):
     return w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], -1)
 
 
-def prepare_weights(sd, device, enc16=torch.float16):
+# fp16 operands: largest finite value and smallest NORMAL magnitude (below it precision degrades bit by bit)
+FP16_MAX, FP16_MIN_NORMAL = 65504.0, 6.103515625e-05
+SUBNORMAL_FRACTION_LIMIT = 0.01
+
+
+def required_keys():
+    """Names of the checkpoint tensors the `get_latent_feature` path reads (danet.py:86-109, 216-238)."""
+    keys = ["backbone.conv1.weight", "backbone.conv1.bias"]
+    bn = lambda p: [p + s for s in (".weight", ".bias", ".running_mean", ".running_var")]  # noqa: E731
+    keys += bn("backbone.bn1")
+    for li in range(1, 5):
+        for bi in range(2):
+            p = f"backbone.layer{li}.{bi}"
+            keys += [p + ".conv1.weight", p + ".conv2.weight"] + bn(p + ".bn1") + bn(p + ".bn2")
+            if li > 1 and bi == 0:
+                keys += [p + ".downsample.0.weight"] + bn(p + ".downsample.1")
+    for nm in ("conv5a", "conv5c", "conv51", "conv52"):
+        keys += [f"da_head.{nm}.0.weight"] + bn(f"da_head.{nm}.1")
+    for nm in ("query_conv", "key_conv", "value_conv"):
+        keys += [f"da_head.sa.{nm}.weight", f"da_head.sa.{nm}.bias"]
+    keys += ["da_head.sa.gamma", "da_head.sc.gamma", "da_head.conv8.1.weight", "da_head.conv8.1.bias",
+             "visual_conv.weight", "visual_conv.bias", "bc_conv.weight", "bc_conv.bias"]
+    for task in ("visual", "bc"):
+        for role in ("query", "key", "value"):
+            p = f"inter_task_att.{task}_{role}_layer"
+            keys += [p + ".1.weight", p + ".1.bias", p + ".3.weight", p + ".3.bias"]
+    return keys
+
+
+def prepare_weights(sd, device, enc16=torch.float16, check_range=True):
     """DANet state dict (reference key names) -> dict of device tensors in the library's layouts.
-    `enc16` is the library's 16-bit operand type (`_lib.enc_dtype()`)."""
+    `enc16` is the library's 16-bit operand type (`_lib.enc_dtype()`).
+
+    The folds run in fp64 and the results are rounded ONCE to fp16, without per-channel scales. That is safe as long as
+    a folded matrix fits the fp16 range, which `check_range` verifies instead of assuming: a folded weight beyond
+    65504 (a BatchNorm with a vanishing running_var, say) or a matrix with more than 1 % of its non-zero entries below
+    the smallest normal fp16 raises CadreError naming the tensor - never a silently saturated / flushed operand."""
+    missing = [k for k in required_keys() if k not in sd]
+    if missing:
+        raise _lib.CadreError(f"perception checkpoint lacks {len(missing)} tensor(s) of the get_latent_feature path, "
+                              f"e.g. {missing[:4]}")
     sd = {k: v.detach().cpu() for k, v in sd.items()}
     out = {}
 
     def put(name, t, dtype):
+        if check_range and dtype == torch.float16:
+            a = t.detach().abs().double()
+            if not torch.isfinite(a).all() or float(a.max()) > FP16_MAX:
+                raise _lib.CadreError(f"folded weight `{name}` does not fit fp16 (max |w| = {float(a.max()):.3e} > "
+                                      f"{FP16_MAX}); the checkpoint's BatchNorm statistics drive it out of range")
+            nz = a > 0
+            sub = float(((a < FP16_MIN_NORMAL) & nz).sum()) / max(1, int(nz.sum()))
+            if sub > SUBNORMAL_FRACTION_LIMIT:
+                raise _lib.CadreError(f"folded weight `{name}`: {100 * sub:.1f} % of its non-zero entries are below the "
+                                      f"smallest normal fp16 ({FP16_MIN_NORMAL:.2e}) and would lose precision")
         out[name] = t.to(dtype).contiguous().to(device)
 
     # stem (resnet.py:111-112,169-171): conv7x7 s2 with bias + BN

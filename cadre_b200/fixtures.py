@@ -32,12 +32,32 @@ def fixture_tensor(name, shape, seed, std=1.0, mean=0.0, uniform=None):
     return torch.randn(shape, generator=g, dtype=torch.float32) * std + mean
 
 
+_XAVIER = False   # set by danet_fixture_state(init="xavier") while it builds a state dict
+
+
+def _xavier(name, shape, seed):
+    """nn.init.xavier_uniform_: U(-a, a), a = sqrt(6 / (fan_in + fan_out)) (experiments_builder.py:163-188)."""
+    rf = 1
+    for d in shape[2:]:
+        rf *= d
+    a = math.sqrt(6.0 / (shape[1] * rf + shape[0] * rf))
+    return fixture_tensor(name, shape, seed, uniform=(-a, a))
+
+
 def _conv_w(sd, name, cout, cin, k, seed, gain=1.0):
+    if _XAVIER:
+        sd[name] = _xavier(name, (cout, cin, k, k), seed)
+        return
     fan_in = cin * k * k
     sd[name] = fixture_tensor(name, (cout, cin, k, k), seed, std=gain * math.sqrt(2.0 / fan_in))
 
 
 def _bn(sd, prefix, c, seed):
+    if _XAVIER:   # experiments_builder.py:177-179 + BatchNorm2d defaults: the identity at eval time (up to eps)
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = torch.ones(c), torch.zeros(c)
+        sd[prefix + ".running_mean"], sd[prefix + ".running_var"] = torch.zeros(c), torch.ones(c)
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+        return
     # randomised affine + running statistics (defaults would make eval-mode BN ~identity, SURVEY.md §8c.3)
     sd[prefix + ".weight"] = fixture_tensor(prefix + ".weight", (c,), seed, uniform=(0.6, 1.4))
     sd[prefix + ".bias"] = fixture_tensor(prefix + ".bias", (c,), seed, std=0.1)
@@ -47,20 +67,39 @@ def _bn(sd, prefix, c, seed):
 
 
 def _linear(sd, prefix, out_f, in_f, seed, gain=1.0, bias_std=0.02):
+    if _XAVIER:
+        sd[prefix + ".weight"] = _xavier(prefix + ".weight", (out_f, in_f), seed)
+        sd[prefix + ".bias"] = torch.zeros(out_f)
+        return
     sd[prefix + ".weight"] = fixture_tensor(prefix + ".weight", (out_f, in_f), seed, std=gain / math.sqrt(in_f))
     sd[prefix + ".bias"] = fixture_tensor(prefix + ".bias", (out_f,), seed, std=bias_std)
 
 
-def danet_fixture_state(seed=0, peaky=False):
+def danet_fixture_state(seed=0, peaky=False, init="default"):
     """State-dict entries (reference key names) of every DANet tensor on the `get_latent_feature` path.
+
+    `init="xavier"`: the reference trainer's initialisation (Models/experiments_builder.py:163-188): Xavier-uniform
+    conv / linear weights, zero biases, identity BatchNorm, and the zero-initialised attention gammas of
+    da_att.py:29,61 - i.e. an untrained network, whose activations are orders of magnitude smaller than the default
+    fixture's (a dynamic-range test for the fp16 operands).
 
     Keys follow carla_perception/Networks/danet.py:86-109 (backbone, da_head, visual_conv, bc_conv,
     inter_task_att); decoder heads (visual_branch, bc_branch, in_bc_speed_fc) are off-path and absent.
     `peaky=True` scales the attention projections so the three softmaxes are far from uniform.
     """
+    global _XAVIER
+    _XAVIER = init == "xavier"
+    try:
+        return _danet_state(seed, peaky)
+    finally:
+        _XAVIER = False
+
+
+def _danet_state(seed, peaky):
     sd = {}
     _conv_w(sd, "backbone.conv1.weight", 64, 4, 7, seed)
-    sd["backbone.conv1.bias"] = fixture_tensor("backbone.conv1.bias", (64,), seed, std=0.05)
+    sd["backbone.conv1.bias"] = (torch.zeros(64) if _XAVIER else
+                                 fixture_tensor("backbone.conv1.bias", (64,), seed, std=0.05))
     _bn(sd, "backbone.bn1", 64, seed)
     inpl = 64
     for li, planes in enumerate((64, 128, 256, 512), start=1):
@@ -81,15 +120,26 @@ def danet_fixture_state(seed=0, peaky=False):
     qk_gain = 1.5 if peaky else 1.0
     for nm, co in (("query_conv", 16), ("key_conv", 16), ("value_conv", 128)):
         g = qk_gain if nm != "value_conv" else 1.0
+        if _XAVIER:
+            sd[f"da_head.sa.{nm}.weight"] = _xavier(f"da_head.sa.{nm}.weight", (co, 128, 1, 1), seed)
+            sd[f"da_head.sa.{nm}.bias"] = torch.zeros(co)
+            continue
         sd[f"da_head.sa.{nm}.weight"] = fixture_tensor(f"da_head.sa.{nm}.weight", (co, 128, 1, 1), seed,
                                                         std=g / math.sqrt(128))
         sd[f"da_head.sa.{nm}.bias"] = fixture_tensor(f"da_head.sa.{nm}.bias", (co,), seed, std=0.05)
-    sd["da_head.sa.gamma"] = torch.tensor([0.7])   # zero-init in the reference (da_att.py:29) = no-op
-    sd["da_head.sc.gamma"] = torch.tensor([0.3])   # da_att.py:61
-    sd["da_head.conv8.1.weight"] = fixture_tensor("da_head.conv8.1.weight", (512, 128, 1, 1), seed,
-                                                  std=1.0 / math.sqrt(128))
-    sd["da_head.conv8.1.bias"] = fixture_tensor("da_head.conv8.1.bias", (512,), seed, std=0.05)
+    sd["da_head.sa.gamma"] = torch.tensor([0.0 if _XAVIER else 0.7])   # zero-init in the reference (da_att.py:29) = no-op
+    sd["da_head.sc.gamma"] = torch.tensor([0.0 if _XAVIER else 0.3])   # da_att.py:61
+    if _XAVIER:
+        sd["da_head.conv8.1.weight"] = _xavier("da_head.conv8.1.weight", (512, 128, 1, 1), seed)
+        sd["da_head.conv8.1.bias"] = torch.zeros(512)
+    else:
+        sd["da_head.conv8.1.weight"] = fixture_tensor("da_head.conv8.1.weight", (512, 128, 1, 1), seed,
+                                                      std=1.0 / math.sqrt(128))
+        sd["da_head.conv8.1.bias"] = fixture_tensor("da_head.conv8.1.bias", (512,), seed, std=0.05)
     for nm in ("visual_conv", "bc_conv"):
+        if _XAVIER:
+            sd[nm + ".weight"], sd[nm + ".bias"] = _xavier(nm + ".weight", (512, 512, 1, 1), seed), torch.zeros(512)
+            continue
         sd[nm + ".weight"] = fixture_tensor(nm + ".weight", (512, 512, 1, 1), seed, std=1.0 / math.sqrt(512))
         sd[nm + ".bias"] = fixture_tensor(nm + ".bias", (512,), seed, std=0.05)
     it_gain = 2.0 if peaky else 1.0

@@ -223,12 +223,21 @@ def create_model(model_cfg, load_vae=False, danet_state=None, ppo_state=None, ma
     return vae_model, model_dict
 
 
-class ModuleState(OrderedDict):
-    """Picklable snapshot entry: a state dict that also answers `.state_dict()`, which is all the reference's
-    `load_snapshot` asks of an entry (agent.py:266-267: `model_dict[name].state_dict()`)."""
+class ModuleState:
+    """Picklable snapshot entry: holds one module's state dict and answers `.state_dict()`, which is all the
+    reference's `load_snapshot` asks of an entry (agent.py:266-267: `model_dict[name].state_dict()`)."""
+
+    def __init__(self, sd=()):
+        self.sd = OrderedDict(sd)
 
     def state_dict(self):
-        return OrderedDict(self)
+        return self.sd
+
+
+# torch >= 2.6 loads with weights_only=True by default (the reference's torch.load call, agent.py:266, has no such
+# argument): allow-list the class so that those loaders accept our snapshots as well
+if hasattr(torch.serialization, "add_safe_globals"):
+    torch.serialization.add_safe_globals([ModuleState])
 
 
 def save_model_dict(model_dict, model_path):

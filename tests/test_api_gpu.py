@@ -1,5 +1,7 @@
 """Drop-in API on the B200: CadreAgent / RolloutStorage / Learner behave like the reference objects
 (ppo_agent/agent.py, storage.py, train.py + chief.py) and agree with the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -198,3 +200,91 @@ def test_train_loop_runs_against_the_synthetic_env(batched):
     new = learner.state()
     moved = (new["steer_lstm_0"]["rnn.weight_ih"].cpu() - ppo0["steer_lstm_0"]["rnn.weight_ih"]).abs().max().item()
     assert 0 < moved < 0.1                  # Adam moved the parameters by ~lr per step
+
+
+def test_agent_from_unmodified_reference_config(tmp_path, monkeypatch):
+    """`CadreAgent(**agent_cfg)` with the reference's config as it is (no extra keys, nothing injected): the
+    perception checkpoint is found where models.py:54-63 + auto_danet.py:161-171 look for it
+    ($CHALLENGE_DIR/carla_perception/Experiments34/.../net_epoch90), in the reference's file format, with off-path
+    decoder tensors present."""
+    from cadre_b200.agent import CadreAgent
+    from cadre_b200.config import load_config
+    from cadre_b200.models import default_pretrained_path
+    monkeypatch.setenv("CHALLENGE_DIR", str(tmp_path))
+    path = default_pretrained_path()
+    os.makedirs(os.path.dirname(path))
+    state = dict(R.danet_fixture_state(0))
+    state["visual_branch.deconv.0.weight"] = torch.randn(4, 4, 3, 3)       # off the latent path
+    torch.save({"epoch": 90, "metric": 0.0, "autoencoder": state}, path)
+    cfg = load_config()
+    assert "pretrained_path" not in cfg.agent_cfg.model_cfg
+    torch.manual_seed(0)
+    agent = CadreAgent(**cfg.agent_cfg)
+    tick = R.synthetic_tick(np.random.RandomState(31))
+    feat = agent.get_latent_feature(tick)
+    with torch.no_grad():
+        ref = R.agent_latent_feature(tick["rgb"], tick["route_fig"].copy(), tick["measurements"],
+                                     R.danet_fixture_state(0))
+    assert rel(feat, ref) < 1e-2
+    assert agent.vae_params.networks["autoencoder"]["pretrained_path"] == path
+    x = agent.pre_process(tick)
+    assert np.array_equal(x.cpu().numpy(), R.pre_process(tick["rgb"], tick["route_fig"].copy()))
+
+
+def test_snapshot_and_update_model_on_the_device(agent, tmp_path):
+    """save_snapshot -> load_snapshot into a second agent -> identical act() values; update_model pulls parameters from
+    a shared model list (agent.py:239-271)."""
+    from cadre_b200.models import FlatParams, ModelDict
+    path = str(tmp_path / "ppo_model_7.pt")
+    agent.save_snapshot(path)
+    other = ModelDict(FlatParams(agent.device, R.ppo_fixture_state(9)))
+    keep = agent.owner.params.clone()
+    try:
+        agent.update_model(other)
+        assert torch.equal(agent.owner.params, other.owner.params) and not torch.equal(agent.owner.params, keep)
+        tick = R.synthetic_tick(np.random.RandomState(8))
+        v_other = agent.get_value(False, (agent.get_latent_feature(tick), 1), (agent.get_latent_feature(tick), 2))
+        agent.load_snapshot(path, agent.device)
+        assert torch.equal(agent.owner.params, keep)
+        v_back = agent.get_value(False, (agent.get_latent_feature(tick), 1), (agent.get_latent_feature(tick), 2))
+        assert abs(v_other[0].item() - v_back[0].item()) > 1e-6         # different parameters, different value
+    finally:
+        agent.owner.params.copy_(keep)
+
+
+def test_batched_actor_sampler_follows_the_policy_distribution(agent):
+    """distributions.py:96-99 draws actions from softmax(logits); BatchedActor draws them for all environments with one
+    multinomial per head. Over many ticks on the same observation the empirical action frequencies must match the
+    policy's probabilities (chi-square, steer head folded to the bins with expected count >= 5)."""
+    from cadre_b200.actor import BatchedActor
+    E, ticks = 64, 40
+    tick = R.synthetic_tick(np.random.RandomState(12))
+    actor = BatchedActor(agent, E, verify_window=False)
+    torch.manual_seed(123)
+    feats, actions, logp, values = actor.act_batch([dict(tick, command=2) for _ in range(E)])
+    # the policy's own probabilities for this observation / command, from the oracle
+    ppo = R.ppo_fixture_state(0)
+    counts = [torch.zeros(33), torch.zeros(3)]
+    for _ in range(ticks):
+        for e in range(E):
+            actor.reset(e)                       # same 8-frame window every tick: the observation stays fixed
+        _, actions, logp, _ = actor.act_batch([dict(tick, command=2) for _ in range(E)])
+        for h in range(2):
+            counts[h] += torch.bincount(actions[:, h].cpu(), minlength=counts[h].numel()).float()
+    with torch.no_grad():
+        for h, head in enumerate(("steer", "throttle")):
+            f, _ = R.lstm_forward(feats[0].cpu(), torch.zeros(1, 530), torch.zeros(1, 530), ppo[f"{head}_lstm_2"])
+            logits = R._mlp3(f, ppo[f"{head}_ppo_2"], "control.linear.")
+            p = torch.softmax(logits, -1)[0]
+            n = E * ticks
+            exp = p * n
+            big = exp >= 5
+            chi = (((counts[h][big] - exp[big]) ** 2) / exp[big]).sum().item()
+            if (~big).any():
+                e_small, c_small = exp[~big].sum().item(), counts[h][~big].sum().item()
+                chi += (c_small - e_small) ** 2 / max(e_small, 1e-9)
+            dof = int(big.sum().item())
+            assert chi < dof + 6 * (2 * dof) ** 0.5 + 10, (head, chi, dof)   # far beyond the 1e-6 tail of chi^2(dof)
+            # log-prob returned with the action is the policy's
+            a = int(actions[0, h])
+            assert abs(logp[0, h].item() - torch.log(p[a]).item()) < 2e-2

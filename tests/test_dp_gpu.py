@@ -1,0 +1,118 @@
+"""Data-parallel update step on the GPU under test: `Learner.update_step` with world_size 2 (each rank batching two
+logical workers) against the oracle's chief step on the SUM over all four workers' gradients (train.py:101-110,
+models.py:231-239, chief.py:12-24).
+
+With >= 2 GPUs the two ranks use one GPU each over NCCL; on a one-GPU box both ranks share cuda:0 and exchange the
+gradient with gloo (NCCL refuses two ranks on one device) - the learner code path (W_ih block reduced on a side stream
+behind `cadre_ppo_wait_wih`, remainder on the main stream, replicated clip + Adam) is the same."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+W_LOCAL, MB, T, WORLD = 2, 100, 200, 2
+
+
+def _fill_worker(gid):
+    """Logical worker `gid`'s two storages (CPU tensors) with returns / advantages from the oracle's GAE."""
+    from oracle import restate as R
+    rs = np.random.RandomState(900 + gid)
+    pair = [R.synthetic_storage(rs, T=T, actions=a) for a in (R.STEER_ACTIONS, R.THROTTLE_ACTIONS)]
+    nv = [0.1 + 0.05 * gid, -0.2]
+    return pair, nv
+
+
+def _rank(rank, world, port, out_dir, backend, overlap):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ["CADRE_NO_ALLREDUCE_OVERLAP"] = "0" if overlap else "1"
+    import torch.distributed as dist
+    dev_index = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_index)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    from cadre_b200.learner import Learner, RolloutPool
+    from oracle import restate as R
+    dev = f"cuda:{dev_index}"
+    learner = Learner(W_LOCAL, MB, R.ppo_fixture_state(0), dev, seeds=[500 + rank * W_LOCAL + w for w in range(W_LOCAL)])
+    assert learner.world == world
+    pool = RolloutPool(W_LOCAL, dict(num_steps=T, mini_batch_num=T // MB, feature_dims=530, seq_length=8, use_gae=True,
+                                     gamma=0.99, tau=0.95), dev)
+    nvs = torch.zeros(W_LOCAL, 2)
+    for w in range(W_LOCAL):
+        pair, nv = _fill_worker(rank * W_LOCAL + w)
+        for h, c in enumerate(pair):
+            for k in ("obs", "rewards", "value_preds", "action_log_probs", "action", "masks", "command"):
+                getattr(pool.storages[w][h], k).copy_(c[k])
+            nvs[w, h] = nv[h]
+    pool.compute_returns(nvs)
+    idx = learner.sample_epoch_indices(pool.storages)
+    learner.update_step(pool.storages, idx[0])
+    learner.update_step(pool.storages, idx[1])           # a second step: Adam moments + step count in play
+    torch.cuda.synchronize()
+    torch.save({"params": learner.params.cpu(), "idx": idx, "losses": learner.scaled_losses(),
+                "grads": learner.grads.cpu()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap):
+    from cadre_b200 import ppo_params as P
+    from oracle import restate as R
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    port = 29700 + (os.getpid() % 1000) + (1 if overlap else 0)
+    mp.spawn(_rank, args=(WORLD, port, str(tmp_path), backend, overlap), nprocs=WORLD, join=True)
+    res = [torch.load(str(tmp_path / f"rank{r}.pt"), weights_only=False) for r in range(WORLD)]
+    # replicas are bit-identical (same reduced gradient, same deterministic clip + Adam)
+    assert torch.equal(res[0]["params"], res[1]["params"])
+    assert torch.equal(res[0]["grads"], res[1]["grads"])
+
+    # oracle: four reference workers + the chief, two update steps
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = R.ppo_fixture_state(0)
+    workers = []
+    for gid in range(WORLD * W_LOCAL):
+        pair, nv = _fill_worker(gid)
+        advs = []
+        for st, v in zip(pair, nv):
+            st["returns"], st["value_preds"] = R.compute_returns(st["rewards"], st["value_preds"], st["masks"],
+                                                                 torch.tensor([[v]]))
+            advs.append(R.normalized_advantages(st["returns"], st["value_preds"]))
+        workers.append((pair, advs))
+    pref = {m: {n: t.detach().clone() for n, t in d.items()} for m, d in sd.items()}
+    adam = {m: {n: {"exp_avg": torch.zeros_like(t), "exp_avg_sq": torch.zeros_like(t)} for n, t in d.items()}
+            for m, d in sd.items()}
+    for step in range(2):
+        params = {m: {n: t.clone().requires_grad_(True) for n, t in d.items()} for m, d in pref.items()}
+        summed = {m: {n: torch.zeros_like(t) for n, t in d.items()} for m, d in sd.items()}
+        for gid, (pair, advs) in enumerate(workers):
+            r, w = divmod(gid, W_LOCAL)
+            ix = res[r]["idx"][step, w]
+            samples = [R.gather_minibatch(pair[h], advs[h], list(ix[h])) for h in range(2)]
+            ref_l = R.update_policy(samples[0], samples[1], params)
+            if step == 1:       # the learner reports the last step's losses, per local worker
+                np.testing.assert_allclose(res[r]["losses"][w].numpy(), np.array(ref_l), rtol=2e-3)
+            for m in params:
+                for n in params[m]:
+                    summed[m][n] += params[m][n].grad
+        R.chief_step(pref, summed, adam, step=step + 1)
+    names = [(m, n) for m in P.MODULE_ORDER for n in P.module_param_names(m)]
+    post = P.unpack_state(res[0]["params"])
+    a = torch.cat([post[m][n].flatten() for m, n in names]).double()
+    b = torch.cat([pref[m][n].flatten() for m, n in names]).double()
+    a0 = torch.cat([sd[m][n].flatten() for m, n in names]).double()
+    assert ((a - b).norm() / b.norm()).item() < 2e-3
+    d_rel = (((a - a0) - (b - a0)).norm() / (b - a0).norm()).item()
+    print(f"two ranks x two workers, two steps ({backend}, overlap={overlap}): delta-theta rel-L2 {d_rel:.4f}")
+    assert d_rel < 0.25
+    # the reduced gradient of step 2 is the sum over all four workers
+    g = P.unpack_state(res[0]["grads"])
+    ga = torch.cat([g[m][n].flatten() for m, n in names]).double()
+    gb = torch.cat([summed[m][n].flatten() for m, n in names]).double()
+    assert ((ga - gb).norm() / gb.norm()).item() < 2e-2

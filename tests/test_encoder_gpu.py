@@ -145,3 +145,128 @@ def test_two_encoders_on_two_streams_match_sequential(encoders):
                 e.forward_u8(rgb[s:s + 32], route[s:s + 32], meas[s:s + 32], out[s:s + 32])
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------ benchmarked shapes
+def _u8_frames(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.randint(0, 256, (n, 144, 256, 3), dtype=torch.uint8, generator=g)
+    route = (torch.rand(n, 256, 144, generator=g) < 0.1).to(torch.uint8).mul(255)
+    meas = torch.rand(n, 3, dtype=torch.float64, generator=g)
+    return rgb, route, meas
+
+
+def _oracle_features(rgb, route, meas, sd, rows):
+    """agent_latent_feature (agent.py:97-112) for the selected frame indices, 8 frames per call like the reference."""
+    out = []
+    with torch.no_grad():
+        for s in range(0, len(rows), 8):
+            ix = rows[s:s + 8]
+            out.append(R.agent_latent_feature(rgb[ix].numpy(), route[ix].numpy().copy(), meas[ix].numpy(), sd))
+    return torch.cat(out)
+
+
+@pytest.fixture(scope="module")
+def bench_encoders():
+    """bench.py's configuration: two encoder instances with max_batch = 640."""
+    from cadre_b200.encoder import Encoder
+    sd = R.danet_fixture_state(0)
+    return [Encoder(sd, "cuda:0", max_batch=640) for _ in range(2)]
+
+
+@pytest.mark.parametrize("B", [640, 1024])
+def test_bench_batch_sizes_match_oracle(bench_encoders, B):
+    """BASELINE config 2's top batch sizes on the encoder bench.py uses (max_batch = 640; 1024 = chunks of 640 + 384):
+    EVERY frame against the CPU oracle."""
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    rgb, route, meas = _u8_frames(B, seed=B)
+    feat = bench_encoders[0].forward_u8(rgb.cuda(), route.cuda(), meas.cuda()).cpu()
+    ref = _oracle_features(rgb, route, meas, R.danet_fixture_state(0), list(range(B)))
+    assert feat.shape == (B, 530) and torch.isfinite(feat).all()
+    assert torch.equal(feat[:, 512:], ref[:, 512:])
+    assert rel_l2(feat[:, :512], ref[:, :512]) < REL_FEATURE
+    per_frame = ((feat[:, :512] - ref[:, :512]).double().norm(dim=1) / ref[:, :512].double().norm(dim=1))
+    assert per_frame.max().item() < 2 * REL_FEATURE, per_frame.max().item()     # no single frame is off either
+
+
+def test_bench_two_stream_ramp_schedule(bench_encoders):
+    """bench.py's e2e schedule: chunks of 128, 512, 640, 640 frames alternating between two encoder instances on two
+    streams, each writing its rows of one [N,530] feature matrix through ld_out. Bit-identical to one encoder on one
+    stream, and equal to the oracle on a sample of frames from every chunk."""
+    sizes = [128, 512, 640, 640]
+    n = sum(sizes)
+    rgb, route, meas = _u8_frames(n, seed=77)
+    d = [t.cuda() for t in (rgb, route, meas)]
+    one = bench_encoders[0].forward_u8(*d).clone()
+    torch.cuda.synchronize()
+    out = torch.zeros(n, 530, device="cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    s0 = 0
+    for i, m in enumerate(sizes):
+        with torch.cuda.stream(streams[i % 2]):
+            bench_encoders[i % 2].forward_u8(d[0][s0:s0 + m], d[1][s0:s0 + m], d[2][s0:s0 + m], out[s0:s0 + m])
+        s0 += m
+    torch.cuda.synchronize()
+    assert torch.equal(out, one)
+    rows = [0, 5, 127, 128, 300, 639, 640, 1000, 1279, 1280, 1500, 1919, 64, 777, 1281, 1800]
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    ref = _oracle_features(rgb, route, meas, R.danet_fixture_state(0), rows)
+    assert rel_l2(out[rows, :512].cpu(), ref[:, :512]) < REL_FEATURE
+
+
+def test_features_written_through_ld_out_into_rollout_obs(bench_encoders):
+    """The learner writes encoder features straight into RolloutStorage.obs (row stride 530, arbitrary base)."""
+    rgb, route, meas = _u8_frames(24, seed=5)
+    d = [t.cuda() for t in (rgb, route, meas)]
+    obs = torch.full((4, 8, 530), -7.0, device="cuda")       # [steps, seq, 530] like storage.obs[t0:t0+4]
+    plain = bench_encoders[0].forward_u8(*d)
+    bench_encoders[0].forward_u8(*d, out=obs[1:4].view(24, 530))
+    assert torch.equal(obs[1:4].view(24, 530), plain) and float(obs[0].min()) == -7.0
+
+
+# ------------------------------------------------------------------------------------------------ dynamic range
+@pytest.mark.parametrize("tag", ["xavier", "wide"])
+def test_fp16_dynamic_range_fixtures(tag):
+    """SURVEY §8c.3 fixtures beyond base / peaky: (xavier) the reference trainer's initialisation
+    (experiments_builder.py:163-188): activations two orders of magnitude below the base fixture's; (wide) calibrated
+    BatchNorm statistics spanning running_var 1e-5 .. 1e+5 with gammas up to 5. Latent within 1e-2 and no 16-bit store
+    anywhere near saturation."""
+    from cadre_b200.encoder import Encoder
+    torch.set_num_threads(8)
+    sd = R.danet_fixture_state(0, init="xavier") if tag == "xavier" else R.danet_wide_fixture_state(0)
+    if tag == "wide":
+        v = torch.cat([t.flatten() for k, t in sd.items() if k.endswith("running_var")])
+        assert v.min().item() < 1e-3 and v.max().item() > 1e3
+    enc = Encoder(sd, "cuda:0", max_batch=16)
+    x = torch.from_numpy(np.random.RandomState(17).rand(12, 4, 144, 256).astype(np.float32))
+    lat = enc.forward_f32(x.cuda()).cpu()
+    with torch.no_grad():
+        ref = R.encoder_latent(x, sd)
+    assert torch.isfinite(lat).all()
+    assert rel_l2(lat, ref) < REL_FEATURE, rel_l2(lat, ref)
+    assert enc.activation_absmax(12) < 0.25 * 65504.0
+
+
+def test_intertask_stage_matches_oracle(encoders):
+    """a7 (intertask_att.py:39-80, 123-176) as its own stage: the six Linear(20480,512)+LeakyReLU hidden vectors that
+    the library computes as ONE folded [5120 -> 3072] GEMM (conv8 and the two 1x1 task convs folded in) against the
+    oracle's unfolded conv8 -> visual_conv / bc_conv -> flatten -> Linear chain."""
+    import torch.nn.functional as F
+    enc = encoders["base"]
+    sd = R.danet_fixture_state(0)
+    B = 6
+    x = torch.from_numpy(np.random.RandomState(23).rand(B, 4, 144, 256).astype(np.float32))
+    lat = enc.forward_f32(x.cuda()).cpu()
+    with torch.no_grad():
+        da = R.da_head(R.backbone(x, sd), sd)
+        hid = []
+        for task, conv in (("visual", "visual_conv"), ("bc", "bc_conv")):
+            t = F.conv2d(da, sd[conv + ".weight"], sd[conv + ".bias"]).reshape(B, -1)
+            for role in ("query", "key", "value"):
+                p = f"inter_task_att.{task}_{role}_layer"
+                hid.append(F.leaky_relu(F.linear(t, sd[p + ".1.weight"], sd[p + ".1.bias"]), 0.01))
+        hid = torch.cat(hid, 1)                                           # [B, 6*512] in the library's order
+        ref = R.encoder_latent(x, sd)
+    got = enc.debug_buffer(5, B).view(B, 3072).float().cpu()
+    assert rel_l2(got, hid) < 5e-3, rel_l2(got, hid)
+    assert rel_l2(lat, ref) < REL_FEATURE

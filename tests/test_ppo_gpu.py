@@ -175,15 +175,76 @@ def test_gradients_match_oracle_and_golden(two_worker_update, golden_dir):
     ref = torch.cat([u["summed"][m][n].flatten() for m, n in names])
     assert rel(got, ref) < 2e-2                                                   # all 19.4 M gradients
     per = sorted(rel(g[m][n], u["summed"][m][n]) for m, n in names)
-    assert per[len(per) // 2] < 5e-3 and per[-1] < 1e-1
+    assert per[len(per) // 2] < 5e-3 and per[-1] < 5e-2       # worst single tensor (ReLU-mask flips)
     # layout padding never receives gradient
     probe = torch.zeros(P.TOTAL)
     for m, n in names:
         P.tensor_view(probe, m, n)[0].fill_(1.0)
     assert u["grads"].cpu()[probe == 0].abs().max().item() == 0.0
-    # unused experts get exactly zero gradient (reference: masked rows contribute 0)
+    # the reference run's own numbers (golden): per-module norms of the summed gradient (chief.py:19, clip_grad_norm_)
     gold = np.load(os.path.join(golden_dir, "update.npz"))
-    assert gold["w0_grad_stats"].shape[0] == 128
+    got_norms = [torch.sqrt(sum((g[m][n].double() ** 2).sum() for n in P.module_param_names(m))).item()
+                 for m in P.MODULE_ORDER]
+    np.testing.assert_allclose(got_norms, gold["module_grad_norms"], rtol=1e-2)
+
+
+def test_worker0_gradient_slices_match_reference_golden(two_worker_update, golden_dir):
+    """update.npz `w0_grad_slices` / `w0_grad_stats`: worker 0's own gradient from the reference run (first 32 elements,
+    [sum, norm, absmax] of all 128 tensors), against a one-worker CUDA update on the same minibatch."""
+    from cadre_b200 import ppo
+    u = two_worker_update
+    P = u["ppo_params"]
+    gold = np.load(os.path.join(golden_dir, "update.npz"))
+    c = u["cpu"][0]
+    storages = [(_dev(c[0][0]), _dev(c[0][1]))]
+    advs = [(c[1][0].to(DEV).contiguous(), c[1][1].to(DEV).contiguous())]
+    idx = np.array([[c[2][0], c[2][1]]], dtype=np.int32)
+    grads = torch.zeros_like(u["flat"])
+    ppo.PpoEngine(1, 100, device=DEV).update(storages, advs, idx, u["flat"], grads)
+    g = P.unpack_state(grads.cpu())
+    k = 0
+    num = den = 0.0
+    for m in P.MODULE_ORDER:
+        for n in P.module_param_names(m):
+            t = g[m][n].flatten().double()
+            ref_sl = torch.from_numpy(gold["w0_grad_slices"][k][:min(32, t.numel())]).double()
+            num += ((t[:len(ref_sl)] - ref_sl) ** 2).sum().item()
+            den += (ref_sl ** 2).sum().item()
+            ref_sum, ref_norm, ref_max = gold["w0_grad_stats"][k]
+            assert abs(t.norm().item() - ref_norm) <= 2e-2 * ref_norm + 1e-9, (m, n)
+            assert abs(t.abs().max().item() - ref_max) <= 5e-2 * ref_max + 1e-9, (m, n)
+            k += 1
+    assert k == 128 and (num / den) ** 0.5 < 2e-2
+
+
+def test_unrouted_experts_get_exactly_zero_gradient():
+    """agent.py:170-182 masks every row by its command, so an expert no row is routed to receives a zero gradient
+    (autograd of `x * False`). Here such experts are never visited; every element of their 8 x 16 tensors must be
+    EXACTLY 0.0 while the visited experts' gradients are not."""
+    from cadre_b200 import ppo, ppo_params as P
+    rs = np.random.RandomState(9)
+    sts = []
+    for a, cmds in ((R.STEER_ACTIONS, (0, 1)), (R.THROTTLE_ACTIONS, (3,))):
+        st = R.synthetic_storage(rs, T=64, actions=a)
+        st["command"] = torch.from_numpy(rs.choice(cmds, size=(65, 1)).astype(np.int32))
+        st["returns"] = torch.from_numpy(rs.randn(65, 1).astype(np.float32))
+        sts.append(st)
+    adv = [torch.from_numpy(rs.randn(64, 1).astype(np.float32)) for _ in range(2)]
+    idx = np.array([[list(rs.permutation(64)[:32]), list(rs.permutation(64)[:32])]], dtype=np.int32)
+    flat = P.pack_state(R.ppo_fixture_state(0), DEV)
+    grads = torch.full_like(flat, 123.0)                                   # stale values must be overwritten
+    ppo.PpoEngine(1, 32, device=DEV).update([(_dev(sts[0]), _dev(sts[1]))],
+                                            [(adv[0].to(DEV), adv[1].to(DEV))], idx, flat, grads)
+    g = P.unpack_state(grads.cpu())
+    visited = {"steer": (0, 1), "throttle": (3,)}
+    for head in ("steer", "throttle"):
+        for c in range(4):
+            for m in (f"{head}_lstm_{c}", f"{head}_ppo_{c}"):
+                tot = sum(t.abs().sum().item() for t in g[m].values())
+                if c in visited[head]:
+                    assert tot > 0.0, m
+                else:
+                    assert all(t.abs().max().item() == 0.0 for t in g[m].values()), m
 
 
 def test_clip_adam_matches_oracle(two_worker_update):
@@ -220,6 +281,67 @@ def test_clip_adam_matches_oracle(two_worker_update):
     assert rel(a, b) < 1e-6
 
 
+def _delta_agreement(d_got, d_ref):
+    """How well two first-Adam-step updates agree. The first step moves every weight by ~ lr * sign(g) (bias-corrected
+    m / sqrt(v) = g / |g|), so the relative L2 of the DELTAS is sqrt(4 * fraction of sign flips) - a far sharper
+    measure than the relative L2 of theta (|delta| ~ 3e-4 on |theta| ~ 4e-2 would let a no-op Adam pass)."""
+    d_got, d_ref = d_got.double().flatten().cpu(), d_ref.double().flatten().cpu()
+    rel_d = ((d_got - d_ref).norm() / d_ref.norm()).item()
+    moved = d_ref.abs() > 0
+    flips = ((torch.sign(d_got) != torch.sign(d_ref)) & moved).double().mean().item()
+    return rel_d, flips
+
+
+# Stated tolerance for post-step parameters (north_star: "post-step parameters within a stated tf32 tolerance"):
+#   relative L2 of delta-theta <= DELTA_REL, i.e. at most DELTA_REL^2 / 4 of the 19.4 M weights step the other way
+#   (those are weights whose gradient is within TF32 noise of zero).
+DELTA_REL = 0.25
+
+
+def test_delta_theta_matches_oracle(two_worker_update):
+    """CUDA gradients -> CUDA clip + Adam against the oracle's chief step on the oracle's gradients: the UPDATE itself
+    (delta theta), not theta."""
+    u = two_worker_update
+    P = u["ppo_params"]
+    flat = u["flat"].clone()
+    m1, m2 = torch.zeros_like(flat), torch.zeros_like(flat)
+    u["eng"].adam_step(flat, u["grads"], m1, m2, step=1)
+    sd = u["sd"]
+    adam = {m: {n: {"exp_avg": torch.zeros_like(t), "exp_avg_sq": torch.zeros_like(t)} for n, t in d.items()}
+            for m, d in sd.items()}
+    pref = {m: {n: t.detach().clone() for n, t in d.items()} for m, d in sd.items()}
+    R.chief_step(pref, u["summed"], adam, step=1)
+    post = P.unpack_state(flat.cpu())
+    names = [(m, n) for m in P.MODULE_ORDER for n in P.module_param_names(m)]
+    d_got = torch.cat([(post[m][n] - sd[m][n]).flatten() for m, n in names])
+    d_ref = torch.cat([(pref[m][n] - sd[m][n]).flatten() for m, n in names])
+    rel_d, flips = _delta_agreement(d_got, d_ref)
+    print(f"delta-theta rel-L2 {rel_d:.4f}, sign flips {flips:.5f}")
+    assert d_got.abs().max().item() <= 3e-4 * 1.001 and d_got.abs().max().item() > 2.9e-4   # Adam really stepped by lr
+    assert rel_d < DELTA_REL, (rel_d, flips)
+
+
+def test_post_step_statistics_match_reference_golden(two_worker_update, golden_dir):
+    """update.npz `post_delta_stats` ([sum, norm, absmax] of delta theta per tensor, from the reference's own
+    optimizer.step()) against the CUDA step."""
+    u = two_worker_update
+    P = u["ppo_params"]
+    gold = np.load(os.path.join(golden_dir, "update.npz"))
+    flat = u["flat"].clone()
+    m1, m2 = torch.zeros_like(flat), torch.zeros_like(flat)
+    u["eng"].adam_step(flat, u["grads"], m1, m2, step=1)
+    post = P.unpack_state(flat.cpu())
+    k = 0
+    for m in P.MODULE_ORDER:
+        for n in P.module_param_names(m):
+            d = (post[m][n] - u["sd"][m][n]).double().flatten()
+            _, ref_norm, ref_max = gold["post_delta_stats"][k]
+            assert abs(d.norm().item() - ref_norm) <= 2e-2 * ref_norm + 1e-12, (m, n, d.norm().item(), ref_norm)
+            assert abs(d.abs().max().item() - ref_max) <= 1e-2 * ref_max + 1e-12, (m, n)
+            k += 1
+    assert k == 128
+
+
 def test_end_to_end_step_parameters(two_worker_update, golden_dir):
     """CUDA gradients -> CUDA clip + Adam vs the reference's post-step parameters (golden)."""
     u = two_worker_update
@@ -241,3 +363,107 @@ def test_end_to_end_step_parameters(two_worker_update, golden_dir):
             assert (sl - ref).abs().max().item() <= 2 * 3e-4 + 1e-6
             k += 1
     assert (num / den) ** 0.5 < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ declared configs
+def _make_worker(w, T, seed0):
+    rs = np.random.RandomState(seed0 + w)
+    pair = [R.synthetic_storage(rs, T=T, actions=a) for a in (R.STEER_ACTIONS, R.THROTTLE_ACTIONS)]
+    if w % 3 == 1:                                           # non-zero stored recurrent state in some workers
+        for st in pair:
+            st["hn"] = torch.from_numpy(rs.randn(T + 1, 530).astype(np.float32) * 0.3)
+            st["cn"] = torch.from_numpy(rs.randn(T + 1, 530).astype(np.float32) * 0.3)
+    advs = []
+    for st, nv in zip(pair, (0.1, -0.2)):
+        st["returns"], st["value_preds"] = R.compute_returns(st["rewards"], st["value_preds"], st["masks"],
+                                                             torch.tensor([[nv]]))
+        advs.append(R.normalized_advantages(st["returns"], st["value_preds"]))
+    return pair, advs
+
+
+def _run_config(W, mb, T, seed0):
+    """One update step of W workers (storages of T steps, minibatches of mb rows drawn like storage.py:93-97) on the
+    GPU and in the oracle (per-worker update_policy, gradients summed like Shared_grad_buffers.add_gradient, chief
+    step). Returns losses, gradient and delta-theta agreement."""
+    from cadre_b200 import ppo, ppo_params as P
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = R.ppo_fixture_state(0)
+    cpu = [_make_worker(w, T, seed0) for w in range(W)]
+    idx = np.empty((W, 2, mb), dtype=np.int32)
+    for w in range(W):
+        torch.manual_seed(seed0 + 1000 + w)
+        idx[w, 0] = R.minibatch_indices(T, T // mb)[0]
+        idx[w, 1] = R.minibatch_indices(T, T // mb)[1 % (T // mb)]
+    storages = [(_dev(c[0][0]), _dev(c[0][1])) for c in cpu]
+    advs = [(c[1][0].to(DEV).contiguous(), c[1][1].to(DEV).contiguous()) for c in cpu]
+    flat = P.pack_state(sd, DEV)
+    grads = torch.zeros_like(flat)
+    eng = ppo.PpoEngine(W, mb, device=DEV)
+    losses = eng.update(storages, advs, idx, flat, grads).cpu()
+    post_flat = flat.clone()
+    m1, m2 = torch.zeros_like(flat), torch.zeros_like(flat)
+    eng.adam_step(post_flat, grads, m1, m2, step=1)
+    # oracle
+    params = {m: {n: t.clone().requires_grad_(True) for n, t in d.items()} for m, d in sd.items()}
+    summed = {m: {n: torch.zeros_like(t) for n, t in d.items()} for m, d in sd.items()}
+    for w in range(W):
+        samples = [R.gather_minibatch(cpu[w][0][h], cpu[w][1][h], list(idx[w, h])) for h in range(2)]
+        ref_l = R.update_policy(samples[0], samples[1], params)
+        L = losses[w].sum(0)
+        got = np.array([0.1 * L[0].item(), L[1].item(), 0.01 * L[2].item()])
+        np.testing.assert_allclose(got, np.array(ref_l), rtol=1e-3, err_msg=f"worker {w}")
+        for m in params:
+            for n in params[m]:
+                summed[m][n] += params[m][n].grad
+    adam = {m: {n: {"exp_avg": torch.zeros_like(t), "exp_avg_sq": torch.zeros_like(t)} for n, t in d.items()}
+            for m, d in sd.items()}
+    pref = {m: {n: t.detach().clone() for n, t in d.items()} for m, d in sd.items()}
+    R.chief_step(pref, summed, adam, step=1)
+    names = [(m, n) for m in P.MODULE_ORDER for n in P.module_param_names(m)]
+    g = P.unpack_state(grads.cpu())
+    post = P.unpack_state(post_flat.cpu())
+    cat = lambda d: torch.cat([d[m][n].flatten() for m, n in names])   # noqa: E731
+    g_rel = rel(cat(g), cat(summed))
+    per = sorted(rel(g[m][n], summed[m][n]) for m, n in names)
+    th_rel = rel(cat(post), cat(pref))
+    d_rel, flips = _delta_agreement(cat(post) - cat(sd), cat(pref) - cat(sd))
+    norms = eng.module_norms()
+    for m in sd:
+        ref_n = torch.sqrt(sum((summed[m][n].double() ** 2).sum() for n in sd[m])).item()
+        assert norms[m] == pytest.approx(ref_n, rel=2e-2), m
+    print(f"W={W} mb={mb} T={T}: grad rel-L2 {g_rel:.4e} (median tensor {per[len(per) // 2]:.2e}, worst {per[-1]:.2e}), "
+          f"theta rel-L2 {th_rel:.2e}, delta-theta rel-L2 {d_rel:.4f} (sign flips {flips:.5f})")
+    return g_rel, per, th_rel, d_rel
+
+
+def test_cfg3_update_step_four_workers():
+    """BASELINE config 3 (the shape bench.py times): 4 workers x minibatches of 100 rows x 2 heads from T = 200."""
+    g_rel, per, th_rel, d_rel = _run_config(W=4, mb=100, T=200, seed0=300)
+    assert g_rel < 2e-2 and per[len(per) // 2] < 5e-3 and per[-1] < 5e-2
+    assert th_rel < 2e-3 and d_rel < DELTA_REL
+
+
+def test_cfg5_update_step_eight_workers_T800():
+    """BASELINE config 5 per GPU: 8 environments x minibatches of 400 rows x 2 heads from T = 800 (3200 rows per head:
+    several 128-row tiles per expert, the tensor-core-bound regime of the TF32 GEMMs)."""
+    g_rel, per, th_rel, d_rel = _run_config(W=8, mb=400, T=800, seed0=700)
+    assert g_rel < 2e-2 and per[len(per) // 2] < 5e-3 and per[-1] < 5e-2
+    assert th_rel < 2e-3 and d_rel < DELTA_REL
+
+
+def test_cfg5_gae_128_sequences_T800():
+    """cfg 5's GAE launch: 128 sequences (64 envs x 2 heads) x 800 steps in one call, every sequence vs the oracle."""
+    from cadre_b200 import ppo
+    E, T = 128, 800
+    gen = torch.Generator().manual_seed(5)
+    r = torch.rand(E, T + 1, generator=gen)
+    v = torch.randn(E, T + 1, generator=gen)
+    m = (torch.rand(E, T + 1, generator=gen) > 0.02).float()
+    nv = torch.randn(E, generator=gen)
+    vd = v.to(DEV).clone()
+    ret, adv = torch.zeros(E, T + 1, device=DEV), torch.zeros(E, T, device=DEV)
+    ppo.gae(r.to(DEV), vd, m.to(DEV), nv.to(DEV), ret, adv)
+    for e in range(E):
+        ref_ret, vp = R.compute_returns(r[e].view(-1, 1), v[e].view(-1, 1).clone(), m[e].view(-1, 1), nv[e].view(1, 1))
+        np.testing.assert_allclose(ret[e, :T].cpu().numpy(), ref_ret[:T, 0].numpy(), rtol=1e-5, atol=1e-5)
+        assert rel(adv[e], R.normalized_advantages(ref_ret, vp)[:, 0]) < 2e-5

@@ -297,6 +297,42 @@ void launch_clip_adam(const OptTables& t, float* params, const float* grads, flo
   }                                  \
   return 0;
 
+namespace cadre {
+// ---------------------------------------------------------------------------------------------------------
+// Sliding-window assembly of rollout observations. The env wrapper hands every tick the last `seq` frames
+// (env_wrapper.py:900-914) and train.py:69-72 stores that [seq, F] feature window as obs[t] of BOTH heads'
+// storages. The frozen encoder maps frames independently, so with the features U[w][k] of the T + seq - 1 UNIQUE
+// frames of a worker's rollout, obs[w][head][t][j] = U[w][t + j]: a pure gather. One warp copies one feature row
+// (float2, 265 per row) into its up to `seq` x 2 destinations: U is read once, obs written once.
+__global__ void __launch_bounds__(256) window_scatter_kernel(const float* __restrict__ U, float* __restrict__ obs,
+                                                             int W, int T, int seq, int F, long long obs_head_stride,
+                                                             long long obs_step_stride) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = T + seq - 1;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;   // (worker, unique frame k)
+  if (row >= static_cast<long long>(W) * K) return;
+  const int w = static_cast<int>(row / K), k = static_cast<int>(row - static_cast<long long>(w) * K);
+  const float2* src = reinterpret_cast<const float2*>(U + row * F);
+  const int F2 = F >> 1;
+  for (int c = lane; c < F2; c += 32) {
+    const float2 v = src[c];
+    // frame k is element j of the window of step t = k - j
+    for (int j = 0; j < seq; ++j) {
+      const int t = k - j;
+      if (t < 0 || t >= T) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* dst = obs + (static_cast<long long>(w) * 2 + h) * obs_head_stride + t * obs_step_stride +
+                     static_cast<long long>(j) * F;
+        reinterpret_cast<float2*>(dst)[c] = v;
+      }
+    }
+  }
+}
+}  // namespace cadre
+
 extern "C" {
 
 int cadre_gae(const float* rewards, float* values, const float* masks, const float* next_value, float* returns,
@@ -315,6 +351,20 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   if (smem > 48 * 1024) cadre::ensure_dynamic_smem(kern, smem, configured[which]);
   cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
                   rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  CADRE_API_END
+}
+
+int cadre_window_scatter(const float* unique_feats, float* obs, int workers, int num_steps, int seq_length,
+                         int feature_dims, int64_t obs_head_stride, int64_t obs_step_stride, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(unique_feats && obs && workers > 0 && num_steps > 0 && seq_length > 0, "window_scatter arguments");
+  CADRE_REQUIRE(feature_dims % 2 == 0 && obs_step_stride % 2 == 0 && obs_head_stride % 2 == 0,
+                "window_scatter: feature_dims and strides must be even (float2 copies)");
+  const long long rows = static_cast<long long>(workers) * (num_steps + seq_length - 1);
+  cadre::launch_k(cadre::window_scatter_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0,
+                  static_cast<cudaStream_t>(stream), unique_feats, obs, workers, num_steps, seq_length, feature_dims,
+                  static_cast<long long>(obs_head_stride), static_cast<long long>(obs_step_stride));
   CADRE_CUDA_CHECK(cudaGetLastError());
   CADRE_API_END
 }

@@ -134,6 +134,15 @@ int cadre_encoder_launches(void* handle);
 int cadre_gae(const float* rewards, float* values, const float* masks, const float* next_value, float* returns,
               float* adv, int E, int T, float gamma, float tau, int normalize, void* stream);
 
+/* Sliding-window assembly of rollout observations (env_wrapper.py:900-914 stacks the last `seq_length` frames per
+ * tick; train.py:69-72 inserts that window into the steer AND the throttle storage). unique_feats: fp32
+ * [workers][num_steps + seq_length - 1][feature_dims] = encoder features of every DISTINCT frame of each worker's
+ * rollout, oldest first. Writes obs[(w*2 + head)*obs_head_stride + t*obs_step_stride + j*feature_dims + :] =
+ * unique_feats[w][t + j][:] for head 0..1, t < num_steps, j < seq_length (strides in floats; RolloutStorage.obs of
+ * the batched pool: head stride (T+1)*seq*F, step stride seq*F). */
+int cadre_window_scatter(const float* unique_feats, float* obs, int workers, int num_steps, int seq_length,
+                         int feature_dims, int64_t obs_head_stride, int64_t obs_step_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * PPO update = CadreAgent.update_policy (ppo_agent/agent.py:166-237) for `workers` logical workers at once
  * (forward + hand-written backward; gradients are the SUM over workers, like Shared_grad_buffers.add_gradient,

@@ -110,7 +110,7 @@ def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap):
     assert ((a - b).norm() / b.norm()).item() < 2e-3
     d_rel = (((a - a0) - (b - a0)).norm() / (b - a0).norm()).item()
     print(f"two ranks x two workers, two steps ({backend}, overlap={overlap}): delta-theta rel-L2 {d_rel:.4f}")
-    assert d_rel < 0.25
+    assert d_rel < 0.2          # same stated tolerance as tests/test_ppo_gpu.py (measured: 0.097)
     # the reduced gradient of step 2 is the sum over all four workers
     g = P.unpack_state(res[0]["grads"])
     ga = torch.cat([g[m][n].flatten() for m, n in names]).double()

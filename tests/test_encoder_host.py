@@ -59,3 +59,13 @@ def test_prepare_weights_matches_oracle_math():
                 k += 1
     assert pw["fc1_w"].shape == (3072, 5120) and pw["fc2_w"].shape == (6, 256, 512)
     assert pw["head5_w"].shape == (256, 4608) and pw["pam_wqk"].shape == (32, 128)
+
+
+def test_ingest_chunk_schedule():
+    from cadre_b200.ingest import chunk_schedule
+    assert chunk_schedule(6400, 640) == [128, 512] + [640] * 9           # bench.py's e2e ramp (round 1: 128, 512, 9 x 640)
+    assert chunk_schedule(828, 640) == [128, 512, 188]                   # cfg 3, distinct frames only: 4 x 207
+    assert chunk_schedule(300, 640) == [300] and chunk_schedule(640, 640) == [640]
+    assert chunk_schedule(6400, 640, ramp=()) == [640] * 10
+    for n in (1, 127, 641, 5000):
+        assert sum(chunk_schedule(n, 640)) == n and max(chunk_schedule(n, 640)) <= 640

@@ -295,7 +295,7 @@ def _delta_agreement(d_got, d_ref):
 # Stated tolerance for post-step parameters (north_star: "post-step parameters within a stated tf32 tolerance"):
 #   relative L2 of delta-theta <= DELTA_REL, i.e. at most DELTA_REL^2 / 4 of the 19.4 M weights step the other way
 #   (those are weights whose gradient is within TF32 noise of zero).
-DELTA_REL = 0.25
+DELTA_REL = 0.2     # measured on B200: 0.096 (2 workers x 100 rows), 0.127 (cfg 3), 0.161 (cfg 5: 0.7 % sign flips)
 
 
 def test_delta_theta_matches_oracle(two_worker_update):

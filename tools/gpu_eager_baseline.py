@@ -1,11 +1,16 @@
 """GPU-side bar: the reference graph (oracle/restate.py, plain PyTorch modules' formulas) run in
-torch eager on the B200 -- cuDNN / cuBLAS library path, fp32 with torch's default TF32 convolution setting --
-next to the same workload through cadre_b200. Not product code; writes gpurun_out/r1_eager_baseline.json."""
+torch eager on the B200 -- cuDNN / cuBLAS library path: fp32 with torch's default TF32 convolution setting, bf16
+autocast, and bf16 autocast on channels_last tensors -- next to the same workload through cadre_b200.
+A baseline tool, not product code. Default: a batch sweep written to gpurun_out/r2_eager_baseline.json;
+`--json-line` (used by bench.py in a SUBPROCESS, so that no library kernel is loaded into the measured process): batch
+640 + the PPO update step only, one JSON line on stdout."""
 import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import restate as R
-from cadre_b200.encoder import Encoder
+JSON_LINE = "--json-line" in sys.argv
+if not JSON_LINE:
+    from cadre_b200.encoder import Encoder
 dev = torch.device("cuda:0")
 out = {"torch": torch.__version__, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32,
        "matmul_allow_tf32": torch.backends.cuda.matmul.allow_tf32}
@@ -23,23 +28,31 @@ def timed(fn, iters, warm=3):
 
 sd_cpu = R.danet_fixture_state(0)
 sd = {k: v.to(dev) for k, v in sd_cpu.items()}
-enc = Encoder(sd_cpu, "cuda:0", max_batch=640)
+sd_cl = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+enc = None if JSON_LINE else Encoder(sd_cpu, "cuda:0", max_batch=640)
 rows = []
-for B in (8, 64, 256, 640):
+for B in ((640,) if JSON_LINE else (8, 64, 256, 640)):
     x = torch.rand(B, 4, 144, 256, device=dev)
+    x_cl = x.contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
         ms_ref = timed(lambda: R.encoder_latent(x, sd), 5)
         torch.backends.cudnn.benchmark = True
         ms_ref_b = timed(lambda: R.encoder_latent(x, sd), 5, warm=5)
-        torch.backends.cudnn.benchmark = False
         with torch.autocast("cuda", dtype=torch.bfloat16):
             ms_ref_bf16 = timed(lambda: R.encoder_latent(x, sd), 5, warm=5)
-    o = torch.empty(B, 512, device=dev)
-    ms_new = timed(lambda: enc.forward_f32(x, o), 10)
-    rows.append({"batch": B, "eager_fp32_ms": round(ms_ref, 3), "eager_fp32_cudnn_benchmark_ms": round(ms_ref_b, 3),
-                 "eager_autocast_bf16_ms": round(ms_ref_bf16, 3), "cadre_b200_ms": round(ms_new, 3),
-                 "speedup_vs_best_eager": round(min(ms_ref, ms_ref_b, ms_ref_bf16) / ms_new, 2)})
-    print(rows[-1], flush=True)
+            ms_ref_bf16_cl = timed(lambda: R.encoder_latent(x_cl, sd_cl), 5, warm=5)
+        torch.backends.cudnn.benchmark = False
+    row = {"batch": B, "eager_fp32_ms": round(ms_ref, 3), "eager_fp32_cudnn_benchmark_ms": round(ms_ref_b, 3),
+           "eager_autocast_bf16_ms": round(ms_ref_bf16, 3),
+           "eager_autocast_bf16_channels_last_ms": round(ms_ref_bf16_cl, 3)}
+    if enc is not None:
+        o = torch.empty(B, 512, device=dev)
+        ms_new = timed(lambda: enc.forward_f32(x, o), 10)
+        row["cadre_b200_ms"] = round(ms_new, 3)
+        row["speedup_vs_best_eager"] = round(min(ms_ref, ms_ref_b, ms_ref_bf16, ms_ref_bf16_cl) / ms_new, 2)
+    rows.append(row)
+    if not JSON_LINE:
+        print(rows[-1], flush=True)
 out["encoder"] = rows
 del enc
 
@@ -82,8 +95,20 @@ def ref_update():
 try:
     ms = timed(ref_update, 5, warm=2)
     out["ppo_update_eager_ms"] = round(ms, 3)
-    print("eager PPO update step (4 workers, dense 4-command formulation)", ms, "ms", flush=True)
+    if not JSON_LINE:
+        print("eager PPO update step (4 workers, dense 4-command formulation)", ms, "ms", flush=True)
 except Exception as e:  # the restatement is CPU-first; report rather than fail
     out["ppo_update_eager_error"] = repr(e)[:300]
-    print("eager PPO update failed:", repr(e)[:300], flush=True)
-json.dump(out, open("gpurun_out/r1_eager_baseline.json", "w"), indent=1)
+    if not JSON_LINE:
+        print("eager PPO update failed:", repr(e)[:300], flush=True)
+if JSON_LINE:
+    r = rows[0]
+    print(json.dumps({"what": "reference graph in torch eager (cuDNN / cuBLAS) on the same GPU, separate process",
+                      "torch": out["torch"], "encoder_b640_fp32_ms": r["eager_fp32_ms"],
+                      "encoder_b640_bf16_ms": r["eager_autocast_bf16_ms"],
+                      "encoder_b640_bf16_channels_last_ms": r["eager_autocast_bf16_channels_last_ms"],
+                      "ppo_update_step_fp32_ms": out.get("ppo_update_eager_ms"),
+                      "ppo_update_error": out.get("ppo_update_eager_error")}))
+else:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/r2_eager_baseline.json", "w"), indent=1)

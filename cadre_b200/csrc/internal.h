@@ -117,6 +117,10 @@ struct GemmArgs {
   long long ldh = 0, h_bs = 0;
 };
 void launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// cuTensorMapEncodeTiled for an fp16 tensor, 128B swizzle, zero fill out of bounds; dims / box innermost first,
+// strides_bytes has rank-1 entries (dimension 0 is contiguous)
+void make_tensor_map_f16(CUtensorMap* m, int rank, const void* base, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);
 
 // Implicit-GEMM convolution over NHWC bf16 activations; weights [Cout][KH][KW][Cin] bf16 (BN folded).
 struct ConvArgs {

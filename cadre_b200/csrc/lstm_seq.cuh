@@ -1,0 +1,518 @@
+// Persistent LSTM recurrence kernels of the PPO update (ppo_agent/models.py:139-152: eight sequential nn.LSTMCell
+// steps per row; ppo_agent/agent.py:170-182 evaluates them for every command expert).
+//
+// The recurrent part of a step, gates += h_{t-1} W_hh^T, used to be one grid launch per step (8 forward, 7 + 8
+// backward): every launch re-read its 128 x 530 fp32 slice of W_hh from L2 and paid launch + pipeline fill. Here ONE
+// kernel per direction keeps the recurrent weights resident in shared memory for all eight steps:
+//   * grid = 8 experts x 17 slices = 136 CTAs (<= 148 SMs, one CTA per SM, all co-resident);
+//   * forward  : CTA (e, j) owns gate columns [128 j, 128 j + 128) = hidden units [32 j, 32 j + 32): its W_hh rows as
+//                fp16 [128 x 576] (147 KB, K zero-padded 530 -> 576) in the canonical 128B-swizzled K-major layout;
+//   * backward : CTA (e, j) owns hidden units [32 j, 32 j + 32) of dh: W_hh[:, units] transposed, fp16 [32 x 2176];
+//   * per step the A operand (h_{t-1}, resp. dG_t, all rows of the expert, fp16) streams from L2 through a TMA ring,
+//     tcgen05.mma (kind::f16, fp32 accumulation in TMEM) produces the CTA's slice, the epilogue warps apply the LSTM
+//     cell (resp. its derivative) and write the next step's operand slice back to global memory;
+//   * the 17 CTAs of an expert exchange their slices through L2: release-increment of a per-expert counter after the
+//     slice is written, acquire-poll before the next step's first TMA load (generic -> async proxy fences on both
+//     sides). Different experts never wait for each other.
+// fp16 operands carry the same 11-bit significand as the TF32 path they replace; accumulation, cell state, gate
+// activations and every tensor kept for the weight-gradient GEMMs stay fp32. Backward operands are scaled by a power
+// of two (params.scale) so that small gradients stay in fp16's normal range; conversions saturate.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "internal.h"
+#include "ppo_layout.h"
+#include "ptx.cuh"
+
+namespace cadre {
+
+constexpr int LS_SLICES = 17;                 // ceil(2120 / 128) = ceil(530 / 32)
+constexpr int LS_A_STAGE = 128 * 128;         // one A k-block: 128 rows x 64 halves
+constexpr int LS_LDH16 = 544;                 // row pitch (halves) of the fp16 h exchange buffer  [E][cap][2][544]
+constexpr int LS_LDG16 = 2176;                // row pitch (halves) of the fp16 dG exchange buffer [E][cap][2][2176]
+constexpr int LS_STG_LD = 33;                 // fp32 staging pitch (conflict-free row and column access)
+constexpr unsigned LS_SPIN_LIMIT = 1u << 22;  // bounded polling: a lost hand-off raises an error flag instead of hanging
+
+// forward
+constexpr int LSF_KB = 9;                     // 64-wide k-blocks over K = 530 (padded to 576)
+constexpr int LSF_STAGES = 2;
+constexpr int LSF_W_BYTES = LSF_KB * 128 * 128;
+constexpr int LSF_STG_BYTES = 8 * 32 * LS_STG_LD * 4;
+constexpr int LSF_SMEM = LSF_W_BYTES + LSF_STAGES * LS_A_STAGE + LSF_STG_BYTES + 256 + 1024;
+constexpr int LSF_THREADS = 64 + 256;
+// backward
+constexpr int LSB_KB = 34;                    // 64-wide k-blocks over K = 2120 (padded to 2176)
+constexpr int LSB_STAGES = 3;
+constexpr int LSB_W_BYTES = LSB_KB * 32 * 128;
+constexpr int LSB_STG_BYTES = 4 * 32 * LS_STG_LD * 4;
+constexpr int LSB_SMEM = LSB_W_BYTES + LSB_STAGES * LS_A_STAGE + LSB_STG_BYTES + 256 + 1024;
+constexpr int LSB_THREADS = 64 + 128;
+constexpr int LSB_NBUF = 4;                   // TMEM accumulator buffers (32 columns each)
+
+struct LstmFwdParams {
+  CUtensorMap tmH;        // H16 as {k = 530, row = cap, buf = 2, expert = 8}, box {64, 128, 1, 1}, 128B swizzle
+  const float* params;    // flat parameter buffer (W_hh at OFF_WHH, gate-interleaved rows)
+  const float* XP9;       // [E][cap][9][G]   x_t W_ih^T + b_ih + b_hh
+  float* G9;              // [E][cap][9][G]   gate activations (i, f, g, o per unit), kept for the backward pass
+  float* C9;              // [E][cap][9][LDF] slot t holds c_{t-1}
+  float* H9;              // [E][cap][9][LDF] slot t holds h_{t-1}
+  __half* H16;            // [E][cap][2][LS_LDH16] h_t in buffer t & 1 (buffer 0 initialised with h_{-1} by the gather)
+  const int* counts;      // [E] routed rows per expert
+  unsigned* sync;         // [E] arrival counters (zero at launch), [E] = error flag
+  int cap;
+};
+
+struct LstmBwdParams {
+  CUtensorMap tmDG;       // dG16 as {k = 2176, row = cap, buf = 2, expert = 8}, box {64, 128, 1, 1}
+  const float* params;
+  const float* G9;
+  const float* C9;
+  float* dG9;             // [E][cap][9][G]  d loss / d gate pre-activations (fp32, for the weight-gradient GEMMs)
+  __half* dG16;           // [E][cap][2][LS_LDG16] scale * dG_t in buffer t & 1
+  const float* dH8;       // [E][cap][LDF]   d loss / d h_8 (from the first-layer dgrad GEMM)
+  float* dC;              // [E][cap][LDF]   running d loss / d c
+  const int* counts;
+  unsigned* sync;         // [E] counters (zero at launch), [E] = error flag
+  int cap;
+  float scale, inv_scale;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// wait until *ctr >= target (one polling lane, the warp re-converges afterwards); sets *err on timeout
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, unsigned* err, int lane) {
+  if (lane == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(ctr) < target) {
+      __nanosleep(32);
+      if (++spins > LS_SPIN_LIMIT) {
+        atomicExch(err, 1u);
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  fence_proxy_async_all();   // the slices acquired above were written through the generic proxy; TMA reads them next
+}
+
+__device__ __forceinline__ uint4 pack8_half(const float (&v)[8], float s) {
+  uint4 u;
+  __half2 h0 = __floats2half2_rn(v[0] * s, v[1] * s), h1 = __floats2half2_rn(v[2] * s, v[3] * s);
+  __half2 h2 = __floats2half2_rn(v[4] * s, v[5] * s), h3 = __floats2half2_rn(v[6] * s, v[7] * s);
+  u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+// byte offset of (row, 16-byte chunk) inside a [rows x 64 halves] 128B-swizzled K-major tile (1024-byte aligned):
+// what TMA SWIZZLE_128B writes and what umma_smem_desc(.., LBO 16, SBO 1024, layout 2) reads
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ float ls_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ls_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ unsigned short f2h_sat_bits(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+
+// =========================================================================================================== forward
+__global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __grid_constant__ LstmFwdParams p) {
+  using namespace ppo;
+  extern __shared__ uint8_t ls_raw[];
+  uint8_t* smem = ls_raw + ((1024u - (smem_u32(ls_raw) & 1023u)) & 1023u);
+  uint8_t* w_s = smem;                                   // LSF_KB tiles [128 n x 64 k]
+  uint8_t* a_s = w_s + LSF_W_BYTES;                      // LSF_STAGES tiles [128 rows x 64 k]
+  float* stg_all = reinterpret_cast<float*>(a_s + LSF_STAGES * LS_A_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_all) + LSF_STG_BYTES);
+  uint64_t* empty = full + LSF_STAGES;
+  uint64_t* acc_full = empty + LSF_STAGES;               // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.y, j = blockIdx.x;
+  const int n0 = j * 128;                                // first gate column (= W_hh row) of this CTA
+  pdl_trigger();
+
+  // ---- resident weights: W_hh[e][n0 .. n0+127][0 .. 529] -> fp16, swizzled K-major tiles. Parameters were written
+  // by an earlier, fully completed launch (the update starts with stream-ordered memsets), so this runs before
+  // pdl_wait and overlaps the predecessor's tail.
+  {
+    const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
+    for (int task = threadIdx.x; task < 128 * (LSF_KB * 8); task += LSF_THREADS) {
+      const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);   // consecutive lanes: consecutive chunks
+      const int k0 = chunk_all * 8, n = n0 + r;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (n < G && k0 < F) {
+        const float* src = W + static_cast<long long>(n) * LDF + k0;
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+        if (k0 + 4 < LDF) {
+          const float4 b = *reinterpret_cast<const float4*>(src + 4);
+          v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (k0 + i >= F) v[i] = 0.f;
+      }
+      const int kb = chunk_all >> 3, c = chunk_all & 7;
+      *reinterpret_cast<uint4*>(w_s + kb * (128 * 128) + sw128_offset(r, c)) = pack8_half(v, 1.0f);
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmH);
+    for (int s = 0; s < LSF_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);      // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();             // the weight tiles were written with generic stores; tcgen05 reads them
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();                           // counts, XP9, H16 buffer 0, the zeroed counters: all from earlier launches
+  const int count = p.counts[e];
+  const int n_mt = (count + 127) >> 7;
+  unsigned* ctr = p.sync + e;
+  unsigned* err = p.sync + E;
+
+  if (count > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer: h_{t-1}, all rows of expert e
+      uint32_t it = 0;
+      for (int t = 0; t < 8; ++t) {
+        if (t > 0) wait_counter(ctr, static_cast<unsigned>(LS_SLICES * t), err, lane);
+        for (int mt = 0; mt < n_mt; ++mt)
+          for (int kb = 0; kb < LSF_KB; ++kb, ++it) {
+            const int s = it % LSF_STAGES;
+            mbar_wait(&empty[s], ((it / LSF_STAGES) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], LS_A_STAGE);
+              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmH, &full[s], kb * 64, mt * 128, t & 1, e);
+            }
+            __syncwarp();
+          }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc(0u, 0, 0, 128, 128);   // fp16 x fp16 -> fp32, both K-major
+      uint32_t it = 0, tile = 0;
+      for (int t = 0; t < 8; ++t)
+        for (int mt = 0; mt < n_mt; ++mt, ++tile) {
+          const uint32_t buf = tile & 1;
+          mbar_wait(&acc_empty[buf], ((tile >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 128;
+          for (int kb = 0; kb < LSF_KB; ++kb, ++it) {
+            const int s = it % LSF_STAGES;
+            mbar_wait(&full[s], (it / LSF_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_s + s * LS_A_STAGE);
+            const uint32_t b_addr = smem_u32(w_s + kb * (128 * 128));
+            if (elect_one()) {
+              const int nk = kb == LSF_KB - 1 ? 2 : 4;   // k >= 544 is zero on both sides
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nk)
+                  tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32, 16, 1024, 2),
+                             umma_smem_desc(b_addr + k * 32, 16, 1024, 2), idesc, (kb | k) != 0);
+              tc_commit(&empty[s]);
+              if (kb == LSF_KB - 1) tc_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+          }
+        }
+    } else {
+      // ------------------------------------------------------------------ epilogue: LSTM cell (8 warps)
+      const int q = warp & 3, hf = (warp - 2) >> 2;      // TMEM lane quarter, column half
+      float* stg = stg_all + (warp - 2) * 32 * LS_STG_LD;
+      const int rsub = lane >> 3, ul = lane & 7;         // coalesced pass: 4 rows x 8 units per instruction
+      uint32_t tile = 0;
+      for (int t = 0; t < 8; ++t) {
+        for (int mt = 0; mt < n_mt; ++mt, ++tile) {
+          const uint32_t buf = tile & 1;
+          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);   // rows to write (zeros beyond count)
+          // x-part pre-activations and c_{t-1} of both column passes: issued BEFORE waiting for the accumulator, so
+          // that their L2 / HBM latency hides behind the hand-off wait and the MMAs of this step
+          float4 x4[2][8];
+          float cp[2][8];
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mt * 128 + q * 32 + i * 4 + rsub;
+              const long long r9 = (static_cast<long long>(e) * p.cap + m) * 9 + t;
+              const bool ok = m < count && col0 < G;
+              x4[pass][i] = ok ? *reinterpret_cast<const float4*>(p.XP9 + r9 * G + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cp[pass][i] = ok ? p.C9[r9 * LDF + (col0 >> 2)] : 0.f;
+            }
+          }
+          mbar_wait(&acc_full[buf], (tile >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128 + hf * 64 + pass * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) stg[lane * LS_STG_LD + c] = __uint_as_float(r[c]);
+            __syncwarp();
+            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;   // gate column of this lane's unit
+            const int unit = col0 >> 2;
+            if (col0 < G) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = i * 4 + rsub, rt = q * 32 + row, m = mt * 128 + rt;
+                if (rt >= rows_tile) continue;
+                const long long rg = static_cast<long long>(e) * p.cap + m;
+                const long long r9 = rg * 9 + t;
+                float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
+                if (m < count) {
+                  const float* a = stg + row * LS_STG_LD + 4 * ul;
+                  gi = ls_sigmoid(a[0] + x4[pass][i].x);
+                  gf = ls_sigmoid(a[1] + x4[pass][i].y);
+                  gg = ls_tanh(a[2] + x4[pass][i].z);
+                  go = ls_sigmoid(a[3] + x4[pass][i].w);
+                  cn = fmaf(gf, cp[pass][i], gi * gg);
+                  hn = go * ls_tanh(cn);
+                }
+                *reinterpret_cast<float4*>(p.G9 + r9 * G + col0) = make_float4(gi, gf, gg, go);
+                p.C9[(r9 + 1) * LDF + unit] = cn;
+                p.H9[(r9 + 1) * LDF + unit] = hn;
+                reinterpret_cast<unsigned short*>(p.H16)[(rg * 2 + ((t + 1) & 1)) * LS_LDH16 + unit] = f2h_sat_bits(hn);
+              }
+            }
+            __syncwarp();
+          }
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        // publish h_t of this slice (all row tiles): stores -> fences -> barrier of the epilogue warps -> release
+        __threadfence();
+        fence_proxy_async_all();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ========================================================================================================== backward
+// Per step t = 7 .. 0 and expert:  dG_t = cell'(dh_t, dc_t; gates_t, c_{t-1}, c_t),  dc_{t-1} = dc_t * f_t,
+// dh_{t-1} = dG_t W_hh  (models.py:146-151 backwards; the pointwise part is the derivative of nn.LSTMCell).
+__global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __grid_constant__ LstmBwdParams p) {
+  using namespace ppo;
+  extern __shared__ uint8_t ls_raw[];
+  uint8_t* smem = ls_raw + ((1024u - (smem_u32(ls_raw) & 1023u)) & 1023u);
+  uint8_t* w_s = smem;                                   // LSB_KB tiles [32 units x 64 gate rows]
+  uint8_t* a_s = w_s + LSB_W_BYTES;
+  float* stg_all = reinterpret_cast<float*>(a_s + LSB_STAGES * LS_A_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_all) + LSB_STG_BYTES);
+  uint64_t* empty = full + LSB_STAGES;
+  uint64_t* acc_full = empty + LSB_STAGES;               // [LSB_NBUF]
+  uint64_t* acc_empty = acc_full + LSB_NBUF;             // [LSB_NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + LSB_NBUF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.y, j = blockIdx.x;
+  const int u0 = j * 32;                                 // first hidden unit of this CTA
+  pdl_trigger();
+
+  // ---- resident weights: B[n = unit][k = gate row] = W_hh[e][k][u0 + n], fp16, swizzled K-major tiles of 64 k.
+  // A warp reads 8 consecutive gate rows (each a coalesced 128-byte segment, lane = unit) and writes one 16-byte chunk
+  // per lane (conflict-free: the 128B swizzle spreads 8 consecutive rows over the 8 chunks).
+  {
+    const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
+    const int unit = u0 + lane;
+    for (int c_all = warp; c_all < LSB_KB * 8; c_all += LSB_THREADS / 32) {
+      const int k0 = c_all * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (unit < F && k0 + i < G) ? W[static_cast<long long>(k0 + i) * LDF + unit] : 0.f;
+      *reinterpret_cast<uint4*>(w_s + (c_all >> 3) * (32 * 128) + sw128_offset(lane, c_all & 7)) = pack8_half(v, 1.0f);
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDG);
+    for (int s = 0; s < LSB_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < LSB_NBUF; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 32 * LSB_NBUF);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();
+  const int count = p.counts[e];
+  const int n_mt = (count + 127) >> 7;
+  unsigned* ctr = p.sync + e;
+  unsigned* err = p.sync + E;
+
+  if (count > 0) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer: dG_t, all rows of expert e
+      uint32_t it = 0;
+      for (int t = 7; t >= 1; --t) {
+        wait_counter(ctr, static_cast<unsigned>(LS_SLICES * (8 - t)), err, lane);
+        for (int mt = 0; mt < n_mt; ++mt)
+          for (int kb = 0; kb < LSB_KB; ++kb, ++it) {
+            const int s = it % LSB_STAGES;
+            mbar_wait(&empty[s], ((it / LSB_STAGES) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], LS_A_STAGE);
+              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmDG, &full[s], kb * 64, mt * 128, t & 1, e);
+            }
+            __syncwarp();
+          }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer: dh_{t-1}[:, units] = dG_t W_hh
+      constexpr uint32_t idesc = umma_idesc(0u, 0, 0, 128, 32);
+      uint32_t it = 0, tile = 0;
+      for (int t = 7; t >= 1; --t)
+        for (int mt = 0; mt < n_mt; ++mt, ++tile) {
+          const uint32_t buf = tile % LSB_NBUF;
+          mbar_wait(&acc_empty[buf], ((tile / LSB_NBUF) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 32;
+          for (int kb = 0; kb < LSB_KB; ++kb, ++it) {
+            const int s = it % LSB_STAGES;
+            mbar_wait(&full[s], (it / LSB_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_s + s * LS_A_STAGE);
+            const uint32_t b_addr = smem_u32(w_s + kb * (32 * 128));
+            if (elect_one()) {
+              const int nk = kb == LSB_KB - 1 ? 1 : 4;   // gate rows >= 2128 are zero on both sides (2120 = 33*64 + 8)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nk)
+                  tc_mma_f16(d_tmem, umma_smem_desc(a_addr + k * 32, 16, 1024, 2),
+                             umma_smem_desc(b_addr + k * 32, 16, 1024, 2), idesc, (kb | k) != 0);
+              tc_commit(&empty[s]);
+              if (kb == LSB_KB - 1) tc_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+          }
+        }
+    } else {
+      // ------------------------------------------------------------------ epilogue: LSTM cell backward (4 warps)
+      const int q = warp & 3;
+      float* stg = stg_all + (warp - 2) * 32 * LS_STG_LD;
+      const int unit = u0 + lane;
+      const bool unit_ok = unit < F;
+      uint32_t tile = 0;                                  // accumulator tiles consumed so far
+      for (int t = 7; t >= 0; --t) {
+        for (int mt = 0; mt < n_mt; ++mt) {
+          const bool from_acc = t < 7;
+          uint32_t buf = 0;
+          if (from_acc) {
+            buf = tile % LSB_NBUF;
+            mbar_wait(&acc_full[buf], (tile / LSB_NBUF) & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) stg[lane * LS_STG_LD + c] = __uint_as_float(r[c]);
+            __syncwarp();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);  // registers -> staging done: the buffer may be refilled
+            ++tile;
+          }
+          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);
+          // lane = unit, the warp walks its 32 rows in batches of 8 (all loads of a batch in flight together)
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 8) {
+            float4 g4[8];
+            float cprev[8], ct[8], dh[8], dcin[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rt = q * 32 + rb + i, m = mt * 128 + rt;
+              const bool ok = unit_ok && m < count;
+              const long long rg = static_cast<long long>(e) * p.cap + m;
+              const long long r9 = rg * 9 + t;
+              g4[i] = ok ? *reinterpret_cast<const float4*>(p.G9 + r9 * G + 4 * unit) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cprev[i] = ok ? p.C9[r9 * LDF + unit] : 0.f;
+              ct[i] = ok ? p.C9[(r9 + 1) * LDF + unit] : 0.f;
+              dh[i] = !ok ? 0.f : (from_acc ? stg[(rb + i) * LS_STG_LD + lane] * p.inv_scale : p.dH8[rg * LDF + unit]);
+              dcin[i] = (ok && from_acc) ? p.dC[rg * LDF + unit] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rt = q * 32 + rb + i, m = mt * 128 + rt;
+              if (rt >= rows_tile || !unit_ok) continue;
+              const long long rg = static_cast<long long>(e) * p.cap + m;
+              const long long r9 = rg * 9 + t;
+              float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m < count) {
+                const float4 g = g4[i];            // i, f, g, o
+                const float tc = tanhf(ct[i]);
+                const float dc = fmaf(dh[i] * g.w, 1.f - tc * tc, dcin[i]);
+                d = make_float4(dc * g.z * g.x * (1.f - g.x), dc * cprev[i] * g.y * (1.f - g.y),
+                                dc * g.x * (1.f - g.z * g.z), dh[i] * tc * g.w * (1.f - g.w));
+                p.dC[rg * LDF + unit] = dc * g.y;
+              }
+              *reinterpret_cast<float4*>(p.dG9 + r9 * G + 4 * unit) = d;
+              uint2 hbits;
+              hbits.x = static_cast<uint32_t>(f2h_sat_bits(d.x * p.scale)) |
+                        (static_cast<uint32_t>(f2h_sat_bits(d.y * p.scale)) << 16);
+              hbits.y = static_cast<uint32_t>(f2h_sat_bits(d.z * p.scale)) |
+                        (static_cast<uint32_t>(f2h_sat_bits(d.w * p.scale)) << 16);
+              *reinterpret_cast<uint2*>(p.dG16 + (rg * 2 + (t & 1)) * LS_LDG16 + 4 * unit) = hbits;
+            }
+          }
+          __syncwarp();                                   // staging is reused by the next tile
+        }
+        if (t > 0) {   // publish dG_t of this slice; nobody consumes dG_0
+          __threadfence();
+          fence_proxy_async_all();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 32 * LSB_NBUF);
+}
+
+}  // namespace cadre

@@ -14,6 +14,7 @@
 #include "internal.h"
 #include "ptx.cuh"
 #include "ppo_layout.h"
+#include "lstm_seq.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
                                                    const int* __restrict__ row_slot,
                                                    const int* __restrict__ row_expert, float* __restrict__ X9,
                                                    float* __restrict__ H9, float* __restrict__ C9,
-                                                   RowScalars sc) {
+                                                   __half* __restrict__ H16, RowScalars sc) {
   pdl_trigger();
   pdl_wait();
   const int r = blockIdx.x, h = blockIdx.y, R = W * mb;
@@ -117,8 +118,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
   }
   float* h0 = H9 + row * 9 * LDF;
   float* c0 = C9 + row * 9 * LDF;
+  __half* h16 = H16 + row * 2 * LS_LDH16;   // buffer 0 of the recurrence kernel's fp16 exchange: h_{-1}
   for (int f = threadIdx.x; f < F; f += 256) {
-    h0[f] = ref.hn[static_cast<long long>(t) * F + f];
+    const float hv = ref.hn[static_cast<long long>(t) * F + f];
+    h0[f] = hv;
+    h16[f] = __float2half_rn(hv);
     c0[f] = ref.cn[static_cast<long long>(t) * F + f];
   }
   if (threadIdx.x == 0) {
@@ -448,6 +452,12 @@ struct PpoPlan {
   float *X9 = nullptr, *XP9 = nullptr, *G9 = nullptr, *dG9 = nullptr, *H9 = nullptr, *C9 = nullptr;
   float *Y1 = nullptr, *Y2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dH = nullptr, *dC = nullptr;
   float* bsum = nullptr;
+  // persistent recurrence kernels (lstm_seq.cuh): fp16 exchange buffers, hand-off counters, prebuilt tensor maps
+  __half *H16 = nullptr, *dG16 = nullptr;
+  unsigned* seq_sync = nullptr;          // [0, E]: forward counters + error flag, [16, 16 + E]: backward
+  CUtensorMap tmH, tmDG;
+  float bwd_scale = 1.f;
+  bool use_seq = true;
   RowScalars sc{};
   int *row_slot = nullptr, *row_expert = nullptr, *counts = nullptr, *counts9 = nullptr;
   int* idx_dev = nullptr;
@@ -502,6 +512,26 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wih, cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
+  P->use_seq = getenv("CADRE_PPO_STEP_KERNELS") == nullptr;   // A/B switch: one launch per LSTM step (round-1 path)
+  P->H16 = dalloc<__half>(rows * 2 * LS_LDH16);
+  P->dG16 = dalloc<__half>(rows * 2 * LS_LDG16);
+  P->seq_sync = dalloc<unsigned>(32);
+  {
+    const uint64_t dims_h[4] = {(uint64_t)F, (uint64_t)P->cap, 2, (uint64_t)E};
+    const uint64_t str_h[3] = {2ull * LS_LDH16 * 2, 1ull * LS_LDH16 * 2, (uint64_t)P->cap * 2 * LS_LDH16 * 2};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    make_tensor_map_f16(&P->tmH, 4, P->H16, dims_h, str_h, box);
+    const uint64_t dims_g[4] = {(uint64_t)LS_LDG16, (uint64_t)P->cap, 2, (uint64_t)E};
+    const uint64_t str_g[3] = {2ull * LS_LDG16 * 2, 1ull * LS_LDG16 * 2, (uint64_t)P->cap * 2 * LS_LDG16 * 2};
+    make_tensor_map_f16(&P->tmDG, 4, P->dG16, dims_g, str_g, box);
+    // backward operands are scaled by 2^(ceil(log2(mini_batch)) + 4): the loss seeds carry a 1/mini_batch factor
+    int lg = 0;
+    while ((1 << lg) < cfg->mini_batch) ++lg;
+    P->bwd_scale = ldexpf(1.f, std::min(lg + 4, 14));
+    static size_t cfg_f[CADRE_MAX_DEVICES] = {}, cfg_b[CADRE_MAX_DEVICES] = {};
+    ensure_dynamic_smem(lstm_seq_fwd_kernel, LSF_SMEM, cfg_f);
+    ensure_dynamic_smem(lstm_seq_bwd_kernel, LSB_SMEM, cfg_b);
+  }
   P->sc.action = dalloc<int>(rows);
   P->sc.worker = dalloc<int>(rows);
   P->sc.old_v = dalloc<float>(rows);
@@ -567,7 +597,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
 
 static void ppo_destroy(PpoPlan* P) {
   if (!P) return;
-  void* ptrs[] = {P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
+  void* ptrs[] = {P->H16, P->dG16, P->seq_sync, P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
                   P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
                   P->row_expert, P->counts, P->counts9, P->idx_dev, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
                   P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
@@ -592,12 +622,14 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap, R = P->R;
   const long long rs9F = static_cast<long long>(cap) * 9 * LDF, rs9G = static_cast<long long>(cap) * 9 * G;
   int n = 0;
+  CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync, 0, sizeof(unsigned) * E, s));            // forward hand-off counters
+  CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 16, 0, sizeof(unsigned) * E, s));       // backward
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, idx_host, sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s));
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, refs_host, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
   launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
                                   P->counts9), ++n;
   launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
-                                         P->X9, P->H9, P->C9, P->sc), ++n;
+                                         P->X9, P->H9, P->C9, P->H16, P->sc), ++n;
   launch_k(add2_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
@@ -612,7 +644,14 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.batch_rows = P->counts9;
     launch_gemm(g, s), ++n;
   }
-  for (int t = 0; t < 8; ++t) {  // models.py:146-151: 8 sequential LSTMCell steps
+  if (P->use_seq) {   // models.py:146-151: the 8 sequential LSTMCell steps in ONE persistent launch (lstm_seq.cuh)
+    LstmFwdParams q;
+    q.tmH = P->tmH, q.params = params, q.XP9 = P->XP9, q.G9 = P->G9, q.C9 = P->C9, q.H9 = P->H9, q.H16 = P->H16;
+    q.counts = P->counts, q.sync = P->seq_sync, q.cap = cap;
+    launch_k(lstm_seq_fwd_kernel, dim3(LS_SLICES, E), dim3(LSF_THREADS), LSF_SMEM, s, q), ++n;
+    CADRE_CUDA_CHECK(cudaGetLastError());
+  } else
+  for (int t = 0; t < 8; ++t) {
     GemmArgs g = tf32_gemm(0, 0);
     g.epi = 1;
     g.A = P->H9 + t * LDF, g.lda = 9 * LDF, g.a_bs = rs9F;
@@ -721,6 +760,13 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   const unsigned bwd_full = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
   const unsigned bwd_blocks = bwd_full < 74u ? bwd_full : 74u;   // x 8 experts = 4 blocks per SM, grid-stride inside
   const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
+  if (P->use_seq) {   // BPTT: 8 x (LSTM-cell backward, dh_{t-1} = dG_t W_hh) in ONE persistent launch
+    LstmBwdParams q;
+    q.tmDG = P->tmDG, q.params = params, q.G9 = P->G9, q.C9 = P->C9, q.dG9 = P->dG9, q.dG16 = P->dG16;
+    q.dH8 = P->dH, q.dC = P->dC, q.counts = P->counts, q.sync = P->seq_sync + 16, q.cap = cap;
+    q.scale = P->bwd_scale, q.inv_scale = 1.f / P->bwd_scale;
+    launch_k(lstm_seq_bwd_kernel, dim3(LS_SLICES, E), dim3(LSB_THREADS), LSB_SMEM, s, q), ++n;
+  } else
   for (int t = 7; t >= 0; --t) {
     launch_k(lstm_bwd_kernel, dim3(dim3(bwd_blocks, E)), dim3(256), 0, s, P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
                                                         t == 7, t == 7 ? 1 : P->dgrad_split, dh_split_stride),
@@ -840,6 +886,18 @@ int cadre_ppo_wait_wih(void* handle, void* stream) {
   PpoPlan* P = static_cast<PpoPlan*>(handle);
   CADRE_REQUIRE(P != nullptr, "ppo handle");
   CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), P->ev_wih, 0));
+  CADRE_API_END
+}
+
+int cadre_ppo_check(void* handle) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P != nullptr, "ppo handle");
+  unsigned flags[32];
+  CADRE_CUDA_CHECK(cudaMemcpy(flags, P->seq_sync, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[cadre::ppo::E] != 0 || flags[16 + cadre::ppo::E] != 0)
+    throw cadre::Error(4, std::string("LSTM recurrence kernel: a cross-CTA hand-off timed out (") +
+                              (flags[cadre::ppo::E] ? "forward" : "backward") + "); results of that update are invalid");
   CADRE_API_END
 }
 

@@ -66,6 +66,13 @@ static void make_map(CUtensorMap* m, int es, int rank, const void* base, const u
   if (r != CUDA_SUCCESS) throw Error(3, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
 }
 
+// fp16 tensor map with the 128B swizzle for callers outside this file (lstm_seq.cuh's exchange buffers)
+void make_tensor_map_f16(CUtensorMap* m, int rank, const void* base, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  static_assert(CADRE_ENC_FP16 == 1, "make_tensor_map_f16 relies on the fp16 build of make_map");
+  make_map(m, 2, rank, base, dims, strides_bytes, box);
+}
+
 // matrix operand map: K-major -> dims {K, rows, batch}, box {BK, box_rows, 1};
 //                     MN-major -> dims {rows(MN), K, batch}, box {CHUNK, BK, 1}
 static void make_operand_map(CUtensorMap* m, int es, bool mn_major, const void* base, long long ld,

@@ -124,6 +124,11 @@ class PpoEngine:
         """`stream` (torch.cuda.Stream) waits until the last update() has finished the W_ih block of the gradient."""
         _lib.check(self._lib.cadre_ppo_wait_wih(self._h, ctypes.c_void_p(stream.cuda_stream)))
 
+    def check(self):
+        """Synchronise and raise CadreError if a recurrence kernel of an earlier call timed out on a hand-off."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_check(self._h))
+
     @property
     def launches(self):
         return int(self._lib.cadre_ppo_launches(self._h))

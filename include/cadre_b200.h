@@ -194,6 +194,10 @@ int cadre_ppo_module_norms(void* handle, float* norms16_host);
  * caller can start the all-reduce of that block (Shared_grad_buffers.add_gradient, models.py:231-239) while the
  * W_hh gradient is still being computed. */
 int cadre_ppo_wait_wih(void* handle, void* stream);
+/* Synchronises and returns non-zero (cadre_last_error() explains) if a persistent LSTM recurrence kernel of an
+ * earlier cadre_ppo_update / cadre_ppo_evaluate on this handle gave up waiting for a cross-CTA hand-off (its polling is
+ * bounded so that a lost signal can never hang the GPU). */
+int cadre_ppo_check(void* handle);
 int cadre_ppo_launches(void* handle);
 
 #ifdef __cplusplus

@@ -16,7 +16,7 @@ def _rollout_frames(W, K, seed):
     rgb = torch.randint(0, 256, (W, K, 144, 256, 3), dtype=torch.uint8, generator=g)
     route = (torch.rand(W, K, 256, 144, generator=g) < 0.1).to(torch.uint8).mul(255)
     route[0, 3] = (torch.rand(256, 144, generator=g) * 200).to(torch.uint8)     # non-binary map (truncation quirk)
-    route[1, 5] = 0                                                            # all-zero map
+    route[W - 1, 5] = 0                                                        # all-zero map
     meas = torch.rand(W, K, 3, dtype=torch.float64, generator=g)
     return rgb, route, meas
 

@@ -118,6 +118,7 @@ def two_worker_update():
     eng = ppo.PpoEngine(2, 100, device=DEV)
     ev = eng.evaluate(storages, advs, idx, flat).cpu()
     losses = eng.update(storages, advs, idx, flat, grads).cpu()
+    eng.check()             # no hand-off of the persistent recurrence kernels timed out
     # oracle: per-worker update_policy, gradients summed like Shared_grad_buffers.add_gradient
     params = {m: {n: t.clone().requires_grad_(True) for n, t in d.items()} for m, d in sd.items()}
     summed = {m: {n: torch.zeros_like(t) for n, t in d.items()} for m, d in sd.items()}
@@ -233,8 +234,9 @@ def test_unrouted_experts_get_exactly_zero_gradient():
     idx = np.array([[list(rs.permutation(64)[:32]), list(rs.permutation(64)[:32])]], dtype=np.int32)
     flat = P.pack_state(R.ppo_fixture_state(0), DEV)
     grads = torch.full_like(flat, 123.0)                                   # stale values must be overwritten
-    ppo.PpoEngine(1, 32, device=DEV).update([(_dev(sts[0]), _dev(sts[1]))],
-                                            [(adv[0].to(DEV), adv[1].to(DEV))], idx, flat, grads)
+    eng = ppo.PpoEngine(1, 32, device=DEV)
+    eng.update([(_dev(sts[0]), _dev(sts[1]))], [(adv[0].to(DEV), adv[1].to(DEV))], idx, flat, grads)
+    eng.check()
     g = P.unpack_state(grads.cpu())
     visited = {"steer": (0, 1), "throttle": (3,)}
     for head in ("steer", "throttle"):
@@ -400,6 +402,7 @@ def _run_config(W, mb, T, seed0):
     grads = torch.zeros_like(flat)
     eng = ppo.PpoEngine(W, mb, device=DEV)
     losses = eng.update(storages, advs, idx, flat, grads).cpu()
+    eng.check()
     post_flat = flat.clone()
     m1, m2 = torch.zeros_like(flat), torch.zeros_like(flat)
     eng.adam_step(post_flat, grads, m1, m2, step=1)

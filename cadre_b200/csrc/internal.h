@@ -100,6 +100,8 @@ struct GemmArgs {
   float alpha = 1.f;
   const int* batch_rows = nullptr;
   int rows_is_k = 0;
+  const int* tile_list = nullptr;  // optional device work list {n, (batch, m_tile) x n}; grid.x = max_tiles, grid.z = 1
+  int max_tiles = 0;
   int block_n = 0;  // 0 = choose
   int ksplit = 1;                  // split-K: partial sums go to out + ks * split_out_stride
   long long split_out_stride = 0;

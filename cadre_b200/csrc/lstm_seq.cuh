@@ -60,6 +60,7 @@ struct LstmFwdParams {
   const int* counts;      // [E] routed rows per expert
   unsigned* sync;         // [E] arrival counters (zero at launch), [E] = error flag
   int cap;
+  long long* dbg;         // optional clock64 stamps [CTA][9][8] (cadre_debug_clk), nullptr in production
 };
 
 struct LstmBwdParams {
@@ -75,6 +76,9 @@ struct LstmBwdParams {
   unsigned* sync;         // [E] counters (zero at launch), [E] = error flag
   int cap;
   float scale, inv_scale;
+  float* grads;           // flat gradient buffer: the LSTM bias gradients (column sums of dG over rows and steps) are
+                          // accumulated by the epilogue and written to OFF_BIH / OFF_BHH
+  long long* dbg;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -141,33 +145,43 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.y, j = blockIdx.x;
   const int n0 = j * 128;                                // first gate column (= W_hh row) of this CTA
+  long long* dbg = p.dbg ? p.dbg + static_cast<long long>(e * LS_SLICES + j) * 72 : nullptr;   // [9][8] stamps
   pdl_trigger();
+  if (dbg && threadIdx.x == 0) dbg[64] = clock64();
 
   // ---- resident weights: W_hh[e][n0 .. n0+127][0 .. 529] -> fp16, swizzled K-major tiles. Parameters were written
   // by an earlier, fully completed launch (the update starts with stream-ordered memsets), so this runs before
   // pdl_wait and overlaps the predecessor's tail.
   {
     const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
-    for (int task = threadIdx.x; task < 128 * (LSF_KB * 8); task += LSF_THREADS) {
-      const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);   // consecutive lanes: consecutive chunks
-      const int k0 = chunk_all * 8, n = n0 + r;
-      float v[8];
+    constexpr int TASKS = 128 * (LSF_KB * 8), UNR = 4;
+    for (int task0 = threadIdx.x; task0 < TASKS; task0 += UNR * LSF_THREADS) {
+      float4 a[UNR], b[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (n < G && k0 < F) {
-        const float* src = W + static_cast<long long>(n) * LDF + k0;
-        const float4 a = *reinterpret_cast<const float4*>(src);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
-        if (k0 + 4 < LDF) {
-          const float4 b = *reinterpret_cast<const float4*>(src + 4);
-          v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+      for (int u = 0; u < UNR; ++u) {           // all global loads of the batch first
+        const int task = task0 + u * LSF_THREADS;
+        const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);   // consecutive lanes: consecutive chunks
+        const int k0 = chunk_all * 8, n = n0 + r;
+        a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (task < TASKS && n < G && k0 < F) {
+          const float* src = W + static_cast<long long>(n) * LDF + k0;
+          a[u] = *reinterpret_cast<const float4*>(src);
+          if (k0 + 4 < LDF) b[u] = *reinterpret_cast<const float4*>(src + 4);
         }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int task = task0 + u * LSF_THREADS;
+        if (task >= TASKS) continue;
+        const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);
+        const int k0 = chunk_all * 8;
+        float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (k0 + i >= F) v[i] = 0.f;
+        const int kb = chunk_all >> 3, c = chunk_all & 7;
+        *reinterpret_cast<uint4*>(w_s + kb * (128 * 128) + sw128_offset(r, c)) = pack8_half(v, 1.0f);
       }
-      const int kb = chunk_all >> 3, c = chunk_all & 7;
-      *reinterpret_cast<uint4*>(w_s + kb * (128 * 128) + sw128_offset(r, c)) = pack8_half(v, 1.0f);
     }
   }
   if (warp == 0 && lane == 0) {
@@ -191,8 +205,10 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[65] = clock64();      // weights resident
 
   pdl_wait();                           // counts, XP9, H16 buffer 0, the zeroed counters: all from earlier launches
+  if (dbg && threadIdx.x == 0) dbg[66] = clock64();
   const int count = p.counts[e];
   const int n_mt = (count + 127) >> 7;
   unsigned* ctr = p.sync + e;
@@ -203,7 +219,9 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
       // ------------------------------------------------------------------ TMA producer: h_{t-1}, all rows of expert e
       uint32_t it = 0;
       for (int t = 0; t < 8; ++t) {
+        if (dbg && lane == 0) dbg[t * 8 + 0] = clock64();
         if (t > 0) wait_counter(ctr, static_cast<unsigned>(LS_SLICES * t), err, lane);
+        if (dbg && lane == 0) dbg[t * 8 + 1] = clock64();
         for (int mt = 0; mt < n_mt; ++mt)
           for (int kb = 0; kb < LSF_KB; ++kb, ++it) {
             const int s = it % LSF_STAGES;
@@ -214,6 +232,7 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
             }
             __syncwarp();
           }
+        if (dbg && lane == 0) dbg[t * 8 + 2] = clock64();
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer
@@ -243,6 +262,7 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
             }
             __syncwarp();
           }
+          if (dbg && lane == 0) dbg[t * 8 + 3] = clock64();
         }
     } else {
       // ------------------------------------------------------------------ epilogue: LSTM cell (8 warps)
@@ -272,6 +292,7 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
           }
           mbar_wait(&acc_full[buf], (tile >> 1) & 1);
           tc_fence_after();
+          if (dbg && threadIdx.x == 64) dbg[t * 8 + 4] = clock64();
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             uint32_t r[32];
@@ -311,10 +332,12 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         // publish h_t of this slice (all row tiles): stores -> fences -> barrier of the epilogue warps -> release
+        if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
         __threadfence();
         fence_proxy_async_all();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+        if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
       }
     }
   }
@@ -342,7 +365,9 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.y, j = blockIdx.x;
   const int u0 = j * 32;                                 // first hidden unit of this CTA
+  long long* dbg = p.dbg ? p.dbg + static_cast<long long>(e * LS_SLICES + j) * 72 : nullptr;
   pdl_trigger();
+  if (dbg && threadIdx.x == 0) dbg[64] = clock64();
 
   // ---- resident weights: B[n = unit][k = gate row] = W_hh[e][k][u0 + n], fp16, swizzled K-major tiles of 64 k.
   // A warp reads 8 consecutive gate rows (each a coalesced 128-byte segment, lane = unit) and writes one 16-byte chunk
@@ -350,12 +375,23 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
   {
     const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
     const int unit = u0 + lane;
-    for (int c_all = warp; c_all < LSB_KB * 8; c_all += LSB_THREADS / 32) {
-      const int k0 = c_all * 8;
-      float v[8];
+    constexpr int NW = LSB_THREADS / 32, UNR = 3;
+    for (int c0 = warp; c0 < LSB_KB * 8; c0 += UNR * NW) {
+      float v[UNR][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (unit < F && k0 + i < G) ? W[static_cast<long long>(k0 + i) * LDF + unit] : 0.f;
-      *reinterpret_cast<uint4*>(w_s + (c_all >> 3) * (32 * 128) + sw128_offset(lane, c_all & 7)) = pack8_half(v, 1.0f);
+      for (int u = 0; u < UNR; ++u) {
+        const int k0 = (c0 + u * NW) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[u][i] = (unit < F && k0 + i < G) ? W[static_cast<long long>(k0 + i) * LDF + unit] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c_all = c0 + u * NW;
+        if (c_all < LSB_KB * 8)
+          *reinterpret_cast<uint4*>(w_s + (c_all >> 3) * (32 * 128) + sw128_offset(lane, c_all & 7)) =
+              pack8_half(v[u], 1.0f);
+      }
     }
   }
   if (warp == 0 && lane == 0) {
@@ -379,8 +415,10 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[65] = clock64();
 
   pdl_wait();
+  if (dbg && threadIdx.x == 0) dbg[66] = clock64();
   const int count = p.counts[e];
   const int n_mt = (count + 127) >> 7;
   unsigned* ctr = p.sync + e;
@@ -391,7 +429,9 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
       // ------------------------------------------------------------------ TMA producer: dG_t, all rows of expert e
       uint32_t it = 0;
       for (int t = 7; t >= 1; --t) {
+        if (dbg && lane == 0) dbg[t * 8 + 0] = clock64();
         wait_counter(ctr, static_cast<unsigned>(LS_SLICES * (8 - t)), err, lane);
+        if (dbg && lane == 0) dbg[t * 8 + 1] = clock64();
         for (int mt = 0; mt < n_mt; ++mt)
           for (int kb = 0; kb < LSB_KB; ++kb, ++it) {
             const int s = it % LSB_STAGES;
@@ -402,6 +442,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             }
             __syncwarp();
           }
+        if (dbg && lane == 0) dbg[t * 8 + 2] = clock64();
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------------ MMA issuer: dh_{t-1}[:, units] = dG_t W_hh
@@ -431,6 +472,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             }
             __syncwarp();
           }
+          if (dbg && lane == 0) dbg[t * 8 + 3] = clock64();
         }
     } else {
       // ------------------------------------------------------------------ epilogue: LSTM cell backward (4 warps)
@@ -439,6 +481,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
       const int unit = u0 + lane;
       const bool unit_ok = unit < F;
       uint32_t tile = 0;                                  // accumulator tiles consumed so far
+      float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dG over this warp's rows, all tiles and steps
       for (int t = 7; t >= 0; --t) {
         for (int mt = 0; mt < n_mt; ++mt) {
           const bool from_acc = t < 7;
@@ -447,6 +490,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             buf = tile % LSB_NBUF;
             mbar_wait(&acc_full[buf], (tile / LSB_NBUF) & 1);
             tc_fence_after();
+            if (dbg && threadIdx.x == 64 && mt == 0) dbg[t * 8 + 4] = clock64();
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32, r);
             tmem_ld_wait();
@@ -489,6 +533,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
                 d = make_float4(dc * g.z * g.x * (1.f - g.x), dc * cprev[i] * g.y * (1.f - g.y),
                                 dc * g.x * (1.f - g.z * g.z), dh[i] * tc * g.w * (1.f - g.w));
                 p.dC[rg * LDF + unit] = dc * g.y;
+                bias_acc.x += d.x, bias_acc.y += d.y, bias_acc.z += d.z, bias_acc.w += d.w;
               }
               *reinterpret_cast<float4*>(p.dG9 + r9 * G + 4 * unit) = d;
               uint2 hbits;
@@ -502,12 +547,38 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
           __syncwarp();                                   // staging is reused by the next tile
         }
         if (t > 0) {   // publish dG_t of this slice; nobody consumes dG_0
+          if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
           __threadfence();
           fence_proxy_async_all();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+          if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
         }
       }
+      // LSTM bias gradients: d loss / d b_ih = d loss / d b_hh = sum over rows and steps of dG (models.py:133-137).
+      // Fixed summation order (rows of a warp in sequence, then the four warps in order): deterministic.
+      float4* red = reinterpret_cast<float4*>(stg_all);   // staging is free now: [4 warps][32 lanes]
+      __syncwarp();
+      red[(warp - 2) * 32 + lane] = bias_acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && unit_ok) {
+        float4 s4 = red[lane];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float4 o = red[w * 32 + lane];
+          s4.x += o.x, s4.y += o.y, s4.z += o.z, s4.w += o.w;
+        }
+        *reinterpret_cast<float4*>(p.grads + OFF_BIH + static_cast<long long>(e) * G + 4 * unit) = s4;
+        *reinterpret_cast<float4*>(p.grads + OFF_BHH + static_cast<long long>(e) * G + 4 * unit) = s4;
+      }
+    }
+  } else if (warp == 2) {
+    // an expert without rows: its LSTM bias gradients are exact zeros
+    const int unit = u0 + lane;
+    if (unit < F) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(p.grads + OFF_BIH + static_cast<long long>(e) * G + 4 * unit) = z;
+      *reinterpret_cast<float4*>(p.grads + OFF_BHH + static_cast<long long>(e) * G + 4 * unit) = z;
     }
   }
   tc_fence_before();

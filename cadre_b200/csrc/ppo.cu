@@ -135,12 +135,23 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
   }
 }
 
-__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
-                            int n) {
+// b_ih + b_hh (one bias vector for the x-part GEMM) and the compacted work list of that GEMM: (expert, 128-row tile)
+// pairs covering the 9 * count[e] valid rows of each expert, so that its grid is sized by the rows that exist
+// (2 * 9 * R / 128 + 8 tiles at most) instead of by the per-expert capacity (8 * 9 * cap / 128).
+__global__ void prep_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n,
+                            const int* __restrict__ counts9, int* __restrict__ tile_list, int max_tiles) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
+  if (i == 0) {
+    int nt = 0;
+    for (int e = 0; e < E; ++e) {
+      const int tiles = (counts9[e] + 127) >> 7;
+      for (int m = 0; m < tiles && nt < max_tiles; ++m, ++nt) tile_list[1 + 2 * nt] = e, tile_list[2 + 2 * nt] = m;
+    }
+    tile_list[0] = nt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ heads + loss
@@ -150,17 +161,28 @@ struct HeadParams {
   const float* Y2;      // [E][cap][256] post-ReLU hidden (actor | critic)
   float* dZ2;           // [E][cap][256]
   const float* params;  // flat parameters
-  float* grads;         // flat gradients (W3A/B3A/W3C/B3C accumulated with atomics)
+  float* grads;         // flat gradients (W3A / B3A / W3C / B3C written by the last CTA of each expert)
   const int* counts;
   RowScalars sc;
-  float* losses;        // [W][2][3] value, action, entropy (un-scaled means)
-  int cap;
+  float* losses;        // [W][2][3] value, action, entropy (un-scaled means), written by the last CTA of the grid
+  float* partial;       // [E][cap / HEAD_ROWS][HEAD_PARTIAL] per-CTA partial sums (scratch)
+  float* loss_e;        // [E][W][3] per-expert loss sums (scratch)
+  unsigned* ctr;        // [E] finished CTAs per expert, [E] finished experts (zero at launch)
+  int cap, W;
   float inv_mb, clip, value_coeff, clip_coeff, ent_coeff;
 };
 
-constexpr int HEAD_ROWS_PER_CTA = 64;
+constexpr int HEAD_ROWS_PER_CTA = 32;
+constexpr int HEAD_MAX_W = 64;   // workers per engine the loss reduction is sized for
+// per-CTA partial: dW3A [33][128], dW3C [128], dB3A [36], dB3C [4], losses [HEAD_MAX_W][3]
+constexpr int HP_W3A = 0, HP_W3C = AMAX * HID, HP_B3A = HP_W3C + HID, HP_B3C = HP_B3A + B3A_LD, HP_LOSS = HP_B3C + 4;
+constexpr int HEAD_PARTIAL = HP_LOSS + HEAD_MAX_W * 3;
 constexpr int DGRAD_SPLIT = 4;  // maximum split-K factor of the recurrent dgrad GEMMs (K = 2120); see PpoPlan::dgrad_split
 
+// Every sum of this kernel has a FIXED order (rows of a CTA in sequence, CTAs of an expert by block index, experts of
+// a head by index), so losses and last-layer gradients are bit-reproducible from run to run: each CTA writes its
+// partial sums to scratch, the last CTA of an expert to finish (device-wide counter) reduces them in block order, and
+// the last expert to finish reduces the per-expert losses in expert order. No floating-point atomics.
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   pdl_trigger();
   pdl_wait();
@@ -176,6 +198,9 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float s_y[8][2 * HID];
   __shared__ float s_dl[HEAD_ROWS_PER_CTA][AMAX + 3];  // d loss / d logits of the CTA's rows
   __shared__ float s_dv[HEAD_ROWS_PER_CTA];
+  __shared__ float s_lt[HEAD_ROWS_PER_CTA][3];         // loss terms of the CTA's rows
+  __shared__ int s_wk[HEAD_ROWS_PER_CTA];              // worker of each row (-1: padding row)
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* W3A = p.params + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
   for (int i = tid; i < AMAX * HID; i += 256) {
@@ -185,7 +210,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   if (tid < AMAX) b3a[tid] = p.params[OFF_B3A + e * B3A_LD + tid];
   if (tid < HID) w3c[tid] = p.params[OFF_W3C + e * HID + tid];
   for (int i = tid; i < HEAD_ROWS_PER_CTA * (AMAX + 3); i += 256) (&s_dl[0][0])[i] = 0.f;
-  if (tid < HEAD_ROWS_PER_CTA) s_dv[tid] = 0.f;
+  if (tid < HEAD_ROWS_PER_CTA) s_dv[tid] = 0.f, s_wk[tid] = -1;
   const float b3c = p.params[OFF_B3C + e * 4];
   __syncthreads();
 
@@ -209,17 +234,27 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     }
     __syncwarp();
     float l0 = -INFINITY, l1 = -INFINITY;
-    if (lane < A) {
-      float acc = b3a[lane];
+    if (lane < A) {   // four independent accumulation chains (the sum order is fixed by this code, not by timing)
+      float a0 = b3a[lane], a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < HID; ++k) acc = fmaf(s_y[warp][k], w3aT[k][lane], acc);
-      l0 = acc;
+      for (int k = 0; k < HID; k += 4) {
+        a0 = fmaf(s_y[warp][k], w3aT[k][lane], a0);
+        a1 = fmaf(s_y[warp][k + 1], w3aT[k + 1][lane], a1);
+        a2 = fmaf(s_y[warp][k + 2], w3aT[k + 2][lane], a2);
+        a3 = fmaf(s_y[warp][k + 3], w3aT[k + 3][lane], a3);
+      }
+      l0 = (a0 + a1) + (a2 + a3);
     }
     if (lane + 32 < A) {
-      float acc = b3a[lane + 32];
+      float a0 = b3a[lane + 32], a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < HID; ++k) acc = fmaf(s_y[warp][k], w3aT[k][lane + 32], acc);
-      l1 = acc;
+      for (int k = 0; k < HID; k += 4) {
+        a0 = fmaf(s_y[warp][k], w3aT[k][lane + 32], a0);
+        a1 = fmaf(s_y[warp][k + 1], w3aT[k + 1][lane + 32], a1);
+        a2 = fmaf(s_y[warp][k + 2], w3aT[k + 2][lane + 32], a2);
+        a3 = fmaf(s_y[warp][k + 3], w3aT[k + 3][lane + 32], a3);
+      }
+      l1 = (a0 + a1) + (a2 + a3);
     }
     float v = 0.f;
 #pragma unroll
@@ -252,10 +287,10 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     const float vl = (v - ret) * (v - ret), vlc = (v_clip - ret) * (v_clip - ret);
     const float value_term = 0.5f * fmaxf(vl, vlc);
     if (lane == 0) {
-      float* L = p.losses + (p.sc.worker[row] * 2 + head) * 3;
-      atomicAdd(L + 0, wgt * value_term);
-      atomicAdd(L + 1, wgt * action_term);
-      atomicAdd(L + 2, wgt * ent);
+      s_lt[slot - row0][0] = wgt * value_term;
+      s_lt[slot - row0][1] = wgt * action_term;
+      s_lt[slot - row0][2] = wgt * ent;
+      s_wk[slot - row0] = p.sc.worker[row];
     }
     // backward seeds (autograd conventions of torch.min / torch.max / clamp: ties split evenly, clamp passes
     // the gradient on the closed interval)
@@ -291,38 +326,96 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   }
   __syncthreads();
 
-  // ---- phase 2: last-layer weight gradients of the CTA's rows as small register-tiled products over the
-  // rows (hidden2 is re-read from L2, d logits / d value sit in shared memory), one global atomic per element
-  const int nrows = min(count, row0 + HEAD_ROWS_PER_CTA) - row0;  // valid rows (padding rows carry zeros anyway)
-  if (nrows <= 0) return;
-  const float* Ybase = p.Y2 + (static_cast<long long>(e) * p.cap + row0) * 2 * HID;
+  // ---- phase 2: this CTA's partial last-layer weight gradients as small register-tiled products over its rows
+  // (hidden2 is re-read from L2 eight rows at a time, d logits / d value sit in shared memory) -> scratch
+  const int nrows = min(count, row0 + HEAD_ROWS_PER_CTA) - row0;  // valid rows (>= 1 here; padding rows carry zeros)
+  const int nblk = rows_pad / HEAD_ROWS_PER_CTA;                  // working CTAs of this expert
+  float* part = p.partial + (static_cast<long long>(e) * (p.cap / HEAD_ROWS_PER_CTA) + blockIdx.x) * HEAD_PARTIAL;
   {
+    const float* Ybase = p.Y2 + (static_cast<long long>(e) * p.cap + row0) * 2 * HID;
     const int k = tid & (HID - 1), jh = tid >> 7;          // column k, logits [jh*17, jh*17+17)
     const int j0 = jh * 17, j1 = min(A, j0 + 17);
     float acc[17];
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = 0.f;
-    float accc = 0.f, accb = 0.f;
-    for (int r = 0; r < nrows; ++r) {
-      const float yv = Ybase[r * 2 * HID + k];
+    float accc = 0.f;
+    for (int r0 = 0; r0 < nrows; r0 += 8) {
+      float yv[8], ycv[8];
 #pragma unroll
-      for (int i = 0; i < 17; ++i)
-        if (j0 + i < j1) acc[i] = fmaf(s_dl[r][j0 + i], yv, acc[i]);
-      if (jh == 0) accc = fmaf(s_dv[r], Ybase[r * 2 * HID + HID + k], accc);
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = r0 + i < nrows;
+        yv[i] = ok ? Ybase[(r0 + i) * 2 * HID + k] : 0.f;
+        ycv[i] = (ok && jh == 0) ? Ybase[(r0 + i) * 2 * HID + HID + k] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = min(r0 + i, HEAD_ROWS_PER_CTA - 1);
+#pragma unroll
+        for (int ii = 0; ii < 17; ++ii)
+          if (j0 + ii < j1) acc[ii] = fmaf(s_dl[r][j0 + ii], yv[i], acc[ii]);
+        accc = fmaf(s_dv[r], ycv[i], accc);
+      }
     }
-    float* gW3A = p.grads + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
 #pragma unroll
     for (int i = 0; i < 17; ++i)
-      if (j0 + i < j1) atomicAdd(gW3A + (j0 + i) * HID + k, acc[i]);
-    if (jh == 0) atomicAdd(p.grads + OFF_W3C + e * HID + k, accc);
-    // bias gradients: column sums of d logits / d value
-    if (tid < A) {
+      if (j0 + i < j1) part[HP_W3A + (j0 + i) * HID + k] = acc[i];
+    if (jh == 0) part[HP_W3C + k] = accc;
+    if (tid < A) {          // bias gradients: column sums of d logits / d value
+      float accb = 0.f;
       for (int r = 0; r < nrows; ++r) accb += s_dl[r][tid];
-      atomicAdd(p.grads + OFF_B3A + e * B3A_LD + tid, accb);
+      part[HP_B3A + tid] = accb;
     } else if (tid == 64) {
+      float accb = 0.f;
       for (int r = 0; r < nrows; ++r) accb += s_dv[r];
-      atomicAdd(p.grads + OFF_B3C + e * 4, accb);
+      part[HP_B3C] = accb;
+    } else if (tid >= 128 && tid < 128 + p.W) {   // loss terms of worker tid - 128, rows in order
+      const int w = tid - 128;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+      for (int r = 0; r < HEAD_ROWS_PER_CTA; ++r)
+        if (s_wk[r] == w) l0 += s_lt[r][0], l1 += s_lt[r][1], l2 += s_lt[r][2];
+      part[HP_LOSS + w * 3 + 0] = l0, part[HP_LOSS + w * 3 + 1] = l1, part[HP_LOSS + w * 3 + 2] = l2;
     }
+  }
+  // ---- phase 3: the last CTA of the expert reduces the partials in block order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.ctr + e, 1u) == static_cast<unsigned>(nblk - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pe = p.partial + static_cast<long long>(e) * (p.cap / HEAD_ROWS_PER_CTA) * HEAD_PARTIAL;
+  for (int i = tid; i < HP_LOSS + p.W * 3; i += 256) {
+    float sum = 0.f;
+    for (int b = 0; b < nblk; ++b) sum += __ldcg(pe + static_cast<long long>(b) * HEAD_PARTIAL + i);
+    if (i < HP_W3C) {
+      if (i < A * HID) p.grads[OFF_W3A + static_cast<long long>(e) * AMAX * HID + i] = sum;
+    } else if (i < HP_B3A) {
+      p.grads[OFF_W3C + e * HID + (i - HP_W3C)] = sum;
+    } else if (i < HP_B3C) {
+      if (i - HP_B3A < A) p.grads[OFF_B3A + e * B3A_LD + (i - HP_B3A)] = sum;
+    } else if (i < HP_LOSS) {
+      if (i == HP_B3C) p.grads[OFF_B3C + e * 4] = sum;
+    } else {
+      p.loss_e[e * HEAD_MAX_W * 3 + (i - HP_LOSS)] = sum;
+    }
+  }
+  // ---- phase 4: the last expert to finish adds the per-expert losses in expert order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    int active = 0;
+    for (int x = 0; x < E; ++x) active += p.counts[x] > 0;
+    s_last = (atomicAdd(p.ctr + E, 1u) == static_cast<unsigned>(active - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < p.W * 2 * 3; i += 256) {
+    const int w = i / 6, h = (i / 3) % 2, c = i % 3;
+    float sum = 0.f;
+    for (int x = 0; x < 4; ++x)
+      if (p.counts[h * 4 + x] > 0) sum += __ldcg(p.loss_e + (h * 4 + x) * HEAD_MAX_W * 3 + w * 3 + c);
+    p.losses[(w * 2 + h) * 3 + c] = sum;
   }
 }
 
@@ -454,13 +547,16 @@ struct PpoPlan {
   float* bsum = nullptr;
   // persistent recurrence kernels (lstm_seq.cuh): fp16 exchange buffers, hand-off counters, prebuilt tensor maps
   __half *H16 = nullptr, *dG16 = nullptr;
-  unsigned* seq_sync = nullptr;          // [0, E]: forward counters + error flag, [16, 16 + E]: backward
+  float *head_partial = nullptr, *head_loss_e = nullptr;   // head_kernel scratch (ordered reductions)
+  unsigned* seq_sync = nullptr;          // [0, E]: forward counters + error flag, [16, 16 + E]: backward, [32, 32 + E]: head
   CUtensorMap tmH, tmDG;
   float bwd_scale = 1.f;
   bool use_seq = true;
   RowScalars sc{};
   int *row_slot = nullptr, *row_expert = nullptr, *counts = nullptr, *counts9 = nullptr;
   int* idx_dev = nullptr;
+  int* xp_tiles = nullptr;   // work list of the x-part GEMM (prep_kernel)
+  int xp_max_tiles = 0;
   StorageRef* refs_dev = nullptr;
   OptTables opt;
   int launches = 0;
@@ -515,7 +611,10 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->use_seq = getenv("CADRE_PPO_STEP_KERNELS") == nullptr;   // A/B switch: one launch per LSTM step (round-1 path)
   P->H16 = dalloc<__half>(rows * 2 * LS_LDH16);
   P->dG16 = dalloc<__half>(rows * 2 * LS_LDG16);
-  P->seq_sync = dalloc<unsigned>(32);
+  P->seq_sync = dalloc<unsigned>(64);
+  CADRE_REQUIRE(cfg->workers <= HEAD_MAX_W, "at most 64 workers per engine");
+  P->head_partial = dalloc<float>(static_cast<size_t>(E) * (P->cap / HEAD_ROWS_PER_CTA) * HEAD_PARTIAL);
+  P->head_loss_e = dalloc<float>(static_cast<size_t>(E) * HEAD_MAX_W * 3);
   {
     const uint64_t dims_h[4] = {(uint64_t)F, (uint64_t)P->cap, 2, (uint64_t)E};
     const uint64_t str_h[3] = {2ull * LS_LDH16 * 2, 1ull * LS_LDH16 * 2, (uint64_t)P->cap * 2 * LS_LDH16 * 2};
@@ -543,6 +642,8 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->counts = dalloc<int>(E);
   P->counts9 = dalloc<int>(E);
   P->idx_dev = dalloc<int>(2 * static_cast<size_t>(P->R));
+  P->xp_max_tiles = (2 * 9 * P->R + 127) / 128 + E;   // sum_e ceil(9 count_e / 128), sum_e count_e = 2 R
+  P->xp_tiles = dalloc<int>(1 + 2 * static_cast<size_t>(P->xp_max_tiles));
   P->refs_dev = dalloc<StorageRef>(2 * static_cast<size_t>(cfg->workers));
 
   // optimizer chunk table, grouped by module: module e = LSTM of expert e, module 8+e = actor-critic of expert e
@@ -597,9 +698,9 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
 
 static void ppo_destroy(PpoPlan* P) {
   if (!P) return;
-  void* ptrs[] = {P->H16, P->dG16, P->seq_sync, P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
+  void* ptrs[] = {P->head_partial, P->head_loss_e, P->H16, P->dG16, P->seq_sync, P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
                   P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
-                  P->row_expert, P->counts, P->counts9, P->idx_dev, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
+                  P->row_expert, P->counts, P->counts9, P->idx_dev, P->xp_tiles, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
                   P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
   for (void* p : ptrs) cudaFree(p);
   if (P->side) cudaStreamDestroy(P->side);
@@ -624,13 +725,15 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   int n = 0;
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync, 0, sizeof(unsigned) * E, s));            // forward hand-off counters
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 16, 0, sizeof(unsigned) * E, s));       // backward
+  CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 32, 0, sizeof(unsigned) * (E + 1), s));  // head_kernel reductions
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, idx_host, sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s));
   CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, refs_host, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
   launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
                                   P->counts9), ++n;
   launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
                                          P->X9, P->H9, P->C9, P->H16, P->sc), ++n;
-  launch_k(add2_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G), ++n;
+  launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G,
+           P->counts9, P->xp_tiles, P->xp_max_tiles), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
   // ---- forward
@@ -642,12 +745,14 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.out = P->XP9, g.ldc = G, g.out_bs = rs9G;
     g.bias = P->bsum, g.bias_bs = G;
     g.batch_rows = P->counts9;
+    g.tile_list = P->xp_tiles, g.max_tiles = P->xp_max_tiles;
     launch_gemm(g, s), ++n;
   }
   if (P->use_seq) {   // models.py:146-151: the 8 sequential LSTMCell steps in ONE persistent launch (lstm_seq.cuh)
     LstmFwdParams q;
     q.tmH = P->tmH, q.params = params, q.XP9 = P->XP9, q.G9 = P->G9, q.C9 = P->C9, q.H9 = P->H9, q.H16 = P->H16;
     q.counts = P->counts, q.sync = P->seq_sync, q.cap = cap;
+    q.dbg = g_dbg_clk;
     launch_k(lstm_seq_fwd_kernel, dim3(LS_SLICES, E), dim3(LSF_THREADS), LSF_SMEM, s, q), ++n;
     CADRE_CUDA_CHECK(cudaGetLastError());
   } else
@@ -696,7 +801,8 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   {
     HeadParams hp;
     hp.Y2 = P->Y2, hp.dZ2 = P->dZ2, hp.params = params, hp.grads = grads, hp.counts = P->counts, hp.sc = P->sc;
-    hp.losses = losses, hp.cap = cap, hp.inv_mb = 1.f / static_cast<float>(mb);
+    hp.losses = losses, hp.cap = cap, hp.W = W, hp.inv_mb = 1.f / static_cast<float>(mb);
+    hp.partial = P->head_partial, hp.loss_e = P->head_loss_e, hp.ctr = P->seq_sync + 32;
     hp.clip = P->cfg.clip, hp.value_coeff = P->cfg.value_coeff, hp.clip_coeff = P->cfg.clip_coeff;
     hp.ent_coeff = P->cfg.ent_coeff;
     launch_k(head_kernel, dim3(dim3(cap / HEAD_ROWS_PER_CTA, E)), dim3(256), 0, s, hp), ++n;
@@ -765,6 +871,8 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     q.tmDG = P->tmDG, q.params = params, q.G9 = P->G9, q.C9 = P->C9, q.dG9 = P->dG9, q.dG16 = P->dG16;
     q.dH8 = P->dH, q.dC = P->dC, q.counts = P->counts, q.sync = P->seq_sync + 16, q.cap = cap;
     q.scale = P->bwd_scale, q.inv_scale = 1.f / P->bwd_scale;
+    q.grads = grads;
+    q.dbg = g_dbg_clk ? g_dbg_clk + E * LS_SLICES * 72 : nullptr;
     launch_k(lstm_seq_bwd_kernel, dim3(LS_SLICES, E), dim3(LSB_THREADS), LSB_SMEM, s, q), ++n;
   } else
   for (int t = 7; t >= 0; --t) {
@@ -783,12 +891,14 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     }
   }
   CADRE_CUDA_CHECK(cudaGetLastError());
-  if (P->use_side) {   // dG9 is complete: its column sums (LSTM bias gradients) run next to the weight-gradient GEMMs
-    CADRE_CUDA_CHECK(cudaEventRecord(P->ev_bptt, s));
-    CADRE_CUDA_CHECK(cudaStreamWaitEvent(s2, P->ev_bptt, 0));
+  if (!P->use_seq) {   // (the persistent BPTT kernel accumulates the LSTM bias gradients itself)
+    if (P->use_side) {   // dG9 is complete: its column sums run next to the weight-gradient GEMMs
+      CADRE_CUDA_CHECK(cudaEventRecord(P->ev_bptt, s));
+      CADRE_CUDA_CHECK(cudaStreamWaitEvent(s2, P->ev_bptt, 0));
+    }
+    launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s2, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
+                                                         grads + OFF_BHH), ++n;
   }
-  launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s2, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
-                                                       grads + OFF_BHH), ++n;
   if (P->use_side) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_join, s2));
   for (int which = 0; which < 2; ++which) {  // dW_ih = dG9^T X9, dW_hh = dG9^T H9 (K = 9 * rows)
     GemmArgs g = tf32_gemm(1, 1);

@@ -157,6 +157,7 @@ static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
   p.mask = a.mask, p.ldm = a.ldm, p.mask_bs = a.mask_bs;
   p.act = a.act, p.alpha = a.alpha;
   p.batch_rows = a.batch_rows, p.rows_is_k = a.rows_is_k;
+  p.tile_list = a.tile_list;
   p.dbg_a_shift = a.dbg_a_shift, p.dbg_base_offset = a.dbg_base_offset, p.dbg_clk = a.dbg_clk, p.dbg_epi = a.dbg_epi;
   p.xpart = a.xpart, p.ldx = a.ldx, p.x_bs = a.x_bs;
   p.c_prev = a.c_prev, p.c_out = a.c_out, p.h_out = a.h_out, p.gates_out = a.gates_out;
@@ -213,6 +214,10 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_REQUIRE(p.ksplit == 1 || (!a.bias && !a.res && !a.mask && a.act == 0 && !a.rows_is_k && a.epi == 0),
                 "split-K supports plain partial sums only");
   dim3 grid((a.M + 127) / 128, (a.N + bn - 1) / bn, a.batch * p.ksplit);
+  if (a.tile_list != nullptr) {
+    CADRE_REQUIRE(a.max_tiles > 0 && p.ksplit == 1 && a.batch_rows != nullptr && !a.rows_is_k, "tile list arguments");
+    grid = dim3(a.max_tiles, (a.N + bn - 1) / bn, 1);
+  }
 
 #define CADRE_GEMM_CASE(KIND, AMN, BMN, BN, ST, EPI, OUT_F32, OutT)                                   \
   if (a.kind == KIND && a.a_mn == AMN && a.b_mn == BMN && bn == BN && a.epi == EPI && a.out_f32 == OUT_F32) { \

@@ -47,6 +47,9 @@ struct TcGemmParams {
   int dbg_a_shift, dbg_base_offset;  // experiment: A descriptor start shifted by rows (128 B each)
   const int* batch_rows;  // optional [gridDim.z]: valid rows (M) per batch, or valid K when rows_is_k
   int rows_is_k;
+  // optional compacted work list (device): tile_list[0] = n, then n pairs (batch, m_tile). blockIdx.x indexes the
+  // list (grid.z = 1): no CTA is launched for the unused part of a batch's row capacity
+  const int* tile_list;
   // EPI_LSTM: acc = h_{t-1} W_hh^T (gate-interleaved columns 4*u+g); xpart holds x_t W_ih^T + b_ih + b_hh
   const float* xpart;
   long long ldx, x_bs;
@@ -103,9 +106,15 @@ __global__ void __launch_bounds__(64 + 128 * EW) tc_gemm_kernel(const __grid_con
   pdl_trigger();
   pdl_wait();   // batch_rows / bias below may have been written by the previous launch (route kernel, Adam)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  int m_tile = blockIdx.x;
+  const int n_tile = blockIdx.y;
   const int ks = p.ksplit > 1 ? static_cast<int>(blockIdx.z) % p.ksplit : 0;
-  const int batch = p.ksplit > 1 ? static_cast<int>(blockIdx.z) / p.ksplit : static_cast<int>(blockIdx.z);
+  int batch = p.ksplit > 1 ? static_cast<int>(blockIdx.z) / p.ksplit : static_cast<int>(blockIdx.z);
+  if (p.tile_list != nullptr) {   // written by an earlier launch: read after pdl_wait (above)
+    if (static_cast<int>(blockIdx.x) >= p.tile_list[0]) return;   // uniform for the whole CTA, before any barrier
+    batch = p.tile_list[1 + 2 * blockIdx.x];
+    m_tile = p.tile_list[2 + 2 * blockIdx.x];
+  }
   const int n0 = n_tile * BLOCK_N;
   long long* clk = p.dbg_clk ? p.dbg_clk + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (clk && threadIdx.x == 0) clk[0] = clock64();
@@ -287,22 +296,36 @@ __global__ void __launch_bounds__(64 + 128 * EW) tc_gemm_kernel(const __grid_con
           }
           const float alpha = p.alpha;
           const int act = p.act;
-          const bool general = (p.res != nullptr) || (p.mask != nullptr) || (MODE != MODE_GEMM);
+          // the fp32 ReLU-backward mask rides the fast path; residuals, conv row mapping and 16-bit masks do not
+          const bool general = (p.res != nullptr) || (MODE != MODE_GEMM) || (p.mask != nullptr && sizeof(OutT) != 4);
           OutT* obase = reinterpret_cast<OutT*>(p.out) + batch * p.out_bs + ks * p.split_out_stride + n;
           const bool vec = nv == 4 && ((reinterpret_cast<uintptr_t>(obase) | (p.ldc * sizeof(OutT))) % (4 * sizeof(OutT)) == 0);
           const bool zero_rows = (p.batch_rows != nullptr) && !p.rows_is_k;
           if (!general && vec) {
             // fast path: plain GEMM rows, coalesced 16-byte stores
 #pragma unroll 1
+            const float* mbase = (sizeof(OutT) == 4 && p.mask != nullptr)
+                                     ? reinterpret_cast<const float*>(p.mask) + batch * p.mask_bs + n
+                                     : nullptr;
             for (int rr = r_lo; rr < r_hi; rr += 4) {
-              float4 a4[4];
+              float4 a4[4], m4[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
+              for (int k = 0; k < 4; ++k) {
+                a4[k] = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
+                const int m = row_base + rr + k;
+                m4[k] = (mbase != nullptr && m < m_valid)
+                            ? *reinterpret_cast<const float4*>(mbase + static_cast<long long>(m) * p.ldm)
+                            : make_float4(1.f, 1.f, 1.f, 1.f);
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int m = row_base + rr + k;
                 float v0 = fmaf(a4[k].x, alpha, b4.x), v1 = fmaf(a4[k].y, alpha, b4.y);
                 float v2 = fmaf(a4[k].z, alpha, b4.z), v3 = fmaf(a4[k].w, alpha, b4.w);
+                if (!(m4[k].x > 0.f)) v0 = 0.f;   // ReLU backward: zero where the forward activation was <= 0
+                if (!(m4[k].y > 0.f)) v1 = 0.f;
+                if (!(m4[k].z > 0.f)) v2 = 0.f;
+                if (!(m4[k].w > 0.f)) v3 = 0.f;
                 if (act == ACT_RELU) {
                   v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
                 } else if (act == ACT_LEAKY) {

@@ -35,18 +35,18 @@ constexpr unsigned LS_SPIN_LIMIT = 1u << 22;  // bounded polling: a lost hand-of
 
 // forward
 constexpr int LSF_KB = 9;                     // 64-wide k-blocks over K = 530 (padded to 576)
-constexpr int LSF_STAGES = 2;
+constexpr int LSF_STAGES = 3;
 constexpr int LSF_W_BYTES = LSF_KB * 128 * 128;
 constexpr int LSF_STG_BYTES = 8 * 32 * LS_STG_LD * 4;
 constexpr int LSF_SMEM = LSF_W_BYTES + LSF_STAGES * LS_A_STAGE + LSF_STG_BYTES + 256 + 1024;
 constexpr int LSF_THREADS = 64 + 256;
 // backward
 constexpr int LSB_KB = 34;                    // 64-wide k-blocks over K = 2120 (padded to 2176)
-constexpr int LSB_STAGES = 3;
+constexpr int LSB_STAGES = 4;
 constexpr int LSB_W_BYTES = LSB_KB * 32 * 128;
 constexpr int LSB_STG_BYTES = 4 * 32 * LS_STG_LD * 4;
 constexpr int LSB_SMEM = LSB_W_BYTES + LSB_STAGES * LS_A_STAGE + LSB_STG_BYTES + 256 + 1024;
-constexpr int LSB_THREADS = 64 + 128;
+constexpr int LSB_THREADS = 64 + 256;
 constexpr int LSB_NBUF = 4;                   // TMEM accumulator buffers (32 columns each)
 
 struct LstmFwdParams {
@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
         }
     } else {
       // ------------------------------------------------------------------ epilogue: LSTM cell (8 warps)
+      // Order of the global stores: the fp16 h slice the OTHER CTAs are waiting for goes out first, is fenced and
+      // published; gates / cell state / fp32 h (read by later kernels and by this thread only) follow, so their
+      // store traffic overlaps the next step's hand-off instead of sitting in front of the fence.
       const int q = warp & 3, hf = (warp - 2) >> 2;      // TMEM lane quarter, column half
       float* stg = stg_all + (warp - 2) * 32 * LS_STG_LD;
       const int rsub = lane >> 3, ul = lane & 7;         // coalesced pass: 4 rows x 8 units per instruction
@@ -276,8 +279,9 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
           const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);   // rows to write (zeros beyond count)
           // x-part pre-activations and c_{t-1} of both column passes: issued BEFORE waiting for the accumulator, so
           // that their L2 / HBM latency hides behind the hand-off wait and the MMAs of this step
-          float4 x4[2][8];
-          float cp[2][8];
+          float4 x4[2][8];      // becomes the gate activations (i, f, g, o) in place
+          float cp[2][8];       // becomes c_t in place
+          float hn[2][8];
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;
@@ -303,41 +307,57 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
             __syncwarp();
             const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;   // gate column of this lane's unit
             const int unit = col0 >> 2;
-            if (col0 < G) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = i * 4 + rsub, rt = q * 32 + row, m = mt * 128 + rt;
-                if (rt >= rows_tile) continue;
-                const long long rg = static_cast<long long>(e) * p.cap + m;
-                const long long r9 = rg * 9 + t;
-                float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
-                if (m < count) {
-                  const float* a = stg + row * LS_STG_LD + 4 * ul;
-                  gi = ls_sigmoid(a[0] + x4[pass][i].x);
-                  gf = ls_sigmoid(a[1] + x4[pass][i].y);
-                  gg = ls_tanh(a[2] + x4[pass][i].z);
-                  go = ls_sigmoid(a[3] + x4[pass][i].w);
-                  cn = fmaf(gf, cp[pass][i], gi * gg);
-                  hn = go * ls_tanh(cn);
-                }
-                *reinterpret_cast<float4*>(p.G9 + r9 * G + col0) = make_float4(gi, gf, gg, go);
-                p.C9[(r9 + 1) * LDF + unit] = cn;
-                p.H9[(r9 + 1) * LDF + unit] = hn;
-                reinterpret_cast<unsigned short*>(p.H16)[(rg * 2 + ((t + 1) & 1)) * LS_LDH16 + unit] = f2h_sat_bits(hn);
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rsub, rt = q * 32 + row, m = mt * 128 + rt;
+              float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, h = 0.f;
+              if (m < count && col0 < G) {
+                const float* a = stg + row * LS_STG_LD + 4 * ul;
+                gi = ls_sigmoid(a[0] + x4[pass][i].x);
+                gf = ls_sigmoid(a[1] + x4[pass][i].y);
+                gg = ls_tanh(a[2] + x4[pass][i].z);
+                go = ls_sigmoid(a[3] + x4[pass][i].w);
+                cn = fmaf(gf, cp[pass][i], gi * gg);
+                h = go * ls_tanh(cn);
               }
+              x4[pass][i] = make_float4(gi, gf, gg, go);
+              cp[pass][i] = cn;
+              hn[pass][i] = h;
+              if (rt < rows_tile && col0 < G)
+                reinterpret_cast<unsigned short*>(p.H16)[((static_cast<long long>(e) * p.cap + m) * 2 + ((t + 1) & 1)) *
+                                                             LS_LDH16 + unit] = f2h_sat_bits(h);
             }
             __syncwarp();
           }
           tc_fence_before();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (mt == n_mt - 1) {
+            // publish h_t of this slice (all row tiles): stores -> fences -> barrier of the epilogue warps -> release
+            if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
+            __threadfence();
+            fence_proxy_async_all();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+            if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
+          }
+          // the tensors kept for the backward pass and the weight-gradient GEMMs
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;
+            const int unit = col0 >> 2;
+            if (col0 < G) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rt = q * 32 + i * 4 + rsub, m = mt * 128 + rt;
+                if (rt >= rows_tile) continue;
+                const long long r9 = (static_cast<long long>(e) * p.cap + m) * 9 + t;
+                *reinterpret_cast<float4*>(p.G9 + r9 * G + col0) = x4[pass][i];
+                p.C9[(r9 + 1) * LDF + unit] = cp[pass][i];
+                p.H9[(r9 + 1) * LDF + unit] = hn[pass][i];
+              }
+            }
+          }
         }
-        // publish h_t of this slice (all row tiles): stores -> fences -> barrier of the epilogue warps -> release
-        if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
-        __threadfence();
-        fence_proxy_async_all();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
-        if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
       }
     }
   }
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
     }
     for (int b = 0; b < LSB_NBUF; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], 8);      // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -475,96 +495,112 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
           if (dbg && lane == 0) dbg[t * 8 + 3] = clock64();
         }
     } else {
-      // ------------------------------------------------------------------ epilogue: LSTM cell backward (4 warps)
-      const int q = warp & 3;
-      float* stg = stg_all + (warp - 2) * 32 * LS_STG_LD;
+      // ------------------------------------------------------------------ epilogue: LSTM cell backward (8 warps)
+      // Two warps per TMEM lane quarter: each drains 16 accumulator columns into the quarter's staging tile, then owns
+      // 16 of its 32 rows with lane = hidden unit. Everything the pointwise derivative needs besides dh (gates, c_{t-1},
+      // c_t, running dc) is loaded BEFORE the accumulator wait; of the results only the fp16 dG slice the other CTAs
+      // wait for is stored ahead of the fence + publish, the fp32 dG / dc stores follow.
+      const int q = warp & 3, hf = (warp - 2) >> 2;
+      float* stg = stg_all + q * 32 * LS_STG_LD;         // shared by the quarter's two warps
       const int unit = u0 + lane;
       const bool unit_ok = unit < F;
+      const int qbar = 2 + q;                             // named barrier of the quarter (64 threads)
       uint32_t tile = 0;                                  // accumulator tiles consumed so far
       float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dG over this warp's rows, all tiles and steps
       for (int t = 7; t >= 0; --t) {
         for (int mt = 0; mt < n_mt; ++mt) {
           const bool from_acc = t < 7;
-          uint32_t buf = 0;
+          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);
+          const int rt0 = q * 32 + hf * 16;               // this warp's first row inside the tile
+          float4 g4[16];                                  // gates (i, f, g, o); becomes dG in place
+          float cprev[16], ct[16], dcin[16], dh[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int m = mt * 128 + rt0 + i;
+            const bool ok = unit_ok && m < count;
+            const long long rg = static_cast<long long>(e) * p.cap + m;
+            const long long r9 = rg * 9 + t;
+            g4[i] = ok ? *reinterpret_cast<const float4*>(p.G9 + r9 * G + 4 * unit) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cprev[i] = ok ? p.C9[r9 * LDF + unit] : 0.f;
+            ct[i] = ok ? p.C9[(r9 + 1) * LDF + unit] : 0.f;
+            dcin[i] = (ok && from_acc) ? p.dC[rg * LDF + unit] : 0.f;
+            dh[i] = (ok && !from_acc) ? p.dH8[rg * LDF + unit] : 0.f;
+          }
           if (from_acc) {
-            buf = tile % LSB_NBUF;
+            const uint32_t buf = tile % LSB_NBUF;
             mbar_wait(&acc_full[buf], (tile / LSB_NBUF) & 1);
             tc_fence_after();
             if (dbg && threadIdx.x == 64 && mt == 0) dbg[t * 8 + 4] = clock64();
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32, r);
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32 + hf * 16, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) stg[lane * LS_STG_LD + c] = __uint_as_float(r[c]);
-            __syncwarp();
+            for (int c = 0; c < 16; ++c) stg[lane * LS_STG_LD + hf * 16 + c] = __uint_as_float(r[c]);
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);  // registers -> staging done: the buffer may be refilled
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);  // registers hold the columns: the buffer may be refilled
             ++tile;
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");   // both halves of the quarter are staged
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dh[i] = stg[(hf * 16 + i) * LS_STG_LD + lane] * p.inv_scale;
           }
-          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);
-          // lane = unit, the warp walks its 32 rows in batches of 8 (all loads of a batch in flight together)
-#pragma unroll 1
-          for (int rb = 0; rb < 32; rb += 8) {
-            float4 g4[8];
-            float cprev[8], ct[8], dh[8], dcin[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rt = q * 32 + rb + i, m = mt * 128 + rt;
-              const bool ok = unit_ok && m < count;
-              const long long rg = static_cast<long long>(e) * p.cap + m;
-              const long long r9 = rg * 9 + t;
-              g4[i] = ok ? *reinterpret_cast<const float4*>(p.G9 + r9 * G + 4 * unit) : make_float4(0.f, 0.f, 0.f, 0.f);
-              cprev[i] = ok ? p.C9[r9 * LDF + unit] : 0.f;
-              ct[i] = ok ? p.C9[(r9 + 1) * LDF + unit] : 0.f;
-              dh[i] = !ok ? 0.f : (from_acc ? stg[(rb + i) * LS_STG_LD + lane] * p.inv_scale : p.dH8[rg * LDF + unit]);
-              dcin[i] = (ok && from_acc) ? p.dC[rg * LDF + unit] : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            const int rt = rt0 + i, m = mt * 128 + rt;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dcp = 0.f;
+            if (unit_ok && m < count) {
+              const float4 g = g4[i];            // i, f, g, o
+              const float tc = ls_tanh(ct[i]);
+              const float dc = fmaf(dh[i] * g.w, 1.f - tc * tc, dcin[i]);
+              d = make_float4(dc * g.z * g.x * (1.f - g.x), dc * cprev[i] * g.y * (1.f - g.y),
+                              dc * g.x * (1.f - g.z * g.z), dh[i] * tc * g.w * (1.f - g.w));
+              dcp = dc * g.y;
+              bias_acc.x += d.x, bias_acc.y += d.y, bias_acc.z += d.z, bias_acc.w += d.w;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rt = q * 32 + rb + i, m = mt * 128 + rt;
-              if (rt >= rows_tile || !unit_ok) continue;
-              const long long rg = static_cast<long long>(e) * p.cap + m;
-              const long long r9 = rg * 9 + t;
-              float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m < count) {
-                const float4 g = g4[i];            // i, f, g, o
-                const float tc = tanhf(ct[i]);
-                const float dc = fmaf(dh[i] * g.w, 1.f - tc * tc, dcin[i]);
-                d = make_float4(dc * g.z * g.x * (1.f - g.x), dc * cprev[i] * g.y * (1.f - g.y),
-                                dc * g.x * (1.f - g.z * g.z), dh[i] * tc * g.w * (1.f - g.w));
-                p.dC[rg * LDF + unit] = dc * g.y;
-                bias_acc.x += d.x, bias_acc.y += d.y, bias_acc.z += d.z, bias_acc.w += d.w;
-              }
-              *reinterpret_cast<float4*>(p.dG9 + r9 * G + 4 * unit) = d;
+            g4[i] = d;
+            dcin[i] = dcp;
+            if (unit_ok && rt < rows_tile && t > 0) {
               uint2 hbits;
               hbits.x = static_cast<uint32_t>(f2h_sat_bits(d.x * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.y * p.scale)) << 16);
               hbits.y = static_cast<uint32_t>(f2h_sat_bits(d.z * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.w * p.scale)) << 16);
-              *reinterpret_cast<uint2*>(p.dG16 + (rg * 2 + (t & 1)) * LS_LDG16 + 4 * unit) = hbits;
+              *reinterpret_cast<uint2*>(p.dG16 + ((static_cast<long long>(e) * p.cap + m) * 2 + (t & 1)) * LS_LDG16 +
+                                        4 * unit) = hbits;
             }
           }
-          __syncwarp();                                   // staging is reused by the next tile
-        }
-        if (t > 0) {   // publish dG_t of this slice; nobody consumes dG_0
-          if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
-          __threadfence();
-          fence_proxy_async_all();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
-          if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
+          if (mt == n_mt - 1 && t > 0) {   // publish dG_t of this slice (all row tiles); nobody consumes dG_0
+            if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
+            __threadfence();
+            fence_proxy_async_all();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+            if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
+          } else if (from_acc) {
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");   // staging is rewritten by the next tile
+          }
+          if (unit_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int rt = rt0 + i, m = mt * 128 + rt;
+              if (rt >= rows_tile) continue;
+              const long long rg = static_cast<long long>(e) * p.cap + m;
+              *reinterpret_cast<float4*>(p.dG9 + (rg * 9 + t) * G + 4 * unit) = g4[i];
+              if (m < count) p.dC[rg * LDF + unit] = dcin[i];
+            }
+          }
         }
       }
       // LSTM bias gradients: d loss / d b_ih = d loss / d b_hh = sum over rows and steps of dG (models.py:133-137).
-      // Fixed summation order (rows of a warp in sequence, then the four warps in order): deterministic.
-      float4* red = reinterpret_cast<float4*>(stg_all);   // staging is free now: [4 warps][32 lanes]
-      __syncwarp();
+      // Fixed summation order (rows of a warp in sequence, then the eight warps in order): deterministic.
+      float4* red = reinterpret_cast<float4*>(stg_all);   // staging is free now: [8 warps][32 lanes]
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       red[(warp - 2) * 32 + lane] = bias_acc;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && unit_ok) {
         float4 s4 = red[lane];
 #pragma unroll
-        for (int w = 1; w < 4; ++w) {
+        for (int w = 1; w < 8; ++w) {
           const float4 o = red[w * 32 + lane];
           s4.x += o.x, s4.y += o.y, s4.z += o.z, s4.w += o.w;
         }

@@ -28,8 +28,8 @@ namespace cadre {
 
 constexpr int LS_SLICES = 17;                 // ceil(2120 / 128) = ceil(530 / 32)
 constexpr int LS_A_STAGE = 128 * 128;         // one A k-block: 128 rows x 64 halves
-constexpr int LS_LDH16 = 544;                 // row pitch (halves) of the fp16 h exchange buffer  [E][cap][2][544]
-constexpr int LS_LDG16 = 2176;                // row pitch (halves) of the fp16 dG exchange buffer [E][cap][2][2176]
+constexpr int LS_LDH16 = 544;                 // row pitch (halves) of the fp16 x / h tensors  [E][cap][9][544]
+constexpr int LS_LDG16 = 2176;                // row pitch (halves) of the fp16 dG tensor      [E][cap][9][2176]
 constexpr int LS_STG_LD = 33;                 // fp32 staging pitch (conflict-free row and column access)
 constexpr unsigned LS_SPIN_LIMIT = 1u << 22;  // bounded polling: a lost hand-off raises an error flag instead of hanging
 
@@ -50,13 +50,14 @@ constexpr int LSB_THREADS = 64 + 256;
 constexpr int LSB_NBUF = 4;                   // TMEM accumulator buffers (32 columns each)
 
 struct LstmFwdParams {
-  CUtensorMap tmH;        // H16 as {k = 530, row = cap, buf = 2, expert = 8}, box {64, 128, 1, 1}, 128B swizzle
+  CUtensorMap tmH;        // H16 as {k = 530, row = cap, slot = 9, expert = 8}, box {64, 128, 1, 1}, 128B swizzle
   const float* params;    // flat parameter buffer (W_hh at OFF_WHH, gate-interleaved rows)
   const float* XP9;       // [E][cap][9][G]   x_t W_ih^T + b_ih + b_hh
-  float* G9;              // [E][cap][9][G]   gate activations (i, f, g, o per unit), kept for the backward pass
+  __half* G16;            // [E][cap][9][G]   gate activations (i, f, g, o per unit), kept for the backward pass
   float* C9;              // [E][cap][9][LDF] slot t holds c_{t-1}
-  float* H9;              // [E][cap][9][LDF] slot t holds h_{t-1}
-  __half* H16;            // [E][cap][2][LS_LDH16] h_t in buffer t & 1 (buffer 0 initialised with h_{-1} by the gather)
+  float* H8;              // [E][cap][LDF]    h_8 in fp32: input of the actor / critic heads
+  __half* H16;            // [E][cap][9][LS_LDH16] slot t holds h_{t-1} (slot 0 written by the gather): the recurrent
+                          // GEMM's A operand of step t and the W_hh weight-gradient GEMM's B operand
   const int* counts;      // [E] routed rows per expert
   unsigned* sync;         // [E] arrival counters (zero at launch), [E] = error flag
   int cap;
@@ -64,12 +65,12 @@ struct LstmFwdParams {
 };
 
 struct LstmBwdParams {
-  CUtensorMap tmDG;       // dG16 as {k = 2176, row = cap, buf = 2, expert = 8}, box {64, 128, 1, 1}
+  CUtensorMap tmDG;       // dG16 as {k = 2176, row = cap, slot = 9, expert = 8}, box {64, 128, 1, 1}
   const float* params;
-  const float* G9;
+  const __half* G16;
   const float* C9;
-  float* dG9;             // [E][cap][9][G]  d loss / d gate pre-activations (fp32, for the weight-gradient GEMMs)
-  __half* dG16;           // [E][cap][2][LS_LDG16] scale * dG_t in buffer t & 1
+  __half* dG16;           // [E][cap][9][LS_LDG16] slot t holds scale * dG_t (d loss / d gate pre-activations): A operand
+                          // of the recurrent dgrad GEMM of step t and of both LSTM weight-gradient GEMMs
   const float* dH8;       // [E][cap][LDF]   d loss / d h_8 (from the first-layer dgrad GEMM)
   float* dC;              // [E][cap][LDF]   running d loss / d c
   const int* counts;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
             mbar_wait(&empty[s], ((it / LSF_STAGES) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&full[s], LS_A_STAGE);
-              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmH, &full[s], kb * 64, mt * 128, t & 1, e);
+              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmH, &full[s], kb * 64, mt * 128, t, e);
             }
             __syncwarp();
           }
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
               cp[pass][i] = cn;
               hn[pass][i] = h;
               if (rt < rows_tile && col0 < G)
-                reinterpret_cast<unsigned short*>(p.H16)[((static_cast<long long>(e) * p.cap + m) * 2 + ((t + 1) & 1)) *
+                reinterpret_cast<unsigned short*>(p.H16)[((static_cast<long long>(e) * p.cap + m) * 9 + t + 1) *
                                                              LS_LDH16 + unit] = f2h_sat_bits(h);
             }
             __syncwarp();
@@ -332,12 +333,15 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
           tc_fence_before();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
           if (mt == n_mt - 1) {
-            // publish h_t of this slice (all row tiles): stores -> fences -> barrier of the epilogue warps -> release
+            // publish h_t of this slice (all row tiles): barrier of the epilogue warps, then ONE thread fences
+            // (cumulative over the writes it observed through the barrier) and releases the counter
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
-            __threadfence();
-            fence_proxy_async_all();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+            if (threadIdx.x == 64) {
+              __threadfence();
+              fence_proxy_async_all();
+              red_release_add_u32(ctr, 1u);
+            }
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
           }
           // the tensors kept for the backward pass and the weight-gradient GEMMs
@@ -350,10 +354,15 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
               for (int i = 0; i < 8; ++i) {
                 const int rt = q * 32 + i * 4 + rsub, m = mt * 128 + rt;
                 if (rt >= rows_tile) continue;
-                const long long r9 = (static_cast<long long>(e) * p.cap + m) * 9 + t;
-                *reinterpret_cast<float4*>(p.G9 + r9 * G + col0) = x4[pass][i];
+                const long long rg = static_cast<long long>(e) * p.cap + m;
+                const long long r9 = rg * 9 + t;
+                const float4 g = x4[pass][i];
+                uint2 gb;      // gates in (-1, 1): fp16 keeps an absolute error <= 2.5e-4
+                gb.x = static_cast<uint32_t>(f2h_sat_bits(g.x)) | (static_cast<uint32_t>(f2h_sat_bits(g.y)) << 16);
+                gb.y = static_cast<uint32_t>(f2h_sat_bits(g.z)) | (static_cast<uint32_t>(f2h_sat_bits(g.w)) << 16);
+                *reinterpret_cast<uint2*>(p.G16 + r9 * G + col0) = gb;
                 p.C9[(r9 + 1) * LDF + unit] = cp[pass][i];
-                p.H9[(r9 + 1) * LDF + unit] = hn[pass][i];
+                if (t == 7) p.H8[rg * LDF + unit] = hn[pass][i];
               }
             }
           }
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             mbar_wait(&empty[s], ((it / LSB_STAGES) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&full[s], LS_A_STAGE);
-              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmDG, &full[s], kb * 64, mt * 128, t & 1, e);
+              tma_load_4d(a_s + s * LS_A_STAGE, &p.tmDG, &full[s], kb * 64, mt * 128, t, e);
             }
             __syncwarp();
           }
@@ -520,7 +529,13 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             const bool ok = unit_ok && m < count;
             const long long rg = static_cast<long long>(e) * p.cap + m;
             const long long r9 = rg * 9 + t;
-            g4[i] = ok ? *reinterpret_cast<const float4*>(p.G9 + r9 * G + 4 * unit) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+              const uint2 gb = *reinterpret_cast<const uint2*>(p.G16 + r9 * G + 4 * unit);
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&gb.x));
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&gb.y));
+              g4[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
             cprev[i] = ok ? p.C9[r9 * LDF + unit] : 0.f;
             ct[i] = ok ? p.C9[(r9 + 1) * LDF + unit] : 0.f;
             dcin[i] = (ok && from_acc) ? p.dC[rg * LDF + unit] : 0.f;
@@ -559,34 +574,33 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             }
             g4[i] = d;
             dcin[i] = dcp;
-            if (unit_ok && rt < rows_tile && t > 0) {
+            if (unit_ok && rt < rows_tile) {
               uint2 hbits;
               hbits.x = static_cast<uint32_t>(f2h_sat_bits(d.x * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.y * p.scale)) << 16);
               hbits.y = static_cast<uint32_t>(f2h_sat_bits(d.z * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.w * p.scale)) << 16);
-              *reinterpret_cast<uint2*>(p.dG16 + ((static_cast<long long>(e) * p.cap + m) * 2 + (t & 1)) * LS_LDG16 +
+              *reinterpret_cast<uint2*>(p.dG16 + ((static_cast<long long>(e) * p.cap + m) * 9 + t) * LS_LDG16 +
                                         4 * unit) = hbits;
             }
           }
-          if (mt == n_mt - 1 && t > 0) {   // publish dG_t of this slice (all row tiles); nobody consumes dG_0
+          if (mt == n_mt - 1 && t > 0) {   // publish dG_t of this slice (all row tiles); no CTA waits for dG_0
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
-            __threadfence();
-            fence_proxy_async_all();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) red_release_add_u32(ctr, 1u);
+            if (threadIdx.x == 64) {
+              __threadfence();
+              fence_proxy_async_all();
+              red_release_add_u32(ctr, 1u);
+            }
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
           } else if (from_acc) {
             asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");   // staging is rewritten by the next tile
           }
-          if (unit_ok) {
+          if (unit_ok && t > 0) {   // running d loss / d c for the next (earlier) step
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int rt = rt0 + i, m = mt * 128 + rt;
-              if (rt >= rows_tile) continue;
-              const long long rg = static_cast<long long>(e) * p.cap + m;
-              *reinterpret_cast<float4*>(p.dG9 + (rg * 9 + t) * G + 4 * unit) = g4[i];
-              if (m < count) p.dC[rg * LDF + unit] = dcin[i];
+              const int m = mt * 128 + rt0 + i;
+              if (m < count) p.dC[(static_cast<long long>(e) * p.cap + m) * LDF + unit] = dcin[i];
             }
           }
         }

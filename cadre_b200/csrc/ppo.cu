@@ -6,10 +6,15 @@
 // gradient, 4x less work). Rows of a head are stably sorted by command into per-expert slots
 // (expert e = head*4 + command); all eight experts run as one grid.z-batched tcgen05 GEMM per layer / step.
 //
-// Time-expanded buffers use 9 time slots per row ("x9" layout [E][cap][9][ld]): slot j<8 of X9 holds x_j, slot j
-// of H9 / C9 holds h_{j-1} / c_{j-1} (j = 0 is the stored recurrent state hn/cn), slot j<8 of G9 / dG9 holds the
-// gate activations / pre-activation gradients of step j and slot 8 of dG9 stays zero. With that layout the
-// weight gradients of all eight steps are single GEMMs over K = 9*rows: dW_ih = dG9^T X9, dW_hh = dG9^T H9.
+// Time-expanded buffers use 9 time slots per row ("x9" layout [E][cap][9][ld]): slot j<8 of X holds x_j, slot j of
+// H / C holds h_{j-1} / c_{j-1} (j = 0 is the stored recurrent state hn/cn), slot j<8 of G / dG holds the gate
+// activations / pre-activation gradients of step j and slot 8 of dG stays zero. With that layout the weight
+// gradients of all eight steps are single GEMMs over K = 9*rows: dW_ih = dG^T X, dW_hh = dG^T H.
+// Precision of the stored tensors: the cell state C (the recurrence's only long accumulation) and the x-part
+// pre-activations stay fp32; h, the gate activations and dG are stored ONCE, as fp16 (11-bit significand like the
+// TF32 operands of the other GEMMs; dG scaled by a power of two): they are tensor-core operands (recurrent GEMMs,
+// weight-gradient GEMMs) or bounded activations in (-1, 1), and halving their bytes is what the L2-bound recurrence
+// and weight-gradient kernels are made of.
 #include "../../include/cadre_b200.h"
 #include "internal.h"
 #include "ptx.cuh"
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
                                                    const int* __restrict__ idx, int W, int mb, int cap,
                                                    const int* __restrict__ row_slot,
                                                    const int* __restrict__ row_expert, float* __restrict__ X9,
-                                                   float* __restrict__ H9, float* __restrict__ C9,
+                                                   __half* __restrict__ X16, float* __restrict__ C9,
                                                    __half* __restrict__ H16, RowScalars sc) {
   pdl_trigger();
   pdl_wait();
@@ -111,18 +116,18 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
   const int e = row_expert[h * R + r], slot = row_slot[h * R + r];
   const long long row = static_cast<long long>(e) * cap + slot;
   const float* obs = ref.obs + static_cast<long long>(t) * 8 * F;
-  float* x = X9 + row * 9 * LDF;
+  float* x = X9 + row * 9 * LDF;             // fp32: A operand of the x-part GEMM (TF32)
+  __half* x16 = X16 + row * 9 * LS_LDH16;    // fp16: B operand of the W_ih weight-gradient GEMM
   for (int k = threadIdx.x; k < 8 * F; k += 256) {
     const int j = k / F, f = k - j * F;
-    x[j * LDF + f] = obs[k];
+    const float v = obs[k];
+    x[j * LDF + f] = v;
+    x16[j * LS_LDH16 + f] = __float2half_rn(v);
   }
-  float* h0 = H9 + row * 9 * LDF;
   float* c0 = C9 + row * 9 * LDF;
-  __half* h16 = H16 + row * 2 * LS_LDH16;   // buffer 0 of the recurrence kernel's fp16 exchange: h_{-1}
+  __half* h16 = H16 + row * 9 * LS_LDH16;    // slot 0: h_{-1}
   for (int f = threadIdx.x; f < F; f += 256) {
-    const float hv = ref.hn[static_cast<long long>(t) * F + f];
-    h0[f] = hv;
-    h16[f] = __float2half_rn(hv);
+    h16[f] = __float2half_rn(ref.hn[static_cast<long long>(t) * F + f]);
     c0[f] = ref.cn[static_cast<long long>(t) * F + f];
   }
   if (threadIdx.x == 0) {
@@ -138,12 +143,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
 // b_ih + b_hh (one bias vector for the x-part GEMM) and the compacted work list of that GEMM: (expert, 128-row tile)
 // pairs covering the 9 * count[e] valid rows of each expert, so that its grid is sized by the rows that exist
 // (2 * 9 * R / 128 + 8 tiles at most) instead of by the per-expert capacity (8 * 9 * cap / 128).
+// It also clears the K padding of the weight-gradient GEMMs: those run over K = 9 * count rows rounded up to a whole
+// 64-row k-block, i.e. they read up to 8 rows past the routed ones. The BPTT kernel writes zeros up to the next
+// multiple of 32 rows only, so dG rows [count, count + 8) are zeroed here (stale rows of an earlier update with more
+// rows for this expert would otherwise leak into the gradient).
+constexpr int WGRAD_PAD_ROWS = 8;
 __global__ void prep_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n,
-                            const int* __restrict__ counts9, int* __restrict__ tile_list, int max_tiles) {
+                            const int* __restrict__ counts9, int* __restrict__ tile_list, int max_tiles,
+                            __half* __restrict__ dG16, int cap) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
+  {
+    constexpr int V = 9 * LS_LDG16 / 8;                       // uint4 per row (all 9 slots)
+    const long long total = static_cast<long long>(E) * WGRAD_PAD_ROWS * V;
+    for (long long k = i; k < total; k += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int e = static_cast<int>(k / (WGRAD_PAD_ROWS * V));
+      const int rr = static_cast<int>((k / V) % WGRAD_PAD_ROWS), v = static_cast<int>(k % V);
+      const int row = counts9[e] / 9 + rr;
+      if (row < cap)
+        reinterpret_cast<uint4*>(dG16 + (static_cast<long long>(e) * cap + row) * 9 * LS_LDG16)[v] =
+            make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   if (i == 0) {
     int nt = 0;
     for (int e = 0; e < E; ++e) {
@@ -177,7 +200,6 @@ constexpr int HEAD_MAX_W = 64;   // workers per engine the loss reduction is siz
 // per-CTA partial: dW3A [33][128], dW3C [128], dB3A [36], dB3C [4], losses [HEAD_MAX_W][3]
 constexpr int HP_W3A = 0, HP_W3C = AMAX * HID, HP_B3A = HP_W3C + HID, HP_B3C = HP_B3A + B3A_LD, HP_LOSS = HP_B3C + 4;
 constexpr int HEAD_PARTIAL = HP_LOSS + HEAD_MAX_W * 3;
-constexpr int DGRAD_SPLIT = 4;  // maximum split-K factor of the recurrent dgrad GEMMs (K = 2120); see PpoPlan::dgrad_split
 
 // Every sum of this kernel has a FIXED order (rows of a CTA in sequence, CTAs of an expert by block index, experts of
 // a head by index), so losses and last-layer gradients are bit-reproducible from run to run: each CTA writes its
@@ -471,45 +493,6 @@ __global__ void __launch_bounds__(256) head_eval_kernel(const float* __restrict_
   if (lane + 32 < A) o[3 + lane + 32] = lp1;
 }
 
-// ------------------------------------------------------------------------------------------ LSTM backward
-// Pointwise part of BPTT for step t (inverse of the LSTM-cell epilogue in tc_gemm.cuh):
-//   dc  = dc_next + dh * o * (1 - tanh(c_t)^2)
-//   di = dc*g*i(1-i)   df = dc*c_{t-1}*f(1-f)   dg = dc*i*(1-g^2)   do = dh*tanh(c_t)*o(1-o)   dc_prev = dc*f
-__global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__ dH, float* __restrict__ dC,
-                                                       const float* __restrict__ G9,
-                                                       const float* __restrict__ C9, float* __restrict__ dG9,
-                                                       const int* __restrict__ counts, int cap, int t,
-                                                       int first, int nsplit, long long split_stride) {
-  pdl_trigger();
-  pdl_wait();
-  const int e = blockIdx.y;
-  const int count = counts[e];
-  const int rows_pad = min(cap, (count + 31) & ~31);
-  // grid.x blocks per expert stride over the (slot, unit) cells that exist: no block is launched for the
-  // unused part of the capacity (the grid used to cover cap rows: 8 480 blocks, most of them exiting at once)
-  const long long cells = static_cast<long long>(rows_pad) * F;
-  for (long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gid < cells;
-       gid += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int slot = static_cast<int>(gid / F), u = static_cast<int>(gid - static_cast<long long>(slot) * F);
-    const long long row = static_cast<long long>(e) * cap + slot;
-    float4* dg = reinterpret_cast<float4*>(dG9 + (row * 9 + t) * G) + u;
-    if (slot >= count) {
-      *dg = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    const float4 g = *(reinterpret_cast<const float4*>(G9 + (row * 9 + t) * G) + u);  // i, f, g, o
-    const float c_prev = C9[(row * 9 + t) * LDF + u], c_t = C9[(row * 9 + t + 1) * LDF + u];
-    float dh = dH[row * LDF + u];  // split-K partial sums of the previous step's dgrad GEMM
-    for (int k = 1; k < nsplit; ++k) dh += dH[k * split_stride + row * LDF + u];
-    const float tc = tanhf(c_t);
-    float dc = dh * g.w * (1.f - tc * tc);
-    if (!first) dc += dC[row * LDF + u];
-    *dg = make_float4(dc * g.z * g.x * (1.f - g.x), dc * c_prev * g.y * (1.f - g.y), dc * g.x * (1.f - g.z * g.z),
-                      dh * tc * g.w * (1.f - g.w));
-    dC[row * LDF + u] = dc * g.y;
-  }
-}
-
 // column sums over the valid rows of each expert (bias gradients); deterministic
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, long long ld,
                                                      long long src_bs, const int* __restrict__ rows, int N,
@@ -542,16 +525,16 @@ struct PpoPlan {
   cadre_ppo_config cfg;
   int cap = 0, R = 0;
   // device buffers
-  float *X9 = nullptr, *XP9 = nullptr, *G9 = nullptr, *dG9 = nullptr, *H9 = nullptr, *C9 = nullptr;
+  float *X9 = nullptr, *XP9 = nullptr, *C9 = nullptr, *H8 = nullptr;   // H8 [E][cap][LDF]: h_8, input of the heads
   float *Y1 = nullptr, *Y2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dH = nullptr, *dC = nullptr;
   float* bsum = nullptr;
-  // persistent recurrence kernels (lstm_seq.cuh): fp16 exchange buffers, hand-off counters, prebuilt tensor maps
-  __half *H16 = nullptr, *dG16 = nullptr;
+  // fp16 tensors in the 9-slot layout (see the file header) + hand-off counters and prebuilt tensor maps of the
+  // persistent recurrence kernels (lstm_seq.cuh)
+  __half *X16 = nullptr, *H16 = nullptr, *G16 = nullptr, *dG16 = nullptr;
   float *head_partial = nullptr, *head_loss_e = nullptr;   // head_kernel scratch (ordered reductions)
   unsigned* seq_sync = nullptr;          // [0, E]: forward counters + error flag, [16, 16 + E]: backward, [32, 32 + E]: head
   CUtensorMap tmH, tmDG;
   float bwd_scale = 1.f;
-  bool use_seq = true;
   RowScalars sc{};
   int *row_slot = nullptr, *row_expert = nullptr, *counts = nullptr, *counts9 = nullptr;
   int* idx_dev = nullptr;
@@ -560,10 +543,9 @@ struct PpoPlan {
   StorageRef* refs_dev = nullptr;
   OptTables opt;
   int launches = 0;
-  int dgrad_split = DGRAD_SPLIT;
   // side stream for the gradient kernels that are off the critical path (dW2, dW1, bias column sums)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_bptt = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_wih = nullptr;   // recorded when the W_ih block of the gradient (the first 36 MB) is final
   bool use_side = true;
 };
@@ -585,43 +567,35 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   const size_t rows = static_cast<size_t>(E) * P->cap;
   P->X9 = dalloc<float>(rows * 9 * LDF);
   P->XP9 = dalloc<float>(rows * 9 * G);
-  P->G9 = dalloc<float>(rows * 9 * G);
-  P->dG9 = dalloc<float>(rows * 9 * G);
-  P->H9 = dalloc<float>(rows * 9 * LDF);
+  P->H8 = dalloc<float>(rows * LDF);
   P->C9 = dalloc<float>(rows * 9 * LDF);
   P->Y1 = dalloc<float>(rows * 2 * HID);
   P->Y2 = dalloc<float>(rows * 2 * HID);
   P->dZ1 = dalloc<float>(rows * 2 * HID);
   P->dZ2 = dalloc<float>(rows * 2 * HID);
-  P->dH = dalloc<float>(rows * LDF * DGRAD_SPLIT);
-  {
-    // split 4 -> 160 working CTAs at cfg 3; measured on B200: PPO update 9.26 ms (split 4), 9.55 (3), 9.78 (2)
-    int ks = DGRAD_SPLIT;
-    if (const char* ev = getenv("CADRE_DGRAD_SPLIT")) ks = atoi(ev) < 1 ? 1 : (atoi(ev) > DGRAD_SPLIT ? DGRAD_SPLIT : atoi(ev));
-    P->dgrad_split = ks;
-  }
+  P->dH = dalloc<float>(rows * LDF);
   P->use_side = getenv("CADRE_PPO_NO_SIDE_STREAM") == nullptr;
   CADRE_CUDA_CHECK(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
-  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_bptt, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wih, cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
-  P->use_seq = getenv("CADRE_PPO_STEP_KERNELS") == nullptr;   // A/B switch: one launch per LSTM step (round-1 path)
-  P->H16 = dalloc<__half>(rows * 2 * LS_LDH16);
-  P->dG16 = dalloc<__half>(rows * 2 * LS_LDG16);
+  P->X16 = dalloc<__half>(rows * 9 * LS_LDH16);
+  P->H16 = dalloc<__half>(rows * 9 * LS_LDH16);
+  P->G16 = dalloc<__half>(rows * 9 * G);
+  P->dG16 = dalloc<__half>(rows * 9 * LS_LDG16);
   P->seq_sync = dalloc<unsigned>(64);
   CADRE_REQUIRE(cfg->workers <= HEAD_MAX_W, "at most 64 workers per engine");
   P->head_partial = dalloc<float>(static_cast<size_t>(E) * (P->cap / HEAD_ROWS_PER_CTA) * HEAD_PARTIAL);
   P->head_loss_e = dalloc<float>(static_cast<size_t>(E) * HEAD_MAX_W * 3);
   {
-    const uint64_t dims_h[4] = {(uint64_t)F, (uint64_t)P->cap, 2, (uint64_t)E};
-    const uint64_t str_h[3] = {2ull * LS_LDH16 * 2, 1ull * LS_LDH16 * 2, (uint64_t)P->cap * 2 * LS_LDH16 * 2};
+    const uint64_t dims_h[4] = {(uint64_t)F, (uint64_t)P->cap, 9, (uint64_t)E};
+    const uint64_t str_h[3] = {9ull * LS_LDH16 * 2, 1ull * LS_LDH16 * 2, (uint64_t)P->cap * 9 * LS_LDH16 * 2};
     const uint32_t box[4] = {64, 128, 1, 1};
     make_tensor_map_f16(&P->tmH, 4, P->H16, dims_h, str_h, box);
-    const uint64_t dims_g[4] = {(uint64_t)LS_LDG16, (uint64_t)P->cap, 2, (uint64_t)E};
-    const uint64_t str_g[3] = {2ull * LS_LDG16 * 2, 1ull * LS_LDG16 * 2, (uint64_t)P->cap * 2 * LS_LDG16 * 2};
+    const uint64_t dims_g[4] = {(uint64_t)LS_LDG16, (uint64_t)P->cap, 9, (uint64_t)E};
+    const uint64_t str_g[3] = {9ull * LS_LDG16 * 2, 1ull * LS_LDG16 * 2, (uint64_t)P->cap * 9 * LS_LDG16 * 2};
     make_tensor_map_f16(&P->tmDG, 4, P->dG16, dims_g, str_g, box);
     // backward operands are scaled by 2^(ceil(log2(mini_batch)) + 4): the loss seeds carry a 1/mini_batch factor
     int lg = 0;
@@ -698,14 +672,13 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
 
 static void ppo_destroy(PpoPlan* P) {
   if (!P) return;
-  void* ptrs[] = {P->head_partial, P->head_loss_e, P->H16, P->dG16, P->seq_sync, P->X9, P->XP9, P->G9, P->dG9, P->H9, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
+  void* ptrs[] = {P->head_partial, P->head_loss_e, P->X16, P->H16, P->G16, P->dG16, P->seq_sync, P->X9, P->XP9, P->H8, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
                   P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
                   P->row_expert, P->counts, P->counts9, P->idx_dev, P->xp_tiles, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
                   P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
   for (void* p : ptrs) cudaFree(p);
   if (P->side) cudaStreamDestroy(P->side);
   if (P->ev_fork) cudaEventDestroy(P->ev_fork);
-  if (P->ev_bptt) cudaEventDestroy(P->ev_bptt);
   if (P->ev_join) cudaEventDestroy(P->ev_join);
   if (P->ev_wih) cudaEventDestroy(P->ev_wih);
   delete P;
@@ -731,9 +704,9 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
                                   P->counts9), ++n;
   launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
-                                         P->X9, P->H9, P->C9, P->H16, P->sc), ++n;
+                                         P->X9, P->X16, P->C9, P->H16, P->sc), ++n;
   launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G,
-           P->counts9, P->xp_tiles, P->xp_max_tiles), ++n;
+           P->counts9, P->xp_tiles, P->xp_max_tiles, P->dG16, cap), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
   // ---- forward
@@ -748,29 +721,17 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.tile_list = P->xp_tiles, g.max_tiles = P->xp_max_tiles;
     launch_gemm(g, s), ++n;
   }
-  if (P->use_seq) {   // models.py:146-151: the 8 sequential LSTMCell steps in ONE persistent launch (lstm_seq.cuh)
+  {   // models.py:146-151: the 8 sequential LSTMCell steps in ONE persistent launch (lstm_seq.cuh)
     LstmFwdParams q;
-    q.tmH = P->tmH, q.params = params, q.XP9 = P->XP9, q.G9 = P->G9, q.C9 = P->C9, q.H9 = P->H9, q.H16 = P->H16;
+    q.tmH = P->tmH, q.params = params, q.XP9 = P->XP9, q.G16 = P->G16, q.C9 = P->C9, q.H8 = P->H8, q.H16 = P->H16;
     q.counts = P->counts, q.sync = P->seq_sync, q.cap = cap;
     q.dbg = g_dbg_clk;
     launch_k(lstm_seq_fwd_kernel, dim3(LS_SLICES, E), dim3(LSF_THREADS), LSF_SMEM, s, q), ++n;
     CADRE_CUDA_CHECK(cudaGetLastError());
-  } else
-  for (int t = 0; t < 8; ++t) {
-    GemmArgs g = tf32_gemm(0, 0);
-    g.epi = 1;
-    g.A = P->H9 + t * LDF, g.lda = 9 * LDF, g.a_bs = rs9F;
-    g.B = params + OFF_WHH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
-    g.M = cap, g.N = G, g.K = F;
-    g.xpart = P->XP9 + t * G, g.gates_out = P->G9 + t * G, g.ldx = 9 * G, g.x_bs = rs9G;
-    g.c_prev = P->C9 + t * LDF, g.c_out = P->C9 + (t + 1) * LDF, g.h_out = P->H9 + (t + 1) * LDF;
-    g.ldh = 9 * LDF, g.h_bs = rs9F;
-    g.batch_rows = P->counts;
-    launch_gemm(g, s), ++n;
   }
   {  // first actor + critic layers share the input h_8: one N = 256 GEMM
     GemmArgs g = tf32_gemm(0, 0);
-    g.A = P->H9 + 8 * LDF, g.lda = 9 * LDF, g.a_bs = rs9F;
+    g.A = P->H8, g.lda = LDF, g.a_bs = static_cast<long long>(cap) * LDF;
     g.B = params + OFF_W1, g.ldb = LDF, g.b_bs = 2LL * HID * LDF;
     g.M = cap, g.N = 2 * HID, g.K = F;
     g.out = P->Y1, g.ldc = 2 * HID, g.out_bs = static_cast<long long>(cap) * 2 * HID;
@@ -794,7 +755,6 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
 static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host, float* params,
                        float* grads, float* losses, cudaStream_t s) {
   const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap;
-  const long long rs9F = static_cast<long long>(cap) * 9 * LDF, rs9G = static_cast<long long>(cap) * 9 * G;
   CADRE_CUDA_CHECK(cudaMemsetAsync(losses, 0, sizeof(float) * W * 2 * 3, s));
   CADRE_CUDA_CHECK(cudaMemsetAsync(grads + OFF_W3A, 0, sizeof(float) * (TOTAL - OFF_W3A), s));
   int n = ppo_forward(P, refs_host, idx_host, params, s);
@@ -848,7 +808,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   {  // dW1 = dZ1^T h_8
     GemmArgs g = tf32_gemm(1, 1);
     g.A = P->dZ1, g.lda = 2 * HID, g.a_bs = bs256;
-    g.B = P->H9 + 8 * LDF, g.ldb = 9 * LDF, g.b_bs = rs9F;
+    g.B = P->H8, g.ldb = LDF, g.b_bs = static_cast<long long>(cap) * LDF;
     g.M = 2 * HID, g.N = F, g.K = cap;
     g.out = grads + OFF_W1, g.ldc = LDF, g.out_bs = 2LL * HID * LDF;
     g.batch_rows = P->counts, g.rows_is_k = 1;
@@ -863,48 +823,25 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
     g.batch_rows = P->counts;
     launch_gemm(g, s), ++n;
   }
-  const unsigned bwd_full = static_cast<unsigned>((static_cast<long long>(cap) * F + 255) / 256);
-  const unsigned bwd_blocks = bwd_full < 74u ? bwd_full : 74u;   // x 8 experts = 4 blocks per SM, grid-stride inside
-  const long long dh_split_stride = static_cast<long long>(E) * cap * LDF;
-  if (P->use_seq) {   // BPTT: 8 x (LSTM-cell backward, dh_{t-1} = dG_t W_hh) in ONE persistent launch
+  {   // BPTT: 8 x (LSTM-cell backward, dh_{t-1} = dG_t W_hh) in ONE persistent launch; it also produces the LSTM
+      // bias gradients (column sums of dG)
     LstmBwdParams q;
-    q.tmDG = P->tmDG, q.params = params, q.G9 = P->G9, q.C9 = P->C9, q.dG9 = P->dG9, q.dG16 = P->dG16;
+    q.tmDG = P->tmDG, q.params = params, q.G16 = P->G16, q.C9 = P->C9, q.dG16 = P->dG16;
     q.dH8 = P->dH, q.dC = P->dC, q.counts = P->counts, q.sync = P->seq_sync + 16, q.cap = cap;
     q.scale = P->bwd_scale, q.inv_scale = 1.f / P->bwd_scale;
     q.grads = grads;
     q.dbg = g_dbg_clk ? g_dbg_clk + E * LS_SLICES * 72 : nullptr;
     launch_k(lstm_seq_bwd_kernel, dim3(LS_SLICES, E), dim3(LSB_THREADS), LSB_SMEM, s, q), ++n;
-  } else
-  for (int t = 7; t >= 0; --t) {
-    launch_k(lstm_bwd_kernel, dim3(dim3(bwd_blocks, E)), dim3(256), 0, s, P->dH, P->dC, P->G9, P->C9, P->dG9, P->counts, cap, t,
-                                                        t == 7, t == 7 ? 1 : P->dgrad_split, dh_split_stride),
-        ++n;
-    if (t > 0) {  // dh_{t-1} = dG_t W_hh
-      GemmArgs g = tf32_gemm(0, 1);
-      g.A = P->dG9 + t * G, g.lda = 9 * G, g.a_bs = rs9G;
-      g.B = params + OFF_WHH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
-      g.M = cap, g.N = F, g.K = G;
-      g.out = P->dH, g.ldc = LDF, g.out_bs = static_cast<long long>(cap) * LDF;
-      g.batch_rows = P->counts;
-      g.ksplit = P->dgrad_split, g.split_out_stride = dh_split_stride;  // lstm_bwd sums the partials
-      launch_gemm(g, s), ++n;
-    }
   }
   CADRE_CUDA_CHECK(cudaGetLastError());
-  if (!P->use_seq) {   // (the persistent BPTT kernel accumulates the LSTM bias gradients itself)
-    if (P->use_side) {   // dG9 is complete: its column sums run next to the weight-gradient GEMMs
-      CADRE_CUDA_CHECK(cudaEventRecord(P->ev_bptt, s));
-      CADRE_CUDA_CHECK(cudaStreamWaitEvent(s2, P->ev_bptt, 0));
-    }
-    launch_k(colsum_kernel, dim3(dim3((G + 31) / 32, E)), dim3(256), 0, s2, P->dG9, G, rs9G, P->counts9, G, grads + OFF_BIH, G,
-                                                         grads + OFF_BHH), ++n;
-  }
   if (P->use_side) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_join, s2));
-  for (int which = 0; which < 2; ++which) {  // dW_ih = dG9^T X9, dW_hh = dG9^T H9 (K = 9 * rows)
-    GemmArgs g = tf32_gemm(1, 1);
-    g.A = P->dG9, g.lda = G, g.a_bs = rs9G;
-    g.B = which ? P->H9 : P->X9, g.ldb = LDF, g.b_bs = rs9F;
+  for (int which = 0; which < 2; ++which) {  // dW_ih = dG^T X, dW_hh = dG^T H (K = 9 * rows), fp16 operands
+    GemmArgs g;
+    g.kind = 0, g.a_mn = 1, g.b_mn = 1, g.batch = E, g.out_f32 = 1, g.block_n = 128;
+    g.A = P->dG16, g.lda = LS_LDG16, g.a_bs = static_cast<long long>(cap) * 9 * LS_LDG16;
+    g.B = which ? P->H16 : P->X16, g.ldb = LS_LDH16, g.b_bs = static_cast<long long>(cap) * 9 * LS_LDH16;
     g.M = G, g.N = F, g.K = 9 * cap;
+    g.alpha = 1.f / P->bwd_scale;      // dG16 holds scale * dG
     g.out = grads + (which ? OFF_WHH : OFF_WIH), g.ldc = LDF, g.out_bs = static_cast<long long>(G) * LDF;
     g.batch_rows = P->counts9, g.rows_is_k = 1;
     launch_gemm(g, s), ++n;

@@ -159,14 +159,12 @@ static void fill_epilogue(TcGemmParams& p, const GemmArgs& a) {
   p.batch_rows = a.batch_rows, p.rows_is_k = a.rows_is_k;
   p.tile_list = a.tile_list;
   p.dbg_a_shift = a.dbg_a_shift, p.dbg_base_offset = a.dbg_base_offset, p.dbg_clk = a.dbg_clk, p.dbg_epi = a.dbg_epi;
-  p.xpart = a.xpart, p.ldx = a.ldx, p.x_bs = a.x_bs;
-  p.c_prev = a.c_prev, p.c_out = a.c_out, p.h_out = a.h_out, p.gates_out = a.gates_out;
-  p.ldh = a.ldh, p.h_bs = a.h_bs;
 }
 
 void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_REQUIRE(a.M > 0 && a.N > 0 && a.K >= 0 && a.batch > 0, "gemm dims");
-  CADRE_REQUIRE(a.A && a.B && (a.out || a.epi == EPI_LSTM), "gemm pointers");
+  CADRE_REQUIRE(a.A && a.B && a.out, "gemm pointers");
+  CADRE_REQUIRE(a.epi == EPI_LINEAR, "the LSTM-cell epilogue moved into the persistent recurrence kernels (lstm_seq.cuh)");
   const int es = a.kind ? 4 : 2;
   const int bk = 128 / es;
   int bn = a.block_n ? a.block_n : (a.N <= 64 ? 64 : 128);
@@ -230,28 +228,14 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(0, 0, 0, 128, 4, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(0, 0, 1, 128, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(0, 1, 1, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 1, 1, 128, 3, EPI_LINEAR, 1, float)   // PPO LSTM weight gradients (fp16 dG^T x / h): 2 CTAs per SM
   // fp32 operands as TF32 (PPO update: forward, dgrad, wgrad, LSTM cell)
   // the PPO GEMMs are latency-bound (few CTAs, short 128-byte k-blocks): deep pipelines, one CTA per SM
-  static const bool tf32_deep = getenv("CADRE_TF32_DEEP") != nullptr;  // A/B: one CTA per SM, 6-stage pipeline
-  if (tf32_deep) {
-    CADRE_GEMM_CASE(1, 0, 0, 64, 8, EPI_LINEAR, 1, float)
-    CADRE_GEMM_CASE(1, 0, 0, 128, 6, EPI_LINEAR, 1, float)
-    CADRE_GEMM_CASE(1, 0, 1, 128, 6, EPI_LINEAR, 1, float)
-    CADRE_GEMM_CASE(1, 1, 1, 128, 6, EPI_LINEAR, 1, float)
-    CADRE_GEMM_CASE(1, 0, 0, 128, 6, EPI_LSTM, 1, float)
-  }
   // default: 3 stages (97 KB) -> two CTAs per SM
   CADRE_GEMM_CASE(1, 0, 0, 64, 4, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(1, 0, 1, 128, 3, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(1, 1, 1, 128, 3, EPI_LINEAR, 1, float)
-  static const bool lstm_ew1 = getenv("CADRE_LSTM_EW1") != nullptr;   // A/B: four epilogue warps for the LSTM cell
-  if (a.kind == 1 && !a.a_mn && !a.b_mn && bn == 128 && a.epi == EPI_LSTM && a.out_f32 == 1 && !lstm_ew1) {
-    launch_inst<1, 0, 0, 128, 4, MODE_GEMM, EPI_LSTM, float, 2>(p, grid, stream);   // 8 epilogue warps, 1 CTA / SM
-    return;
-  }
-  CADRE_GEMM_CASE(1, 0, 0, 128, 3, EPI_LSTM, 1, float)
 #undef CADRE_GEMM_CASE
   throw Error(1, "launch_gemm: unsupported (kind, majors, block_n, epilogue, out dtype) combination");
 }

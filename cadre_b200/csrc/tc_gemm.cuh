@@ -13,7 +13,7 @@
 namespace cadre {
 
 enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_STEM = 2 };
-enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
+enum { EPI_LINEAR = 0 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
 struct ConvTap {
@@ -50,14 +50,6 @@ struct TcGemmParams {
   // optional compacted work list (device): tile_list[0] = n, then n pairs (batch, m_tile). blockIdx.x indexes the
   // list (grid.z = 1): no CTA is launched for the unused part of a batch's row capacity
   const int* tile_list;
-  // EPI_LSTM: acc = h_{t-1} W_hh^T (gate-interleaved columns 4*u+g); xpart holds x_t W_ih^T + b_ih + b_hh
-  const float* xpart;
-  long long ldx, x_bs;
-  const float* c_prev;
-  float* c_out;
-  float* h_out;
-  float* gates_out;
-  long long ldh, h_bs;
 };
 
 template <int KIND, int BLOCK_N, int STAGES>
@@ -72,10 +64,6 @@ struct TcGemmSmem {
   static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
   static constexpr int TOTAL = DATA_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
-
-// exp-based gates with the hardware ex2 path (__expf: ~2 ulp) — far inside the TF32 noise of the pre-activations
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 template <typename OutT>
 __device__ __forceinline__ float load_as_float(const void* base, long long idx) {
@@ -408,52 +396,6 @@ __global__ void __launch_bounds__(64 + 128 * EW) tc_gemm_kernel(const __grid_con
                     o[i] = enc_from_float(v[i]);
                 }
               }
-            }
-          }
-        } else {
-          // EPI_LSTM: nn.LSTMCell pointwise part (ppo_agent/models.py:139-152 -> torch LSTMCell, gate order
-          // i,f,g,o); columns are gate-interleaved, so this lane's 4 columns are the four gates of unit u.
-          const int u = n >> 2;
-          const float* xbase = p.xpart + batch * p.x_bs + n;
-          float* gbase = p.gates_out + batch * p.x_bs + n;
-          const float* cpbase = p.c_prev + batch * p.h_bs + u;
-          float* cobase = p.c_out + batch * p.h_bs + u;
-          float* hobase = p.h_out + batch * p.h_bs + u;
-          const bool zero_rows = (p.batch_rows != nullptr);
-          // 16 rows per batch: all of a batch's global loads (x-part gates, c_{t-1}: HBM latency, the x-part is
-          // 122 MB) are in flight together. With two rows per batch the 16 exposed round trips made this
-          // epilogue 30 k cycles, longer than the GEMM main loop (in-situ clock64 stamps, B200).
-          constexpr int RB = 16;
-#pragma unroll 1
-          for (int rr = r_lo; rr < r_hi; rr += RB) {
-            float4 x4[RB];
-            float cp[RB];
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-              const int m = row_base + rr + k;
-              const bool ok = m < m_valid;
-              x4[k] = ok ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(m) * p.ldx)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-              cp[k] = ok ? cpbase[static_cast<long long>(m) * p.ldh] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-              const long long m = row_base + rr + k;
-              const bool ok = m < m_valid;
-              if (!(ok || (zero_rows && m < p.M))) continue;
-              float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, hn = 0.f;
-              if (ok) {
-                const float4 a4 = *reinterpret_cast<const float4*>(srow + (rr + k) * LDS);
-                gi = sigmoidf_(a4.x + x4[k].x);
-                gf = sigmoidf_(a4.y + x4[k].y);
-                gg = tanhf_(a4.z + x4[k].z);
-                go = sigmoidf_(a4.w + x4[k].w);
-                cn = fmaf(gf, cp[k], gi * gg);
-                hn = go * tanhf_(cn);
-              }
-              *reinterpret_cast<float4*>(gbase + m * p.ldx) = make_float4(gi, gf, gg, go);
-              cobase[m * p.ldh] = cn;
-              hobase[m * p.ldh] = hn;
             }
           }
         }

@@ -267,37 +267,54 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
         }
     } else {
       // ------------------------------------------------------------------ epilogue: LSTM cell (8 warps)
-      // Order of the global stores: the fp16 h slice the OTHER CTAs are waiting for goes out first, is fenced and
-      // published; gates / cell state / fp32 h (read by later kernels and by this thread only) follow, so their
-      // store traffic overlaps the next step's hand-off instead of sitting in front of the fence.
+      // Order of the global stores: the fp16 h slice the OTHER CTAs are waiting for goes out first and is published;
+      // gates / cell state (read by later kernels and by this thread only) follow, so their store traffic overlaps
+      // the next step's hand-off. The epilogue is instruction-issue bound (4096 cells per CTA and step), so every
+      // address is a per-thread base pointer plus a compile-time multiple of the 4-row stride, and row validity is
+      // two bit masks.
       const int q = warp & 3, hf = (warp - 2) >> 2;      // TMEM lane quarter, column half
       float* stg = stg_all + (warp - 2) * 32 * LS_STG_LD;
       const int rsub = lane >> 3, ul = lane & 7;         // coalesced pass: 4 rows x 8 units per instruction
+      const int colA = n0 + hf * 64 + 4 * ul;            // gate column of this lane's unit in pass 0 (+32 in pass 1)
+      const bool colok[2] = {colA < G, colA + 32 < G};
+      constexpr long long S_G = 4LL * 9 * G, S_C = 4LL * 9 * LDF, S_H16 = 4LL * 9 * LS_LDH16, S_H8 = 4LL * LDF;
+      const float* stg_rd = stg + rsub * LS_STG_LD + 4 * ul;
       uint32_t tile = 0;
       for (int t = 0; t < 8; ++t) {
         for (int mt = 0; mt < n_mt; ++mt, ++tile) {
           const uint32_t buf = tile & 1;
-          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);   // rows to write (zeros beyond count)
-          // x-part pre-activations and c_{t-1} of both column passes: issued BEFORE waiting for the accumulator, so
-          // that their L2 / HBM latency hides behind the hand-off wait and the MMAs of this step
-          float4 x4[2][8];      // becomes the gate activations (i, f, g, o) in place
-          float cp[2][8];       // becomes c_t in place
-          float hn[2][8];
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;
+          const int m0 = mt * 128 + q * 32 + rsub;       // this lane's first row; row i is m0 + 4 i
+          const long long rg0 = static_cast<long long>(e) * p.cap + m0;
+          // bit i: row m0 + 4 i is a routed row / has to be written (zeros up to the next multiple of 32 rows)
+          uint32_t ok_mask = 0, wr_mask = 0;
+          {
+            const int wr_end = (count + 31) & ~31;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int m = mt * 128 + q * 32 + i * 4 + rsub;
-              const long long r9 = (static_cast<long long>(e) * p.cap + m) * 9 + t;
-              const bool ok = m < count && col0 < G;
-              x4[pass][i] = ok ? *reinterpret_cast<const float4*>(p.XP9 + r9 * G + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-              cp[pass][i] = ok ? p.C9[r9 * LDF + (col0 >> 2)] : 0.f;
+              ok_mask |= (m0 + 4 * i < count ? 1u : 0u) << i;
+              wr_mask |= (m0 + 4 * i < wr_end ? 1u : 0u) << i;
             }
           }
+          const float* xp_p = p.XP9 + (rg0 * 9 + t) * G + colA;
+          float* c_p = p.C9 + (rg0 * 9 + t) * LDF + (colA >> 2);
+          // x-part pre-activations and c_{t-1} of both column passes: issued BEFORE waiting for the accumulator, so
+          // that their L2 / HBM latency hides behind the hand-off wait and the MMAs of this step
+          float4 x4[2][8];
+          float cp[2][8];       // becomes c_t in place
+          uint2 gb[2][8];       // gate activations (i, f, g, o) as fp16
+          float h8[2][8];
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = ((ok_mask >> i) & 1u) && colok[pass];
+              x4[pass][i] = ok ? *reinterpret_cast<const float4*>(xp_p + i * S_G + pass * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cp[pass][i] = ok ? c_p[i * S_C + pass * 8] : 0.f;
+            }
           mbar_wait(&acc_full[buf], (tile >> 1) & 1);
           tc_fence_after();
           if (dbg && threadIdx.x == 64) dbg[t * 8 + 4] = clock64();
+          unsigned short* h16_p = reinterpret_cast<unsigned short*>(p.H16) + (rg0 * 9 + t + 1) * LS_LDH16 + (colA >> 2);
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             uint32_t r[32];
@@ -306,14 +323,11 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
 #pragma unroll
             for (int c = 0; c < 32; ++c) stg[lane * LS_STG_LD + c] = __uint_as_float(r[c]);
             __syncwarp();
-            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;   // gate column of this lane's unit
-            const int unit = col0 >> 2;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rsub, rt = q * 32 + row, m = mt * 128 + rt;
               float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, cn = 0.f, h = 0.f;
-              if (m < count && col0 < G) {
-                const float* a = stg + row * LS_STG_LD + 4 * ul;
+              if (((ok_mask >> i) & 1u) && colok[pass]) {
+                const float* a = stg_rd + i * 4 * LS_STG_LD;
                 gi = ls_sigmoid(a[0] + x4[pass][i].x);
                 gf = ls_sigmoid(a[1] + x4[pass][i].y);
                 gg = ls_tanh(a[2] + x4[pass][i].z);
@@ -321,51 +335,42 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
                 cn = fmaf(gf, cp[pass][i], gi * gg);
                 h = go * ls_tanh(cn);
               }
-              x4[pass][i] = make_float4(gi, gf, gg, go);
+              // gates in (-1, 1): fp16 keeps an absolute error <= 2.5e-4
+              gb[pass][i].x = static_cast<uint32_t>(f2h_sat_bits(gi)) | (static_cast<uint32_t>(f2h_sat_bits(gf)) << 16);
+              gb[pass][i].y = static_cast<uint32_t>(f2h_sat_bits(gg)) | (static_cast<uint32_t>(f2h_sat_bits(go)) << 16);
               cp[pass][i] = cn;
-              hn[pass][i] = h;
-              if (rt < rows_tile && col0 < G)
-                reinterpret_cast<unsigned short*>(p.H16)[((static_cast<long long>(e) * p.cap + m) * 9 + t + 1) *
-                                                             LS_LDH16 + unit] = f2h_sat_bits(h);
+              h8[pass][i] = h;
+              if (((wr_mask >> i) & 1u) && colok[pass]) h16_p[i * S_H16 + pass * 8] = f2h_sat_bits(h);
             }
             __syncwarp();
           }
           tc_fence_before();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
           if (mt == n_mt - 1) {
-            // publish h_t of this slice (all row tiles): barrier of the epilogue warps, then ONE thread fences
-            // (cumulative over the writes it observed through the barrier) and releases the counter
+            // publish h_t of this slice (all row tiles): barrier of the epilogue warps, then ONE thread releases the
+            // counter. red.release.gpu orders every write this thread observed through the barrier (cumulativity)
+            // before the increment; the generic -> async proxy fence covers the consumers' TMA reads.
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) {
-              __threadfence();
               fence_proxy_async_all();
               red_release_add_u32(ctr, 1u);
             }
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 6] = clock64();
           }
-          // the tensors kept for the backward pass and the weight-gradient GEMMs
+          // the tensors kept for the backward pass (and h_8, the input of the heads)
+          __half* g16_p = p.G16 + (rg0 * 9 + t) * G + colA;
+          float* h8_p = p.H8 + rg0 * LDF + (colA >> 2);
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int col0 = n0 + hf * 64 + pass * 32 + 4 * ul;
-            const int unit = col0 >> 2;
-            if (col0 < G) {
+          for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int rt = q * 32 + i * 4 + rsub, m = mt * 128 + rt;
-                if (rt >= rows_tile) continue;
-                const long long rg = static_cast<long long>(e) * p.cap + m;
-                const long long r9 = rg * 9 + t;
-                const float4 g = x4[pass][i];
-                uint2 gb;      // gates in (-1, 1): fp16 keeps an absolute error <= 2.5e-4
-                gb.x = static_cast<uint32_t>(f2h_sat_bits(g.x)) | (static_cast<uint32_t>(f2h_sat_bits(g.y)) << 16);
-                gb.y = static_cast<uint32_t>(f2h_sat_bits(g.z)) | (static_cast<uint32_t>(f2h_sat_bits(g.w)) << 16);
-                *reinterpret_cast<uint2*>(p.G16 + r9 * G + col0) = gb;
-                p.C9[(r9 + 1) * LDF + unit] = cp[pass][i];
-                if (t == 7) p.H8[rg * LDF + unit] = hn[pass][i];
-              }
+            for (int i = 0; i < 8; ++i) {
+              if (!(((wr_mask >> i) & 1u) && colok[pass])) continue;
+              *reinterpret_cast<uint2*>(g16_p + i * S_G + pass * 32) = gb[pass][i];
+              c_p[(i * S_C + pass * 8) + LDF] = cp[pass][i];          // slot t + 1
+              if (t == 7) h8_p[i * S_H8 + pass * 8] = h8[pass][i];
             }
-          }
+          if (dbg && threadIdx.x == 64) dbg[t * 8 + 7] = clock64();
         }
       }
     }
@@ -516,30 +521,40 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
       const int qbar = 2 + q;                             // named barrier of the quarter (64 threads)
       uint32_t tile = 0;                                  // accumulator tiles consumed so far
       float4 bias_acc = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dG over this warp's rows, all tiles and steps
+      constexpr long long R_G = 9LL * G, R_C = 9LL * LDF, R_DG = 9LL * LS_LDG16;   // element strides between rows
+      const int rt0 = q * 32 + hf * 16;                   // this warp's first row inside a tile
+      const float* stg_rd = stg + hf * 16 * LS_STG_LD + lane;
       for (int t = 7; t >= 0; --t) {
         for (int mt = 0; mt < n_mt; ++mt) {
           const bool from_acc = t < 7;
-          const int rows_tile = min(128, ((count + 31) & ~31) - mt * 128);
-          const int rt0 = q * 32 + hf * 16;               // this warp's first row inside the tile
-          float4 g4[16];                                  // gates (i, f, g, o); becomes dG in place
+          const int m0 = mt * 128 + rt0;                  // rows m0 .. m0 + 15
+          const long long rg0 = static_cast<long long>(e) * p.cap + m0;
+          uint32_t ok_mask = 0, wr_mask = 0;              // bit i: row m0 + i is routed / must be written (zeros)
+          if (unit_ok) {
+            const int wr_end = (count + 31) & ~31;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              ok_mask |= (m0 + i < count ? 1u : 0u) << i;
+              wr_mask |= (m0 + i < wr_end ? 1u : 0u) << i;
+            }
+          }
+          const __half* g_p = p.G16 + (rg0 * 9 + t) * G + 4 * unit;
+          const float* c_p = p.C9 + (rg0 * 9 + t) * LDF + unit;
+          float* dc_p = p.dC + rg0 * LDF + unit;
+          float4 g4[16];                                  // gates (i, f, g, o)
           float cprev[16], ct[16], dcin[16], dh[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int m = mt * 128 + rt0 + i;
-            const bool ok = unit_ok && m < count;
-            const long long rg = static_cast<long long>(e) * p.cap + m;
-            const long long r9 = rg * 9 + t;
-            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-              const uint2 gb = *reinterpret_cast<const uint2*>(p.G16 + r9 * G + 4 * unit);
-              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&gb.x));
-              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&gb.y));
-              g4[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
-            }
-            cprev[i] = ok ? p.C9[r9 * LDF + unit] : 0.f;
-            ct[i] = ok ? p.C9[(r9 + 1) * LDF + unit] : 0.f;
-            dcin[i] = (ok && from_acc) ? p.dC[rg * LDF + unit] : 0.f;
-            dh[i] = (ok && !from_acc) ? p.dH8[rg * LDF + unit] : 0.f;
+            const bool ok = (ok_mask >> i) & 1u;
+            uint2 gb = make_uint2(0u, 0u);
+            if (ok) gb = *reinterpret_cast<const uint2*>(g_p + i * R_G);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&gb.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&gb.y));
+            g4[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            cprev[i] = ok ? c_p[i * R_C] : 0.f;
+            ct[i] = ok ? c_p[i * R_C + LDF] : 0.f;
+            dcin[i] = (ok && from_acc) ? dc_p[i * LDF] : 0.f;
+            dh[i] = (ok && !from_acc) ? p.dH8[(rg0 + i) * LDF + unit] : 0.f;
           }
           if (from_acc) {
             const uint32_t buf = tile % LSB_NBUF;
@@ -556,39 +571,37 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
             ++tile;
             asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");   // both halves of the quarter are staged
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dh[i] = stg[(hf * 16 + i) * LS_STG_LD + lane] * p.inv_scale;
+            for (int i = 0; i < 16; ++i) dh[i] = stg_rd[i * LS_STG_LD] * p.inv_scale;
           }
+          __half* dg_p = p.dG16 + (rg0 * 9 + t) * LS_LDG16 + 4 * unit;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int rt = rt0 + i, m = mt * 128 + rt;
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
             float dcp = 0.f;
-            if (unit_ok && m < count) {
+            if ((ok_mask >> i) & 1u) {
               const float4 g = g4[i];            // i, f, g, o
               const float tc = ls_tanh(ct[i]);
-              const float dc = fmaf(dh[i] * g.w, 1.f - tc * tc, dcin[i]);
+              const float dho = dh[i] * g.w;
+              const float dc = fmaf(dho, 1.f - tc * tc, dcin[i]);
               d = make_float4(dc * g.z * g.x * (1.f - g.x), dc * cprev[i] * g.y * (1.f - g.y),
-                              dc * g.x * (1.f - g.z * g.z), dh[i] * tc * g.w * (1.f - g.w));
+                              dc * g.x * (1.f - g.z * g.z), dho * tc * (1.f - g.w));
               dcp = dc * g.y;
               bias_acc.x += d.x, bias_acc.y += d.y, bias_acc.z += d.z, bias_acc.w += d.w;
             }
-            g4[i] = d;
             dcin[i] = dcp;
-            if (unit_ok && rt < rows_tile) {
+            if ((wr_mask >> i) & 1u) {
               uint2 hbits;
               hbits.x = static_cast<uint32_t>(f2h_sat_bits(d.x * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.y * p.scale)) << 16);
               hbits.y = static_cast<uint32_t>(f2h_sat_bits(d.z * p.scale)) |
                         (static_cast<uint32_t>(f2h_sat_bits(d.w * p.scale)) << 16);
-              *reinterpret_cast<uint2*>(p.dG16 + ((static_cast<long long>(e) * p.cap + m) * 9 + t) * LS_LDG16 +
-                                        4 * unit) = hbits;
+              *reinterpret_cast<uint2*>(dg_p + i * R_DG) = hbits;
             }
           }
           if (mt == n_mt - 1 && t > 0) {   // publish dG_t of this slice (all row tiles); no CTA waits for dG_0
             if (dbg && threadIdx.x == 64) dbg[t * 8 + 5] = clock64();
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x == 64) {
-              __threadfence();
+            if (threadIdx.x == 64) {       // release: see the forward kernel
               fence_proxy_async_all();
               red_release_add_u32(ctr, 1u);
             }
@@ -596,13 +609,12 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
           } else if (from_acc) {
             asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");   // staging is rewritten by the next tile
           }
-          if (unit_ok && t > 0) {   // running d loss / d c for the next (earlier) step
+          if (t > 0) {   // running d loss / d c for the next (earlier) step
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int m = mt * 128 + rt0 + i;
-              if (m < count) p.dC[(static_cast<long long>(e) * p.cap + m) * LDF + unit] = dcin[i];
-            }
+            for (int i = 0; i < 16; ++i)
+              if ((ok_mask >> i) & 1u) dc_p[i * LDF] = dcin[i];
           }
+          if (dbg && threadIdx.x == 64) dbg[t * 8 + 7] = clock64();
         }
       }
       // LSTM bias gradients: d loss / d b_ih = d loss / d b_hh = sum over rows and steps of dG (models.py:133-137).

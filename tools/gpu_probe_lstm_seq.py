@@ -1,7 +1,7 @@
 """Per-step cycle breakdown of the persistent LSTM recurrence kernels (lstm_seq.cuh) inside a real PPO update
 (W=4, mb=100): clock64 stamps written by one thread per role (cadre_debug_clk). Per CTA and step t:
   0 producer enters step | 1 hand-off counter reached | 2 last TMA load issued | 3 last MMA committed |
-  4 epilogue sees the accumulator | 5 epilogue stores issued | 6 slice published
+  4 epilogue sees the accumulator | 5 exchange slice stored | 6 slice published | 7 remaining stores issued
 and per CTA: 64 kernel start | 65 weights resident | 66 griddepcontrol.wait returned."""
 import ctypes, os, statistics, sys
 import torch
@@ -67,6 +67,7 @@ for d, name, steps in ((0, "forward", range(0, 8)), (1, "backward", range(7, 0, 
             "epilogue sees acc after MMA commit": s[:, 4] - s[:, 3],
             "epilogue compute+stores": s[:, 5] - s[:, 4],
             "fence+publish": s[:, 6] - s[:, 5],
+            "bulk stores": s[:, 7] - s[:, 6],
             "step (producer enter -> publish)": s[:, 6] - s[:, 0],
         }
         print(f"  t={t}: " + " | ".join(f"{n} {med(v.tolist()) / MHZ:6.2f}" for n, v in row.items()))

@@ -8,6 +8,8 @@
 //   * forward  : CTA (e, j) owns gate columns [128 j, 128 j + 128) = hidden units [32 j, 32 j + 32): its W_hh rows as
 //                fp16 [128 x 576] (147 KB, K zero-padded 530 -> 576) in the canonical 128B-swizzled K-major layout;
 //   * backward : CTA (e, j) owns hidden units [32 j, 32 j + 32) of dh: W_hh[:, units] transposed, fp16 [32 x 2176];
+//     (both slices arrive by TMA from fp16 copies of W_hh that wcvt_kernel (ppo.cu) refreshes at the start of every
+//     update, concurrently with the routing kernels);
 //   * per step the A operand (h_{t-1}, resp. dG_t, all rows of the expert, fp16) streams from L2 through a TMA ring,
 //     tcgen05.mma (kind::f16, fp32 accumulation in TMEM) produces the CTA's slice, the epilogue warps apply the LSTM
 //     cell (resp. its derivative) and write the next step's operand slice back to global memory;
@@ -51,7 +53,7 @@ constexpr int LSB_NBUF = 4;                   // TMEM accumulator buffers (32 co
 
 struct LstmFwdParams {
   CUtensorMap tmH;        // H16 as {k = 530, row = cap, slot = 9, expert = 8}, box {64, 128, 1, 1}, 128B swizzle
-  const float* params;    // flat parameter buffer (W_hh at OFF_WHH, gate-interleaved rows)
+  CUtensorMap tmW;        // W_hh as fp16 [E][G][544] {k = 530, gate row = 2120, expert}, box {64, 128, 1}
   const float* XP9;       // [E][cap][9][G]   x_t W_ih^T + b_ih + b_hh
   __half* G16;            // [E][cap][9][G]   gate activations (i, f, g, o per unit), kept for the backward pass
   float* C9;              // [E][cap][9][LDF] slot t holds c_{t-1}
@@ -66,7 +68,7 @@ struct LstmFwdParams {
 
 struct LstmBwdParams {
   CUtensorMap tmDG;       // dG16 as {k = 2176, row = cap, slot = 9, expert = 8}, box {64, 128, 1, 1}
-  const float* params;
+  CUtensorMap tmWT;       // W_hh^T as fp16 [E][544][2176] {k = gate row 2120, unit = 530, expert}, box {64, 32, 1}
   const __half* G16;
   const float* C9;
   __half* dG16;           // [E][cap][9][LS_LDG16] slot t holds scale * dG_t (d loss / d gate pre-activations): A operand
@@ -108,19 +110,6 @@ __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned targe
   fence_proxy_async_all();   // the slices acquired above were written through the generic proxy; TMA reads them next
 }
 
-__device__ __forceinline__ uint4 pack8_half(const float (&v)[8], float s) {
-  uint4 u;
-  __half2 h0 = __floats2half2_rn(v[0] * s, v[1] * s), h1 = __floats2half2_rn(v[2] * s, v[3] * s);
-  __half2 h2 = __floats2half2_rn(v[4] * s, v[5] * s), h3 = __floats2half2_rn(v[6] * s, v[7] * s);
-  u.x = *reinterpret_cast<uint32_t*>(&h0), u.y = *reinterpret_cast<uint32_t*>(&h1);
-  u.z = *reinterpret_cast<uint32_t*>(&h2), u.w = *reinterpret_cast<uint32_t*>(&h3);
-  return u;
-}
-// byte offset of (row, 16-byte chunk) inside a [rows x 64 halves] 128B-swizzled K-major tile (1024-byte aligned):
-// what TMA SWIZZLE_128B writes and what umma_smem_desc(.., LBO 16, SBO 1024, layout 2) reads
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
-  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
-}
 __device__ __forceinline__ float ls_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ls_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 __device__ __forceinline__ unsigned short f2h_sat_bits(float x) {
@@ -141,7 +130,8 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
   uint64_t* empty = full + LSF_STAGES;
   uint64_t* acc_full = empty + LSF_STAGES;               // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;                      // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.y, j = blockIdx.x;
@@ -150,43 +140,9 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
   pdl_trigger();
   if (dbg && threadIdx.x == 0) dbg[64] = clock64();
 
-  // ---- resident weights: W_hh[e][n0 .. n0+127][0 .. 529] -> fp16, swizzled K-major tiles. Parameters were written
-  // by an earlier, fully completed launch (the update starts with stream-ordered memsets), so this runs before
-  // pdl_wait and overlaps the predecessor's tail.
-  {
-    const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
-    constexpr int TASKS = 128 * (LSF_KB * 8), UNR = 4;
-    for (int task0 = threadIdx.x; task0 < TASKS; task0 += UNR * LSF_THREADS) {
-      float4 a[UNR], b[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {           // all global loads of the batch first
-        const int task = task0 + u * LSF_THREADS;
-        const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);   // consecutive lanes: consecutive chunks
-        const int k0 = chunk_all * 8, n = n0 + r;
-        a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (task < TASKS && n < G && k0 < F) {
-          const float* src = W + static_cast<long long>(n) * LDF + k0;
-          a[u] = *reinterpret_cast<const float4*>(src);
-          if (k0 + 4 < LDF) b[u] = *reinterpret_cast<const float4*>(src + 4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int task = task0 + u * LSF_THREADS;
-        if (task >= TASKS) continue;
-        const int chunk_all = task % (LSF_KB * 8), r = task / (LSF_KB * 8);
-        const int k0 = chunk_all * 8;
-        float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (k0 + i >= F) v[i] = 0.f;
-        const int kb = chunk_all >> 3, c = chunk_all & 7;
-        *reinterpret_cast<uint4*>(w_s + kb * (128 * 128) + sw128_offset(r, c)) = pack8_half(v, 1.0f);
-      }
-    }
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmH);
+    tma_prefetch_desc(&p.tmW);
     for (int s = 0; s < LSF_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -195,18 +151,23 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 8);      // one arrival per epilogue warp
     }
+    mbar_init(w_full, 1);
     fence_mbar_init();
+    // ---- resident weights: rows [n0, n0 + 128) of the fp16 copy of W_hh[e] (written by wcvt_kernel at the start of
+    // this update; the host joins that kernel's stream before any launch of the forward pass, so it is complete even
+    // though this runs before griddepcontrol.wait). Nine TMA boxes land directly in the swizzled K-major layout;
+    // k >= 530 and gate rows >= 2120 are filled with zeros by the TMA unit.
+    mbar_expect_tx(w_full, LSF_W_BYTES);
+    for (int kb = 0; kb < LSF_KB; ++kb) tma_load_3d(w_s + kb * (128 * 128), &p.tmW, w_full, kb * 64, n0, e);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  fence_proxy_async_smem();             // the weight tiles were written with generic stores; tcgen05 reads them
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (dbg && threadIdx.x == 0) dbg[65] = clock64();      // weights resident
 
   pdl_wait();                           // counts, XP9, H16 buffer 0, the zeroed counters: all from earlier launches
   if (dbg && threadIdx.x == 0) dbg[66] = clock64();
@@ -239,6 +200,8 @@ __global__ void __launch_bounds__(LSF_THREADS, 1) lstm_seq_fwd_kernel(const __gr
       // ------------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = umma_idesc(0u, 0, 0, 128, 128);   // fp16 x fp16 -> fp32, both K-major
       uint32_t it = 0, tile = 0;
+      mbar_wait(w_full, 0);
+      if (dbg && lane == 0) dbg[65] = clock64();             // weights resident
       for (int t = 0; t < 8; ++t)
         for (int mt = 0; mt < n_mt; ++mt, ++tile) {
           const uint32_t buf = tile & 1;
@@ -394,7 +357,8 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
   uint64_t* empty = full + LSB_STAGES;
   uint64_t* acc_full = empty + LSB_STAGES;               // [LSB_NBUF]
   uint64_t* acc_empty = acc_full + LSB_NBUF;             // [LSB_NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + LSB_NBUF);
+  uint64_t* w_full = acc_empty + LSB_NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.y, j = blockIdx.x;
@@ -403,33 +367,9 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
   pdl_trigger();
   if (dbg && threadIdx.x == 0) dbg[64] = clock64();
 
-  // ---- resident weights: B[n = unit][k = gate row] = W_hh[e][k][u0 + n], fp16, swizzled K-major tiles of 64 k.
-  // A warp reads 8 consecutive gate rows (each a coalesced 128-byte segment, lane = unit) and writes one 16-byte chunk
-  // per lane (conflict-free: the 128B swizzle spreads 8 consecutive rows over the 8 chunks).
-  {
-    const float* W = p.params + OFF_WHH + static_cast<long long>(e) * G * LDF;
-    const int unit = u0 + lane;
-    constexpr int NW = LSB_THREADS / 32, UNR = 3;
-    for (int c0 = warp; c0 < LSB_KB * 8; c0 += UNR * NW) {
-      float v[UNR][8];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int k0 = (c0 + u * NW) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          v[u][i] = (unit < F && k0 + i < G) ? W[static_cast<long long>(k0 + i) * LDF + unit] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int c_all = c0 + u * NW;
-        if (c_all < LSB_KB * 8)
-          *reinterpret_cast<uint4*>(w_s + (c_all >> 3) * (32 * 128) + sw128_offset(lane, c_all & 7)) =
-              pack8_half(v[u], 1.0f);
-      }
-    }
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmDG);
+    tma_prefetch_desc(&p.tmWT);
     for (int s = 0; s < LSB_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -438,18 +378,21 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 8);      // one arrival per epilogue warp
     }
+    mbar_init(w_full, 1);
     fence_mbar_init();
+    // ---- resident weights: B[n = unit][k = gate row] = W_hh[e][k][u0 + n] from the transposed fp16 copy written by
+    // wcvt_kernel (see the forward kernel): 34 TMA boxes of [32 units x 64 gate rows]
+    mbar_expect_tx(w_full, LSB_W_BYTES);
+    for (int kb = 0; kb < LSB_KB; ++kb) tma_load_3d(w_s + kb * (32 * 128), &p.tmWT, w_full, kb * 64, u0, e);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 32 * LSB_NBUF);
     tmem_relinquish();
   }
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (dbg && threadIdx.x == 0) dbg[65] = clock64();
 
   pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[66] = clock64();
@@ -482,6 +425,8 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
       // ------------------------------------------------------------------ MMA issuer: dh_{t-1}[:, units] = dG_t W_hh
       constexpr uint32_t idesc = umma_idesc(0u, 0, 0, 128, 32);
       uint32_t it = 0, tile = 0;
+      mbar_wait(w_full, 0);
+      if (dbg && lane == 0) dbg[65] = clock64();
       for (int t = 7; t >= 1; --t)
         for (int mt = 0; mt < n_mt; ++mt, ++tile) {
           const uint32_t buf = tile % LSB_NBUF;

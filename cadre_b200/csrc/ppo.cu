@@ -104,7 +104,7 @@ struct RowScalars {
 __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict__ refs,
                                                    const int* __restrict__ idx, int W, int mb, int cap,
                                                    const int* __restrict__ row_slot,
-                                                   const int* __restrict__ row_expert, float* __restrict__ X9,
+                                                   const int* __restrict__ row_expert,
                                                    __half* __restrict__ X16, float* __restrict__ C9,
                                                    __half* __restrict__ H16, RowScalars sc) {
   pdl_trigger();
@@ -116,13 +116,21 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
   const int e = row_expert[h * R + r], slot = row_slot[h * R + r];
   const long long row = static_cast<long long>(e) * cap + slot;
   const float* obs = ref.obs + static_cast<long long>(t) * 8 * F;
-  float* x = X9 + row * 9 * LDF;             // fp32: A operand of the x-part GEMM (TF32)
-  __half* x16 = X16 + row * 9 * LS_LDH16;    // fp16: B operand of the W_ih weight-gradient GEMM
-  for (int k = threadIdx.x; k < 8 * F; k += 256) {
-    const int j = k / F, f = k - j * F;
-    const float v = obs[k];
-    x[j * LDF + f] = v;
-    x16[j * LS_LDH16 + f] = __float2half_rn(v);
+  // fp16 observations: A operand of the x-part GEMM and B operand of the W_ih weight-gradient GEMM. Eight loads
+  // are in flight per thread (the kernel is latency-, not bandwidth-bound: 17 KB per block).
+  __half* x16 = X16 + row * 9 * LS_LDH16;
+  for (int k0 = threadIdx.x; k0 < 8 * F; k0 += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (k0 + u * 256 < 8 * F) ? obs[k0 + u * 256] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * 256;
+      if (k < 8 * F) {
+        const int j = k / F, f = k - j * F;
+        x16[j * LS_LDH16 + f] = __float2half_rn(v[u]);
+      }
+    }
   }
   float* c0 = C9 + row * 9 * LDF;
   __half* h16 = H16 + row * 9 * LS_LDH16;    // slot 0: h_{-1}
@@ -225,9 +233,16 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* W3A = p.params + OFF_W3A + static_cast<long long>(e) * AMAX * HID;
-  for (int i = tid; i < AMAX * HID; i += 256) {
-    const int j = i / HID, k = i - j * HID;
-    w3aT[k][j] = W3A[i];
+  {   // all 17 loads of a thread in flight together (the kernel is a chain of short latency-bound phases)
+    constexpr int NL = (AMAX * HID + 255) / 256;
+    float wv[NL];
+#pragma unroll
+    for (int u = 0; u < NL; ++u) wv[u] = (tid + u * 256 < AMAX * HID) ? W3A[tid + u * 256] : 0.f;
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 256;
+      if (i < AMAX * HID) w3aT[i % HID][i / HID] = wv[u];
+    }
   }
   if (tid < AMAX) b3a[tid] = p.params[OFF_B3A + e * B3A_LD + tid];
   if (tid < HID) w3c[tid] = p.params[OFF_W3C + e * HID + tid];
@@ -406,9 +421,21 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   if (!s_last) return;
   __threadfence();
   const float* pe = p.partial + static_cast<long long>(e) * (p.cap / HEAD_ROWS_PER_CTA) * HEAD_PARTIAL;
-  for (int i = tid; i < HP_LOSS + p.W * 3; i += 256) {
-    float sum = 0.f;
-    for (int b = 0; b < nblk; ++b) sum += __ldcg(pe + static_cast<long long>(b) * HEAD_PARTIAL + i);
+  const int n_red = HP_LOSS + p.W * 3;
+  for (int i0 = tid; i0 < n_red; i0 += 6 * 256) {
+    float sums[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) sums[u] = 0.f;
+    for (int b = 0; b < nblk; ++b) {       // block order: deterministic; six independent elements per thread in flight
+#pragma unroll
+      for (int u = 0; u < 6; ++u)
+        if (i0 + u * 256 < n_red) sums[u] += __ldcg(pe + static_cast<long long>(b) * HEAD_PARTIAL + i0 + u * 256);
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+    const int i = i0 + u * 256;
+    if (i >= n_red) continue;
+    const float sum = sums[u];
     if (i < HP_W3C) {
       if (i < A * HID) p.grads[OFF_W3A + static_cast<long long>(e) * AMAX * HID + i] = sum;
     } else if (i < HP_B3A) {
@@ -419,6 +446,7 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
       if (i == HP_B3C) p.grads[OFF_B3C + e * 4] = sum;
     } else {
       p.loss_e[e * HEAD_MAX_W * 3 + (i - HP_LOSS)] = sum;
+    }
     }
   }
   // ---- phase 4: the last expert to finish adds the per-expert losses in expert order
@@ -520,17 +548,62 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------ fp16 weight copies
+// The LSTM weights as tensor-core operands: W_ih and W_hh rounded once per update to fp16 (the 11-bit significand of the
+// TF32 operands they replace), rows padded to 544 halves, plus W_hh transposed ([unit][gate row], rows padded to 2176)
+// for the BPTT kernel. Block (x, e): gate rows [32 x, 32 x + 32) of expert e; the transpose goes through a padded
+// shared-memory tile so that all global accesses are row segments. Runs on the plan's side stream while the main
+// stream routes and gathers the minibatch.
+__global__ void __launch_bounds__(256) wcvt_kernel(const float* __restrict__ params, __half* __restrict__ WIH16,
+                                                   __half* __restrict__ WHH16, __half* __restrict__ WHHT16) {
+  __shared__ float tile[32][33];
+  const int e = blockIdx.y, g0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
+  const float* Wih = params + OFF_WIH + static_cast<long long>(e) * G * LDF;
+  const float* Whh = params + OFF_WHH + static_cast<long long>(e) * G * LDF;
+  __half* oih = WIH16 + static_cast<long long>(e) * G * LS_LDH16;
+  __half* ohh = WHH16 + static_cast<long long>(e) * G * LS_LDH16;
+  __half* oT = WHHT16 + static_cast<long long>(e) * LS_LDH16 * LS_LDG16;
+  for (int c0 = 0; c0 < LS_LDH16; c0 += 32) {            // 17 column blocks of 32 units
+    const int c = c0 + tx;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int g = g0 + r;
+      float a = 0.f, b = 0.f;
+      if (g < G && c < F) {
+        a = Wih[static_cast<long long>(g) * LDF + c];
+        b = Whh[static_cast<long long>(g) * LDF + c];
+      }
+      if (g < G) {
+        oih[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(a);
+        ohh[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(b);
+      }
+      tile[r][tx] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {                   // unit c0 + r, gate rows g0 + tx
+      const int u = c0 + r, g = g0 + tx;
+      if (g < LS_LDG16) oT[static_cast<long long>(u) * LS_LDG16 + g] = __float2half_rn(g < G ? tile[tx][r] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ plan
 struct PpoPlan {
   cadre_ppo_config cfg;
   int cap = 0, R = 0;
   // device buffers
-  float *X9 = nullptr, *XP9 = nullptr, *C9 = nullptr, *H8 = nullptr;   // H8 [E][cap][LDF]: h_8, input of the heads
+  float *XP9 = nullptr, *C9 = nullptr, *H8 = nullptr;   // H8 [E][cap][LDF]: h_8, input of the heads
   float *Y1 = nullptr, *Y2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dH = nullptr, *dC = nullptr;
   float* bsum = nullptr;
   // fp16 tensors in the 9-slot layout (see the file header) + hand-off counters and prebuilt tensor maps of the
   // persistent recurrence kernels (lstm_seq.cuh)
   __half *X16 = nullptr, *H16 = nullptr, *G16 = nullptr, *dG16 = nullptr;
+  __half *WIH16 = nullptr, *WHH16 = nullptr, *WHHT16 = nullptr;   // fp16 weight copies (wcvt_kernel)
+  CUtensorMap tmW, tmWT;
+  cudaEvent_t ev_wcvt_fork = nullptr, ev_wcvt = nullptr;
   float *head_partial = nullptr, *head_loss_e = nullptr;   // head_kernel scratch (ordered reductions)
   unsigned* seq_sync = nullptr;          // [0, E]: forward counters + error flag, [16, 16 + E]: backward, [32, 32 + E]: head
   CUtensorMap tmH, tmDG;
@@ -565,7 +638,6 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->R = cfg->workers * cfg->mini_batch;
   P->cap = (P->R + 127) / 128 * 128;  // worst case: every row of a head carries the same command
   const size_t rows = static_cast<size_t>(E) * P->cap;
-  P->X9 = dalloc<float>(rows * 9 * LDF);
   P->XP9 = dalloc<float>(rows * 9 * G);
   P->H8 = dalloc<float>(rows * LDF);
   P->C9 = dalloc<float>(rows * 9 * LDF);
@@ -585,6 +657,11 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->H16 = dalloc<__half>(rows * 9 * LS_LDH16);
   P->G16 = dalloc<__half>(rows * 9 * G);
   P->dG16 = dalloc<__half>(rows * 9 * LS_LDG16);
+  P->WIH16 = dalloc<__half>(static_cast<size_t>(E) * G * LS_LDH16);
+  P->WHH16 = dalloc<__half>(static_cast<size_t>(E) * G * LS_LDH16);
+  P->WHHT16 = dalloc<__half>(static_cast<size_t>(E) * LS_LDH16 * LS_LDG16);
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wcvt_fork, cudaEventDisableTiming));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wcvt, cudaEventDisableTiming));
   P->seq_sync = dalloc<unsigned>(64);
   CADRE_REQUIRE(cfg->workers <= HEAD_MAX_W, "at most 64 workers per engine");
   P->head_partial = dalloc<float>(static_cast<size_t>(E) * (P->cap / HEAD_ROWS_PER_CTA) * HEAD_PARTIAL);
@@ -597,6 +674,14 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
     const uint64_t dims_g[4] = {(uint64_t)LS_LDG16, (uint64_t)P->cap, 9, (uint64_t)E};
     const uint64_t str_g[3] = {9ull * LS_LDG16 * 2, 1ull * LS_LDG16 * 2, (uint64_t)P->cap * 9 * LS_LDG16 * 2};
     make_tensor_map_f16(&P->tmDG, 4, P->dG16, dims_g, str_g, box);
+    const uint64_t dims_w[3] = {(uint64_t)F, (uint64_t)G, (uint64_t)E};
+    const uint64_t str_w[2] = {1ull * LS_LDH16 * 2, (uint64_t)G * LS_LDH16 * 2};
+    const uint32_t box_w[3] = {64, 128, 1};
+    make_tensor_map_f16(&P->tmW, 3, P->WHH16, dims_w, str_w, box_w);
+    const uint64_t dims_t[3] = {(uint64_t)G, (uint64_t)F, (uint64_t)E};
+    const uint64_t str_t[2] = {1ull * LS_LDG16 * 2, (uint64_t)LS_LDH16 * LS_LDG16 * 2};
+    const uint32_t box_t[3] = {64, 32, 1};
+    make_tensor_map_f16(&P->tmWT, 3, P->WHHT16, dims_t, str_t, box_t);
     // backward operands are scaled by 2^(ceil(log2(mini_batch)) + 4): the loss seeds carry a 1/mini_batch factor
     int lg = 0;
     while ((1 << lg) < cfg->mini_batch) ++lg;
@@ -672,13 +757,15 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
 
 static void ppo_destroy(PpoPlan* P) {
   if (!P) return;
-  void* ptrs[] = {P->head_partial, P->head_loss_e, P->X16, P->H16, P->G16, P->dG16, P->seq_sync, P->X9, P->XP9, P->H8, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
+  void* ptrs[] = {P->head_partial, P->head_loss_e, P->X16, P->H16, P->G16, P->dG16, P->WIH16, P->WHH16, P->WHHT16, P->seq_sync, P->XP9, P->H8, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
                   P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
                   P->row_expert, P->counts, P->counts9, P->idx_dev, P->xp_tiles, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
                   P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
   for (void* p : ptrs) cudaFree(p);
   if (P->side) cudaStreamDestroy(P->side);
   if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  if (P->ev_wcvt_fork) cudaEventDestroy(P->ev_wcvt_fork);
+  if (P->ev_wcvt) cudaEventDestroy(P->ev_wcvt);
   if (P->ev_join) cudaEventDestroy(P->ev_join);
   if (P->ev_wih) cudaEventDestroy(P->ev_wih);
   delete P;
@@ -694,8 +781,16 @@ static GemmArgs tf32_gemm(int a_mn, int b_mn) {
 static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host,
                        const float* params, cudaStream_t s) {
   const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap, R = P->R;
-  const long long rs9F = static_cast<long long>(cap) * 9 * LDF, rs9G = static_cast<long long>(cap) * 9 * G;
+  const long long rs9G = static_cast<long long>(cap) * 9 * G;
   int n = 0;
+  // fp16 copies of the LSTM weights for this call (parameters may have changed since the last one: Adam step,
+  // load_state_dict, update_model): on the side stream, next to the routing / gather kernels
+  CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wcvt_fork, s));
+  CADRE_CUDA_CHECK(cudaStreamWaitEvent(P->side, P->ev_wcvt_fork, 0));
+  wcvt_kernel<<<dim3((LS_LDG16 + 31) / 32, E), 256, 0, P->side>>>(params, P->WIH16, P->WHH16, P->WHHT16);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  ++n;
+  CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wcvt, P->side));
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync, 0, sizeof(unsigned) * E, s));            // forward hand-off counters
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 16, 0, sizeof(unsigned) * E, s));       // backward
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 32, 0, sizeof(unsigned) * (E + 1), s));  // head_kernel reductions
@@ -704,16 +799,18 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
                                   P->counts9), ++n;
   launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
-                                         P->X9, P->X16, P->C9, P->H16, P->sc), ++n;
+                                         P->X16, P->C9, P->H16, P->sc), ++n;
   launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G,
            P->counts9, P->xp_tiles, P->xp_max_tiles, P->dG16, cap), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
   // ---- forward
-  {  // x-part of all 8 (+1 dummy) time slots: XP9 = X9 W_ih^T + (b_ih + b_hh)
-    GemmArgs g = tf32_gemm(0, 0);
-    g.A = P->X9, g.lda = LDF, g.a_bs = rs9F;
-    g.B = params + OFF_WIH, g.ldb = LDF, g.b_bs = static_cast<long long>(G) * LDF;
+  CADRE_CUDA_CHECK(cudaStreamWaitEvent(s, P->ev_wcvt, 0));   // the fp16 weight copies are complete from here on
+  {  // x-part of all 8 (+1 dummy) time slots: XP9 = X W_ih^T + (b_ih + b_hh), fp16 operands, fp32 accumulation
+    GemmArgs g;
+    g.kind = 0, g.batch = E, g.out_f32 = 1, g.block_n = 128;
+    g.A = P->X16, g.lda = LS_LDH16, g.a_bs = static_cast<long long>(cap) * 9 * LS_LDH16;
+    g.B = P->WIH16, g.ldb = LS_LDH16, g.b_bs = static_cast<long long>(G) * LS_LDH16;
     g.M = 9 * cap, g.N = G, g.K = F;
     g.out = P->XP9, g.ldc = G, g.out_bs = rs9G;
     g.bias = P->bsum, g.bias_bs = G;
@@ -723,7 +820,7 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   }
   {   // models.py:146-151: the 8 sequential LSTMCell steps in ONE persistent launch (lstm_seq.cuh)
     LstmFwdParams q;
-    q.tmH = P->tmH, q.params = params, q.XP9 = P->XP9, q.G16 = P->G16, q.C9 = P->C9, q.H8 = P->H8, q.H16 = P->H16;
+    q.tmH = P->tmH, q.tmW = P->tmW, q.XP9 = P->XP9, q.G16 = P->G16, q.C9 = P->C9, q.H8 = P->H8, q.H16 = P->H16;
     q.counts = P->counts, q.sync = P->seq_sync, q.cap = cap;
     q.dbg = g_dbg_clk;
     launch_k(lstm_seq_fwd_kernel, dim3(LS_SLICES, E), dim3(LSF_THREADS), LSF_SMEM, s, q), ++n;
@@ -826,7 +923,7 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   {   // BPTT: 8 x (LSTM-cell backward, dh_{t-1} = dG_t W_hh) in ONE persistent launch; it also produces the LSTM
       // bias gradients (column sums of dG)
     LstmBwdParams q;
-    q.tmDG = P->tmDG, q.params = params, q.G16 = P->G16, q.C9 = P->C9, q.dG16 = P->dG16;
+    q.tmDG = P->tmDG, q.tmWT = P->tmWT, q.G16 = P->G16, q.C9 = P->C9, q.dG16 = P->dG16;
     q.dH8 = P->dH, q.dC = P->dC, q.counts = P->counts, q.sync = P->seq_sync + 16, q.cap = cap;
     q.scale = P->bwd_scale, q.inv_scale = 1.f / P->bwd_scale;
     q.grads = grads;

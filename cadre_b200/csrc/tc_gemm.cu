@@ -226,7 +226,7 @@ void launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 0, enc_t)
   CADRE_GEMM_CASE(0, 0, 0, 128, 4, EPI_LINEAR, 0, enc_t)
   CADRE_GEMM_CASE(0, 0, 0, 64, 4, EPI_LINEAR, 1, float)
-  CADRE_GEMM_CASE(0, 0, 0, 128, 4, EPI_LINEAR, 1, float)
+  CADRE_GEMM_CASE(0, 0, 0, 128, 3, EPI_LINEAR, 1, float)   // PPO x-part GEMM (fp16 x W_ih^T): 2 CTAs per SM
   CADRE_GEMM_CASE(0, 0, 1, 128, 4, EPI_LINEAR, 1, float)
   CADRE_GEMM_CASE(0, 1, 1, 128, 3, EPI_LINEAR, 1, float)   // PPO LSTM weight gradients (fp16 dG^T x / h): 2 CTAs per SM
   // fp32 operands as TF32 (PPO update: forward, dgrad, wgrad, LSTM cell)

@@ -551,42 +551,42 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
 // ------------------------------------------------------------------------------------------ fp16 weight copies
 // The LSTM weights as tensor-core operands: W_ih and W_hh rounded once per update to fp16 (the 11-bit significand of the
 // TF32 operands they replace), rows padded to 544 halves, plus W_hh transposed ([unit][gate row], rows padded to 2176)
-// for the BPTT kernel. Block (x, e): gate rows [32 x, 32 x + 32) of expert e; the transpose goes through a padded
-// shared-memory tile so that all global accesses are row segments. Runs on the plan's side stream while the main
+// for the BPTT kernel. Block (x, e, z): gate rows [32 x, 32 x + 32) x units [32 z, 32 z + 32) of expert e; the transpose
+// goes through a padded shared-memory tile so that all global accesses are row segments. Runs on the plan's side stream while the main
 // stream routes and gathers the minibatch.
 __global__ void __launch_bounds__(256) wcvt_kernel(const float* __restrict__ params, __half* __restrict__ WIH16,
                                                    __half* __restrict__ WHH16, __half* __restrict__ WHHT16) {
   __shared__ float tile[32][33];
-  const int e = blockIdx.y, g0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
+  const int e = blockIdx.y, g0 = blockIdx.x * 32, c0 = blockIdx.z * 32;   // 32 gate rows x 32 units per block
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 8 warps, 4 rows each
   const float* Wih = params + OFF_WIH + static_cast<long long>(e) * G * LDF;
   const float* Whh = params + OFF_WHH + static_cast<long long>(e) * G * LDF;
   __half* oih = WIH16 + static_cast<long long>(e) * G * LS_LDH16;
   __half* ohh = WHH16 + static_cast<long long>(e) * G * LS_LDH16;
   __half* oT = WHHT16 + static_cast<long long>(e) * LS_LDH16 * LS_LDG16;
-  for (int c0 = 0; c0 < LS_LDH16; c0 += 32) {            // 17 column blocks of 32 units
-    const int c = c0 + tx;
+  const int c = c0 + tx;
+  float a[4], b[4];
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-      const int g = g0 + r;
-      float a = 0.f, b = 0.f;
-      if (g < G && c < F) {
-        a = Wih[static_cast<long long>(g) * LDF + c];
-        b = Whh[static_cast<long long>(g) * LDF + c];
-      }
-      if (g < G) {
-        oih[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(a);
-        ohh[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(b);
-      }
-      tile[r][tx] = b;
-    }
-    __syncthreads();
+  for (int k = 0; k < 4; ++k) {     // all eight loads of the thread in flight
+    const int g = g0 + ty + 8 * k;
+    const bool ok = g < G && c < F;
+    a[k] = ok ? Wih[static_cast<long long>(g) * LDF + c] : 0.f;
+    b[k] = ok ? Whh[static_cast<long long>(g) * LDF + c] : 0.f;
+  }
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {                   // unit c0 + r, gate rows g0 + tx
-      const int u = c0 + r, g = g0 + tx;
-      if (g < LS_LDG16) oT[static_cast<long long>(u) * LS_LDG16 + g] = __float2half_rn(g < G ? tile[tx][r] : 0.f);
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k, g = g0 + r;
+    if (g < G) {
+      oih[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(a[k]);
+      ohh[static_cast<long long>(g) * LS_LDH16 + c] = __float2half_rn(b[k]);
     }
-    __syncthreads();
+    tile[r][tx] = b[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {     // unit c0 + r, gate rows g0 + tx (zeros in the K padding 2120 .. 2175)
+    const int r = ty + 8 * k;
+    oT[static_cast<long long>(c0 + r) * LS_LDG16 + g0 + tx] = __float2half_rn(tile[tx][r]);
   }
 }
 
@@ -787,7 +787,7 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   // load_state_dict, update_model): on the side stream, next to the routing / gather kernels
   CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wcvt_fork, s));
   CADRE_CUDA_CHECK(cudaStreamWaitEvent(P->side, P->ev_wcvt_fork, 0));
-  wcvt_kernel<<<dim3((LS_LDG16 + 31) / 32, E), 256, 0, P->side>>>(params, P->WIH16, P->WHH16, P->WHHT16);
+  wcvt_kernel<<<dim3(LS_LDG16 / 32, E, LS_LDH16 / 32), 256, 0, P->side>>>(params, P->WIH16, P->WHH16, P->WHHT16);
   CADRE_CUDA_CHECK(cudaGetLastError());
   ++n;
   CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wcvt, P->side));

@@ -177,6 +177,7 @@ struct OptTables {
   int* chunk_len = nullptr;        // [num_chunks] multiple of 4
   int* chunk_mod = nullptr;        // [num_chunks] module id 0..15, non-decreasing
   int* mod_first = nullptr;        // [17] first chunk of each module
+  int mod_first_h[17] = {};        // host copy
   float* partial = nullptr;        // [num_chunks]
   float* clip_coef = nullptr;      // [16]
   float* norms = nullptr;          // [16]
@@ -218,7 +219,9 @@ inline void ensure_dynamic_smem(Kern kern, size_t smem, size_t* flags) {
   }
 }
 
+// modules [mod_begin, mod_end) only (module e < 8: LSTM of expert e, 8 + e: actor-critic of expert e)
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
-                      float lr, float beta1, float beta2, float eps, int step, cudaStream_t s);
+                      float lr, float beta1, float beta2, float eps, int step, cudaStream_t s, int mod_begin = 0,
+                      int mod_end = 16);
 
 }  // namespace cadre

@@ -80,7 +80,7 @@ struct LstmBwdParams {
   int cap;
   float scale, inv_scale;
   float* grads;           // flat gradient buffer: the LSTM bias gradients (column sums of dG over rows and steps) are
-                          // accumulated by the epilogue and written to OFF_BIH / OFF_BHH
+                          // accumulated by the epilogue and written to the expert's b_ih / b_hh
   long long* dbg;
 };
 
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
           const float4 o = red[w * 32 + lane];
           s4.x += o.x, s4.y += o.y, s4.z += o.z, s4.w += o.w;
         }
-        *reinterpret_cast<float4*>(p.grads + OFF_BIH + static_cast<long long>(e) * G + 4 * unit) = s4;
-        *reinterpret_cast<float4*>(p.grads + OFF_BHH + static_cast<long long>(e) * G + 4 * unit) = s4;
+        *reinterpret_cast<float4*>(p.grads + OFF_LSTM + e * LSTM_BLK + LSTM_BIH + 4 * unit) = s4;
+        *reinterpret_cast<float4*>(p.grads + OFF_LSTM + e * LSTM_BLK + LSTM_BHH + 4 * unit) = s4;
       }
     }
   } else if (warp == 2) {
@@ -584,8 +584,8 @@ __global__ void __launch_bounds__(LSB_THREADS, 1) lstm_seq_bwd_kernel(const __gr
     const int unit = u0 + lane;
     if (unit < F) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(p.grads + OFF_BIH + static_cast<long long>(e) * G + 4 * unit) = z;
-      *reinterpret_cast<float4*>(p.grads + OFF_BHH + static_cast<long long>(e) * G + 4 * unit) = z;
+      *reinterpret_cast<float4*>(p.grads + OFF_LSTM + e * LSTM_BLK + LSTM_BIH + 4 * unit) = z;
+      *reinterpret_cast<float4*>(p.grads + OFF_LSTM + e * LSTM_BLK + LSTM_BHH + 4 * unit) = z;
     }
   }
   tc_fence_before();

@@ -156,13 +156,17 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
 // multiple of 32 rows only, so dG rows [count, count + 8) are zeroed here (stale rows of an earlier update with more
 // rows for this expert would otherwise leak into the gradient).
 constexpr int WGRAD_PAD_ROWS = 8;
-__global__ void prep_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n,
+__global__ void prep_kernel(const float* __restrict__ params, float* __restrict__ o, int n,
                             const int* __restrict__ counts9, int* __restrict__ tile_list, int max_tiles,
                             __half* __restrict__ dG16, int cap) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = a[i] + b[i];
+  if (i < n) {
+    const int e = i / G, r = i - e * G;
+    const float* blk = params + OFF_LSTM + e * LSTM_BLK;
+    o[i] = blk[LSTM_BIH + r] + blk[LSTM_BHH + r];
+  }
   {
     constexpr int V = 9 * LS_LDG16 / 8;                       // uint4 per row (all 9 slots)
     const long long total = static_cast<long long>(E) * WGRAD_PAD_ROWS * V;
@@ -559,8 +563,8 @@ __global__ void __launch_bounds__(256) wcvt_kernel(const float* __restrict__ par
   __shared__ float tile[32][33];
   const int e = blockIdx.y, g0 = blockIdx.x * 32, c0 = blockIdx.z * 32;   // 32 gate rows x 32 units per block
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 8 warps, 4 rows each
-  const float* Wih = params + OFF_WIH + static_cast<long long>(e) * G * LDF;
-  const float* Whh = params + OFF_WHH + static_cast<long long>(e) * G * LDF;
+  const float* Wih = params + OFF_LSTM + e * LSTM_BLK + LSTM_WIH;
+  const float* Whh = params + OFF_LSTM + e * LSTM_BLK + LSTM_WHH;
   __half* oih = WIH16 + static_cast<long long>(e) * G * LS_LDH16;
   __half* ohh = WHH16 + static_cast<long long>(e) * G * LS_LDH16;
   __half* oT = WHHT16 + static_cast<long long>(e) * LS_LDH16 * LS_LDG16;
@@ -619,7 +623,11 @@ struct PpoPlan {
   // side stream for the gradient kernels that are off the critical path (dW2, dW1, bias column sums)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev_wih = nullptr;   // recorded when the W_ih block of the gradient (the first 36 MB) is final
+  // data-parallel pipeline: the LSTM weight gradients are produced per group of E / grad_groups experts, one event
+  // per group; ev_mlp fires when every actor-critic gradient (side stream) is final
+  int grad_groups = 1;
+  cudaEvent_t ev_grp[8] = {};
+  cudaEvent_t ev_mlp = nullptr;
   bool use_side = true;
 };
 
@@ -650,7 +658,8 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   CADRE_CUDA_CHECK(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
   CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
-  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_wih, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_grp[i], cudaEventDisableTiming));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_mlp, cudaEventDisableTiming));
   P->dC = dalloc<float>(rows * LDF);
   P->bsum = dalloc<float>(static_cast<size_t>(E) * G);
   P->X16 = dalloc<__half>(rows * 9 * LS_LDH16);
@@ -712,10 +721,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   };
   std::vector<Piece> pieces;
   for (int e = 0; e < E; ++e) {
-    pieces.push_back({OFF_WIH + (long long)e * G * LDF, (long long)G * LDF, e});
-    pieces.push_back({OFF_WHH + (long long)e * G * LDF, (long long)G * LDF, e});
-    pieces.push_back({OFF_BIH + (long long)e * G, G, e});
-    pieces.push_back({OFF_BHH + (long long)e * G, G, e});
+    pieces.push_back({OFF_LSTM + e * LSTM_BLK, LSTM_BLK, e});   // W_ih | W_hh | b_ih | b_hh of expert e: one module
   }
   for (int e = 0; e < E; ++e) {
     pieces.push_back({OFF_W1 + (long long)e * 2 * HID * LDF, 2LL * HID * LDF, 8 + e});
@@ -752,6 +758,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_len, clen.data(), clen.size() * 4, cudaMemcpyHostToDevice));
   CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_mod, cmod.data(), cmod.size() * 4, cudaMemcpyHostToDevice));
   CADRE_CUDA_CHECK(cudaMemcpy(T.mod_first, mfirst.data(), 17 * 4, cudaMemcpyHostToDevice));
+  for (int m = 0; m <= 16; ++m) T.mod_first_h[m] = mfirst[m];
   return P;
 }
 
@@ -767,7 +774,9 @@ static void ppo_destroy(PpoPlan* P) {
   if (P->ev_wcvt_fork) cudaEventDestroy(P->ev_wcvt_fork);
   if (P->ev_wcvt) cudaEventDestroy(P->ev_wcvt);
   if (P->ev_join) cudaEventDestroy(P->ev_join);
-  if (P->ev_wih) cudaEventDestroy(P->ev_wih);
+  for (cudaEvent_t ev : P->ev_grp)
+    if (ev) cudaEventDestroy(ev);
+  if (P->ev_mlp) cudaEventDestroy(P->ev_mlp);
   delete P;
 }
 
@@ -800,7 +809,7 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
                                   P->counts9), ++n;
   launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
                                          P->X16, P->C9, P->H16, P->sc), ++n;
-  launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params + OFF_BIH, params + OFF_BHH, P->bsum, E * G,
+  launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params, P->bsum, E * G,
            P->counts9, P->xp_tiles, P->xp_max_tiles, P->dG16, cap), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
@@ -932,17 +941,26 @@ static void ppo_update(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   }
   CADRE_CUDA_CHECK(cudaGetLastError());
   if (P->use_side) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_join, s2));
-  for (int which = 0; which < 2; ++which) {  // dW_ih = dG^T X, dW_hh = dG^T H (K = 9 * rows), fp16 operands
-    GemmArgs g;
-    g.kind = 0, g.a_mn = 1, g.b_mn = 1, g.batch = E, g.out_f32 = 1, g.block_n = 128;
-    g.A = P->dG16, g.lda = LS_LDG16, g.a_bs = static_cast<long long>(cap) * 9 * LS_LDG16;
-    g.B = which ? P->H16 : P->X16, g.ldb = LS_LDH16, g.b_bs = static_cast<long long>(cap) * 9 * LS_LDH16;
-    g.M = G, g.N = F, g.K = 9 * cap;
-    g.alpha = 1.f / P->bwd_scale;      // dG16 holds scale * dG
-    g.out = grads + (which ? OFF_WHH : OFF_WIH), g.ldc = LDF, g.out_bs = static_cast<long long>(G) * LDF;
-    g.batch_rows = P->counts9, g.rows_is_k = 1;
-    launch_gemm(g, s), ++n;
-    if (which == 0) CADRE_CUDA_CHECK(cudaEventRecord(P->ev_wih, s));   // lets the caller start reducing that block
+  CADRE_CUDA_CHECK(cudaEventRecord(P->ev_mlp, s2));   // (head_kernel's last-layer gradients precede everything on s2)
+  // dW_ih = dG^T X, dW_hh = dG^T H (K = 9 * rows), fp16 operands. With grad_groups > 1 (data-parallel learner) the two
+  // GEMMs run per group of experts and record an event per group: the group's LSTM gradients are one contiguous range
+  // of the flat buffer (ppo_layout.h), which the caller all-reduces while the next group's GEMMs run.
+  const int eg = E / P->grad_groups;
+  for (int grp = 0; grp < P->grad_groups; ++grp) {
+    const int e0 = grp * eg;
+    for (int which = 0; which < 2; ++which) {
+      GemmArgs g;
+      g.kind = 0, g.a_mn = 1, g.b_mn = 1, g.batch = eg, g.out_f32 = 1, g.block_n = 128;
+      g.a_bs = static_cast<long long>(cap) * 9 * LS_LDG16, g.b_bs = static_cast<long long>(cap) * 9 * LS_LDH16;
+      g.A = P->dG16 + e0 * g.a_bs, g.lda = LS_LDG16;
+      g.B = (which ? P->H16 : P->X16) + e0 * g.b_bs, g.ldb = LS_LDH16;
+      g.M = G, g.N = F, g.K = 9 * cap;
+      g.alpha = 1.f / P->bwd_scale;      // dG16 holds scale * dG
+      g.out = grads + OFF_LSTM + e0 * LSTM_BLK + (which ? LSTM_WHH : LSTM_WIH), g.ldc = LDF, g.out_bs = LSTM_BLK;
+      g.batch_rows = P->counts9 + e0, g.rows_is_k = 1;
+      launch_gemm(g, s), ++n;
+    }
+    CADRE_CUDA_CHECK(cudaEventRecord(P->ev_grp[grp], s));
   }
   if (P->use_side) CADRE_CUDA_CHECK(cudaStreamWaitEvent(s, P->ev_join, 0));
   CADRE_CUDA_CHECK(cudaGetLastError());
@@ -1025,11 +1043,44 @@ int cadre_ppo_module_norms(void* handle, float* norms16_host) {
   CADRE_API_END
 }
 
-int cadre_ppo_wait_wih(void* handle, void* stream) {
+int cadre_ppo_set_grad_groups(void* handle, int groups) {
   CADRE_API_BEGIN
   PpoPlan* P = static_cast<PpoPlan*>(handle);
-  CADRE_REQUIRE(P != nullptr, "ppo handle");
-  CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), P->ev_wih, 0));
+  CADRE_REQUIRE(P != nullptr && (groups == 1 || groups == 2 || groups == 4 || groups == 8), "grad groups: 1, 2, 4 or 8");
+  P->grad_groups = groups;
+  CADRE_API_END
+}
+
+int cadre_ppo_grad_range(void* handle, int group, int64_t* offset, int64_t* count, int* mod_begin, int* mod_end) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && offset && count && mod_begin && mod_end && group >= -1 && group < P->grad_groups, "grad range");
+  using namespace cadre::ppo;
+  if (group < 0) {   // the actor-critic tensors of all experts
+    *offset = OFF_W1, *count = TOTAL - OFF_W1, *mod_begin = 8, *mod_end = 16;
+  } else {
+    const int eg = E / P->grad_groups;
+    *offset = OFF_LSTM + static_cast<long long>(group) * eg * LSTM_BLK, *count = eg * LSTM_BLK;
+    *mod_begin = group * eg, *mod_end = (group + 1) * eg;
+  }
+  CADRE_API_END
+}
+
+int cadre_ppo_wait_grads(void* handle, int group, void* stream) {
+  CADRE_API_BEGIN
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P != nullptr && group >= -1 && group < P->grad_groups, "grad group");
+  CADRE_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), group < 0 ? P->ev_mlp : P->ev_grp[group], 0));
+  CADRE_API_END
+}
+
+int cadre_ppo_adam_step_modules(void* handle, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
+                                int mod_begin, int mod_end, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle && params && grads && exp_avg && exp_avg_sq && step >= 1, "adam_step arguments");
+  cadre::launch_clip_adam(static_cast<PpoPlan*>(handle)->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm,
+                          lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream), mod_begin, mod_end);
   CADRE_API_END
 }
 

@@ -80,7 +80,7 @@ class Learner:
         self.step_count = 0
         self.pg = process_group
         self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
-        self._comm_stream = self._comm_done = None
+        self._comm_stream = None
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -126,30 +126,50 @@ class Learner:
         return out
 
     # ---------------------------------------------------------------- one synchronous update step
+    def _setup_pipeline(self):
+        """Streams, events and flat-buffer ranges of the data-parallel gradient pipeline (built on first use)."""
+        groups = int(os.environ.get("CADRE_GRAD_GROUPS", "4")) if self.overlap_allreduce else 1
+        self.engine.set_grad_groups(groups)
+        self._comm_stream = torch.cuda.Stream(device=self.device)
+        self._ranges = [self.engine.grad_range(g) for g in range(groups)] + [self.engine.grad_range(-1)]
+        self._group_ids = list(range(groups)) + [-1]
+        self._reduced = [torch.cuda.Event() for _ in self._ranges]
+        assert sum(r[1] for r in self._ranges) == self.grads.numel()
+
     def update_step(self, storages, indices, async_losses=True):
         """update_policy for all local workers -> all-reduce(sum) -> per-module clip + Adam.
-        storages[w] = (steer, throttle) RolloutStorage with `.advantages`; indices int32 [W,2,mb]."""
+        storages[w] = (steer, throttle) RolloutStorage with `.advantages`; indices int32 [W,2,mb].
+
+        With more than one rank the gradient exchange is pipelined against the end of the backward pass: the LSTM
+        weight gradients (72 of the 78 MB) are produced per group of experts, each group one contiguous range of the
+        flat buffer; a communication stream all-reduces range k as soon as its event fires (the actor-critic range
+        first: it is final before BPTT ends) while the GEMMs of group k+1 still run, and the main stream applies
+        clip + Adam to the modules of range k - a per-module operation, chief.py:16-21 - while range k+1 is on the
+        wire. Sums, clip coefficients and Adam arithmetic are those of the single all-reduce + single step."""
         advs = [(s.advantages, t.advantages) for s, t in storages]
+        if self.world > 1 and self._comm_stream is None:
+            self._setup_pipeline()
         self.engine.update(storages, advs, indices, self.params, self.grads, self.losses)
-        if self.world > 1:
-            if self.overlap_allreduce:
-                # the W_ih block (36 of the 78 MB) is final before the last GEMM of the backward pass starts: reduce it
-                # on a second stream while that GEMM runs, the rest afterwards; same sums, one collective more
-                n1 = ppo_params.OFF["WHH"]
-                if self._comm_stream is None:
-                    self._comm_stream = torch.cuda.Stream(device=self.device)
-                    self._comm_done = torch.cuda.Event()
-                with torch.cuda.stream(self._comm_stream):
-                    self.engine.wait_wih(self._comm_stream)
-                    torch.distributed.all_reduce(self.grads[:n1], op=torch.distributed.ReduceOp.SUM, group=self.pg)
-                    self._comm_done.record(self._comm_stream)
-                torch.distributed.all_reduce(self.grads[n1:], op=torch.distributed.ReduceOp.SUM, group=self.pg)
-                torch.cuda.current_stream().wait_event(self._comm_done)
-            else:
-                torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         self.step_count += 1
-        self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
-                              self.max_grad_norm, self.lr)
+        if self.world > 1:
+            main = torch.cuda.current_stream(self.device)
+            order = [len(self._ranges) - 1] + list(range(len(self._ranges) - 1))     # actor-critic range first
+            with torch.cuda.stream(self._comm_stream):
+                for k in order:
+                    off, cnt, _, _ = self._ranges[k]
+                    self.engine.wait_grads(self._group_ids[k], self._comm_stream)
+                    torch.distributed.all_reduce(self.grads[off:off + cnt], op=torch.distributed.ReduceOp.SUM,
+                                                 group=self.pg)
+                    self._reduced[k].record(self._comm_stream)
+            for k in order:
+                _, _, m0, m1 = self._ranges[k]
+                main.wait_event(self._reduced[k])
+                self.engine.adam_step_modules(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                              m0, m1, self.max_grad_norm, self.lr)
+            self._comm_stream.wait_stream(main)      # the next update overwrites `grads`: order it after these reads
+        else:
+            self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                  self.max_grad_norm, self.lr)
         self.loss_sum += self.losses
         self.loss_steps += 1
         return self.losses if async_losses else self.scaled_losses()

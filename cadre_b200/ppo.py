@@ -62,6 +62,7 @@ class PpoEngine:
         self._h = h
         self._refs = (StorageRefC * (2 * self.workers))()
         self._keep = None
+        self.grad_groups = 1
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -120,9 +121,31 @@ class PpoEngine:
             out[f"{head}_ppo_{c}"] = buf[8 + e]
         return out
 
-    def wait_wih(self, stream):
-        """`stream` (torch.cuda.Stream) waits until the last update() has finished the W_ih block of the gradient."""
-        _lib.check(self._lib.cadre_ppo_wait_wih(self._h, ctypes.c_void_p(stream.cuda_stream)))
+    # ---- data-parallel pipeline (see include/cadre_b200.h: cadre_ppo_set_grad_groups ...)
+    def set_grad_groups(self, groups):
+        _lib.check(self._lib.cadre_ppo_set_grad_groups(self._h, int(groups)))
+        self.grad_groups = int(groups)
+
+    def grad_range(self, group):
+        """(offset, count, mod_begin, mod_end) of group `group`'s LSTM tensors in the flat buffers; group = -1: the
+        actor-critic tensors of all experts."""
+        off, cnt = ctypes.c_int64(), ctypes.c_int64()
+        m0, m1 = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._lib.cadre_ppo_grad_range(self._h, int(group), ctypes.byref(off), ctypes.byref(cnt),
+                                                  ctypes.byref(m0), ctypes.byref(m1)))
+        return off.value, cnt.value, m0.value, m1.value
+
+    def wait_grads(self, group, stream):
+        """`stream` (torch.cuda.Stream) waits until the last update() has finished that range of the gradient."""
+        _lib.check(self._lib.cadre_ppo_wait_grads(self._h, int(group), ctypes.c_void_p(stream.cuda_stream)))
+
+    def adam_step_modules(self, params, grads, exp_avg, exp_avg_sq, step, mod_begin, mod_end, max_grad_norm=250.0,
+                          lr=3e-4, betas=(0.9, 0.999), eps=1e-8):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_adam_step_modules(
+                self._h, _lib.ptr(params), _lib.ptr(grads), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                ctypes.c_float(max_grad_norm), ctypes.c_float(lr), ctypes.c_float(betas[0]), ctypes.c_float(betas[1]),
+                ctypes.c_float(eps), int(step), int(mod_begin), int(mod_end), _lib.stream_ptr(self.device)))
 
     def check(self):
         """Synchronise and raise CadreError if a recurrence kernel of an earlier call timed out on a hand-off."""

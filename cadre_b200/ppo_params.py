@@ -11,8 +11,12 @@ E, F, LDF, G, HID, AMAX, B3A_LD = 8, 530, 532, 2120, 128, 33, 36
 HEADS = ("steer", "throttle")
 ACTIONS = {"steer": 33, "throttle": 3}
 
+# LSTM tensors are expert-major: block e = [W_ih | W_hh | b_ih | b_hh] of expert e (see ppo_layout.h); the
+# actor-critic tensors follow, kind-major.
+LSTM_WIH, LSTM_WHH, LSTM_BIH, LSTM_BHH = 0, G * LDF, 2 * G * LDF, 2 * G * LDF + G
+LSTM_BLK = 2 * G * LDF + 2 * G
 _sizes = [
-    ("WIH", E * G * LDF), ("WHH", E * G * LDF), ("BIH", E * G), ("BHH", E * G),
+    ("LSTM", E * LSTM_BLK),
     ("W1", E * 2 * HID * LDF), ("B1", E * 2 * HID), ("W2", E * 2 * HID * HID), ("B2", E * 2 * HID),
     ("W3A", E * AMAX * HID), ("B3A", E * B3A_LD), ("W3C", E * HID), ("B3C", E * 4),
 ]
@@ -59,11 +63,13 @@ def tensor_view(flat, module_name, param_name):
     except for LSTM tensors, whose rows are gate-interleaved (convert with _gate_(de)interleave)."""
     e = expert_of(module_name)
     if "_lstm_" in module_name:
-        key = {"rnn.weight_ih": "WIH", "rnn.weight_hh": "WHH", "rnn.bias_ih": "BIH", "rnn.bias_hh": "BHH"}[param_name]
-        if key in ("WIH", "WHH"):
-            v = flat[OFF[key] + e * G * LDF: OFF[key] + (e + 1) * G * LDF].view(G, LDF)[:, :F]
+        base = OFF["LSTM"] + e * LSTM_BLK
+        if param_name in ("rnn.weight_ih", "rnn.weight_hh"):
+            base += LSTM_WIH if param_name == "rnn.weight_ih" else LSTM_WHH
+            v = flat[base: base + G * LDF].view(G, LDF)[:, :F]
         else:
-            v = flat[OFF[key] + e * G: OFF[key] + (e + 1) * G]
+            base += LSTM_BIH if param_name == "rnn.bias_ih" else LSTM_BHH
+            v = flat[base: base + G]
         return v, True
     A = ACTIONS[module_name.split("_")[0]]
     br = 0 if param_name.startswith("control") else 1

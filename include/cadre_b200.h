@@ -189,11 +189,21 @@ int cadre_ppo_adam_step(void* handle, float* params, const float* grads, float* 
 /* gradient norms of the 16 modules seen by the last adam_step: [0..7] LSTM of expert e, [8..15] actor-critic
  * of expert e (expert = head*4 + command); synchronises */
 int cadre_ppo_module_norms(void* handle, float* norms16_host);
-/* Makes `stream` wait until the LAST cadre_ppo_update on this handle has finished the W_ih block of `grads`
- * (elements [0, 8*2120*532) of the flat buffer: the first of the two LSTM weight-gradient GEMMs). A data-parallel
- * caller can start the all-reduce of that block (Shared_grad_buffers.add_gradient, models.py:231-239) while the
- * W_hh gradient is still being computed. */
-int cadre_ppo_wait_wih(void* handle, void* stream);
+/* Data-parallel pipeline (replaces Shared_grad_buffers.add_gradient + the chief's single optimizer.step(),
+ * models.py:231-239, chief.py:13-21, by per-group all-reduce + clip + Adam overlapped with the backward pass).
+ * cadre_ppo_set_grad_groups(groups in {1, 2, 4, 8}): subsequent cadre_ppo_update calls produce the LSTM weight
+ * gradients per group of 8 / groups experts. cadre_ppo_grad_range: the contiguous [offset, offset + count) range of the
+ * flat buffers that holds group `group`'s LSTM tensors (group = -1: the actor-critic tensors of all experts) and the
+ * module ids [mod_begin, mod_end) it covers (module e < 8 = LSTM of expert e, 8 + e = actor-critic of expert e: each
+ * is one reference nn.Module, the unit of clip_grad_norm_). cadre_ppo_wait_grads: `stream` waits until the LAST
+ * cadre_ppo_update has finished that range of `grads`. cadre_ppo_adam_step_modules: clip + Adam restricted to the
+ * modules [mod_begin, mod_end). */
+int cadre_ppo_set_grad_groups(void* handle, int groups);
+int cadre_ppo_grad_range(void* handle, int group, int64_t* offset, int64_t* count, int* mod_begin, int* mod_end);
+int cadre_ppo_wait_grads(void* handle, int group, void* stream);
+int cadre_ppo_adam_step_modules(void* handle, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
+                                int mod_begin, int mod_end, void* stream);
 /* Synchronises and returns non-zero (cadre_last_error() explains) if a persistent LSTM recurrence kernel of an
  * earlier cadre_ppo_update / cadre_ppo_evaluate on this handle gave up waiting for a cross-CTA hand-off (its polling is
  * bounded so that a lost signal can never hang the GPU). */

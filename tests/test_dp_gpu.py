@@ -3,8 +3,9 @@ logical workers) against the oracle's chief step on the SUM over all four worker
 models.py:231-239, chief.py:12-24).
 
 With >= 2 GPUs the two ranks use one GPU each over NCCL; on a one-GPU box both ranks share cuda:0 and exchange the
-gradient with gloo (NCCL refuses two ranks on one device) - the learner code path (W_ih block reduced on a side stream
-behind `cadre_ppo_wait_wih`, remainder on the main stream, replicated clip + Adam) is the same."""
+gradient with gloo (NCCL refuses two ranks on one device) - the learner code path is the same: the gradient is
+all-reduced per contiguous range (actor-critic tensors, then one range per group of LSTM experts as their weight-gradient
+GEMMs finish) on a communication stream, and clip + Adam run per range behind it (`overlap=False`: one LSTM range)."""
 import os
 import sys
 

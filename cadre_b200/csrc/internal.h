@@ -181,6 +181,7 @@ struct OptTables {
   float* partial = nullptr;        // [num_chunks]
   float* clip_coef = nullptr;      // [16]
   float* norms = nullptr;          // [16]
+  float* scalars = nullptr;        // [2] Adam step size and sqrt(1 - beta2^step) of the current step
 };
 // Launch with the programmatic-stream-serialization attribute (PDL, see ptx.cuh): all kernels of the library
 // call pdl_wait() before touching global memory, so consecutive launches overlap prologue and launch latency
@@ -222,6 +223,6 @@ inline void ensure_dynamic_smem(Kern kern, size_t smem, size_t* flags) {
 // modules [mod_begin, mod_end) only (module e < 8: LSTM of expert e, 8 + e: actor-critic of expert e)
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
                       float lr, float beta1, float beta2, float eps, int step, cudaStream_t s, int mod_begin = 0,
-                      int mod_end = 16);
+                      int mod_end = 16, const int* dev_step = nullptr);
 
 }  // namespace cadre

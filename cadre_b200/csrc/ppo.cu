@@ -43,12 +43,17 @@ struct StorageRef {  // == cadre_storage_ref
 
 // ------------------------------------------------------------------------------------------ routing
 // Stable counting sort of the R = W*mb rows of one head by command (one CTA per head).
+// Minibatch indices live in a staged device table [steps][W][2][mb]; the update reads slice `*step_ctr`, which the
+// update's own prep_kernel advances afterwards. A sequence of update steps therefore needs no host-to-device copy
+// between steps and can be replayed from a CUDA graph (cadre_ppo_stage / cadre_ppo_update with indices_host = NULL).
 __global__ void __launch_bounds__(1024) route_kernel(const StorageRef* __restrict__ refs,
-                                                     const int* __restrict__ idx, int W, int mb,
+                                                     const int* __restrict__ idx_all,
+                                                     const int* __restrict__ step_ctr, int W, int mb,
                                                      int* __restrict__ row_slot, int* __restrict__ row_expert,
                                                      int* __restrict__ counts, int* __restrict__ counts9) {
   pdl_trigger();
   pdl_wait();
+  const int* idx = idx_all + static_cast<long long>(*step_ctr) * 2 * W * mb;
   __shared__ int base[4];
   __shared__ int wcnt[32][4];
   const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -102,7 +107,8 @@ struct RowScalars {
 };
 
 __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict__ refs,
-                                                   const int* __restrict__ idx, int W, int mb, int cap,
+                                                   const int* __restrict__ idx_all,
+                                                   const int* __restrict__ step_ctr, int W, int mb, int cap,
                                                    const int* __restrict__ row_slot,
                                                    const int* __restrict__ row_expert,
                                                    __half* __restrict__ X16, float* __restrict__ C9,
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
   pdl_trigger();
   pdl_wait();
   const int r = blockIdx.x, h = blockIdx.y, R = W * mb;
+  const int* idx = idx_all + static_cast<long long>(*step_ctr) * 2 * R;
   const int w = r / mb, i = r - w * mb;
   const StorageRef ref = refs[w * 2 + h];
   const int t = idx[(w * 2 + h) * mb + i];
@@ -158,10 +165,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const StorageRef* __restrict_
 constexpr int WGRAD_PAD_ROWS = 8;
 __global__ void prep_kernel(const float* __restrict__ params, float* __restrict__ o, int n,
                             const int* __restrict__ counts9, int* __restrict__ tile_list, int max_tiles,
-                            __half* __restrict__ dG16, int cap) {
+                            __half* __restrict__ dG16, int cap, int* __restrict__ step_ctr,
+                            int* __restrict__ opt_step) {
   pdl_trigger();
-  pdl_wait();
+  pdl_wait();          // the gather (previous launch) has consumed this step's index slice
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    *step_ctr += 1;    // the next update step reads the next slice of the staged table
+    *opt_step += 1;    // 1-based Adam step of this update (cadre_ppo_adam_step* with step = 0 reads it)
+  }
   if (i < n) {
     const int e = i / G, r = i - e * G;
     const float* blk = params + OFF_LSTM + e * LSTM_BLK;
@@ -594,7 +606,13 @@ __global__ void __launch_bounds__(256) wcvt_kernel(const float* __restrict__ par
   }
 }
 
+__global__ void set_counters_kernel(int* ctrs, int step_ctr, int opt_step) {
+  ctrs[0] = step_ctr;
+  ctrs[1] = opt_step;
+}
+
 // ------------------------------------------------------------------------------------------ plan
+constexpr int MAX_STAGED = 64;   // update steps whose minibatch indices can be staged at once (ppo_epoch x minibatches)
 struct PpoPlan {
   cadre_ppo_config cfg;
   int cap = 0, R = 0;
@@ -614,7 +632,13 @@ struct PpoPlan {
   float bwd_scale = 1.f;
   RowScalars sc{};
   int *row_slot = nullptr, *row_expert = nullptr, *counts = nullptr, *counts9 = nullptr;
-  int* idx_dev = nullptr;
+  int* idx_dev = nullptr;          // staged index table [MAX_STAGED][2 R]
+  int* ctrs = nullptr;             // [0] step counter into idx_dev, [1] 1-based Adam step of the current update
+  int32_t* idx_pinned = nullptr;   // pinned staging of the table and of the storage refs
+  StorageRef* refs_pinned = nullptr;
+  cudaEvent_t ev_staged = nullptr;
+  int staged_steps = 0;
+  int host_step = 1;               // Adam step the one-step (non-staged) path writes into ctrs[1]; see adam_step
   int* xp_tiles = nullptr;   // work list of the x-part GEMM (prep_kernel)
   int xp_max_tiles = 0;
   StorageRef* refs_dev = nullptr;
@@ -709,7 +733,11 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   P->row_expert = dalloc<int>(2 * static_cast<size_t>(P->R));
   P->counts = dalloc<int>(E);
   P->counts9 = dalloc<int>(E);
-  P->idx_dev = dalloc<int>(2 * static_cast<size_t>(P->R));
+  P->idx_dev = dalloc<int>(static_cast<size_t>(MAX_STAGED) * 2 * P->R);
+  P->ctrs = dalloc<int>(4);
+  CADRE_CUDA_CHECK(cudaHostAlloc(&P->idx_pinned, sizeof(int32_t) * MAX_STAGED * 2 * P->R, cudaHostAllocDefault));
+  CADRE_CUDA_CHECK(cudaHostAlloc(&P->refs_pinned, sizeof(StorageRef) * 2 * cfg->workers, cudaHostAllocDefault));
+  CADRE_CUDA_CHECK(cudaEventCreateWithFlags(&P->ev_staged, cudaEventDisableTiming));
   P->xp_max_tiles = (2 * 9 * P->R + 127) / 128 + E;   // sum_e ceil(9 count_e / 128), sum_e count_e = 2 R
   P->xp_tiles = dalloc<int>(1 + 2 * static_cast<size_t>(P->xp_max_tiles));
   P->refs_dev = dalloc<StorageRef>(2 * static_cast<size_t>(cfg->workers));
@@ -754,6 +782,7 @@ static PpoPlan* ppo_create(const cadre_ppo_config* cfg) {
   T.partial = dalloc<float>(coff.size());
   T.clip_coef = dalloc<float>(16);
   T.norms = dalloc<float>(16);
+  T.scalars = dalloc<float>(2);
   CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_off, coff.data(), coff.size() * 8, cudaMemcpyHostToDevice));
   CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_len, clen.data(), clen.size() * 4, cudaMemcpyHostToDevice));
   CADRE_CUDA_CHECK(cudaMemcpy(T.chunk_mod, cmod.data(), cmod.size() * 4, cudaMemcpyHostToDevice));
@@ -766,10 +795,13 @@ static void ppo_destroy(PpoPlan* P) {
   if (!P) return;
   void* ptrs[] = {P->head_partial, P->head_loss_e, P->X16, P->H16, P->G16, P->dG16, P->WIH16, P->WHH16, P->WHHT16, P->seq_sync, P->XP9, P->H8, P->C9, P->Y1, P->Y2, P->dZ1, P->dZ2, P->dH, P->dC, P->bsum,
                   P->sc.action, P->sc.worker, P->sc.old_v, P->sc.ret, P->sc.old_lp, P->sc.adv, P->row_slot,
-                  P->row_expert, P->counts, P->counts9, P->idx_dev, P->xp_tiles, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
-                  P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms};
+                  P->row_expert, P->counts, P->counts9, P->idx_dev, P->ctrs, P->xp_tiles, P->refs_dev, P->opt.chunk_off, P->opt.chunk_len,
+                  P->opt.chunk_mod, P->opt.mod_first, P->opt.partial, P->opt.clip_coef, P->opt.norms, P->opt.scalars};
   for (void* p : ptrs) cudaFree(p);
   if (P->side) cudaStreamDestroy(P->side);
+  if (P->idx_pinned) cudaFreeHost(P->idx_pinned);
+  if (P->refs_pinned) cudaFreeHost(P->refs_pinned);
+  if (P->ev_staged) cudaEventDestroy(P->ev_staged);
   if (P->ev_fork) cudaEventDestroy(P->ev_fork);
   if (P->ev_wcvt_fork) cudaEventDestroy(P->ev_wcvt_fork);
   if (P->ev_wcvt) cudaEventDestroy(P->ev_wcvt);
@@ -786,7 +818,26 @@ static GemmArgs tf32_gemm(int a_mn, int b_mn) {
   return g;
 }
 
-// routing + gather + forward through the second hidden layer (Y2); returns the number of kernels launched
+// Upload the storage references and the minibatch indices of `n_steps` consecutive update steps ([n_steps][W][2][mb])
+// and rewind the step counter; `first_step` is the 1-based Adam step of the first of them.
+static void ppo_stage(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host, int n_steps,
+                      int first_step, cudaStream_t s) {
+  CADRE_REQUIRE(n_steps >= 1 && n_steps <= MAX_STAGED, "between 1 and 64 update steps can be staged");
+  const int W = P->cfg.workers, R = P->R;
+  CADRE_CUDA_CHECK(cudaEventSynchronize(P->ev_staged));   // the previous upload has left the pinned buffers
+  memcpy(P->idx_pinned, idx_host, sizeof(int32_t) * static_cast<size_t>(n_steps) * 2 * R);
+  memcpy(P->refs_pinned, refs_host, sizeof(StorageRef) * 2 * W);
+  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, P->idx_pinned, sizeof(int32_t) * static_cast<size_t>(n_steps) * 2 * R,
+                                   cudaMemcpyHostToDevice, s));
+  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, P->refs_pinned, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
+  set_counters_kernel<<<1, 1, 0, s>>>(P->ctrs, 0, first_step - 1);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+  CADRE_CUDA_CHECK(cudaEventRecord(P->ev_staged, s));
+  P->staged_steps = n_steps;
+}
+
+// routing + gather + forward through the second hidden layer (Y2); returns the number of kernels launched.
+// idx_host == nullptr: use the staged table (no host copies: capturable in a CUDA graph).
 static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int32_t* idx_host,
                        const float* params, cudaStream_t s) {
   const int W = P->cfg.workers, mb = P->cfg.mini_batch, cap = P->cap, R = P->R;
@@ -803,14 +854,13 @@ static int ppo_forward(PpoPlan* P, const cadre_storage_ref* refs_host, const int
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync, 0, sizeof(unsigned) * E, s));            // forward hand-off counters
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 16, 0, sizeof(unsigned) * E, s));       // backward
   CADRE_CUDA_CHECK(cudaMemsetAsync(P->seq_sync + 32, 0, sizeof(unsigned) * (E + 1), s));  // head_kernel reductions
-  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->idx_dev, idx_host, sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s));
-  CADRE_CUDA_CHECK(cudaMemcpyAsync(P->refs_dev, refs_host, sizeof(StorageRef) * 2 * W, cudaMemcpyHostToDevice, s));
-  launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, W, mb, P->row_slot, P->row_expert, P->counts,
-                                  P->counts9), ++n;
-  launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, W, mb, cap, P->row_slot, P->row_expert,
+  if (idx_host != nullptr) ppo_stage(P, refs_host, idx_host, 1, P->host_step, s);   // one-step table
+  launch_k(route_kernel, dim3(2), dim3(1024), 0, s, P->refs_dev, P->idx_dev, P->ctrs, W, mb, P->row_slot, P->row_expert,
+           P->counts, P->counts9), ++n;
+  launch_k(pack_kernel, dim3(dim3(R, 2)), dim3(256), 0, s, P->refs_dev, P->idx_dev, P->ctrs, W, mb, cap, P->row_slot, P->row_expert,
                                          P->X16, P->C9, P->H16, P->sc), ++n;
   launch_k(prep_kernel, dim3((E * G + 255) / 256), dim3(256), 0, s, params, P->bsum, E * G,
-           P->counts9, P->xp_tiles, P->xp_max_tiles, P->dG16, cap), ++n;
+           P->counts9, P->xp_tiles, P->xp_max_tiles, P->dG16, cap, P->ctrs, P->ctrs + 1), ++n;
   CADRE_CUDA_CHECK(cudaGetLastError());
 
   // ---- forward
@@ -1002,12 +1052,23 @@ int cadre_ppo_destroy(void* handle) {
   CADRE_API_END
 }
 
+int cadre_ppo_stage(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host, int n_steps,
+                    int first_adam_step, void* stream) {
+  CADRE_API_BEGIN
+  CADRE_REQUIRE(handle && storages_host && indices_host && first_adam_step >= 1, "ppo_stage arguments");
+  cadre::ppo_stage(static_cast<PpoPlan*>(handle), storages_host, indices_host, n_steps, first_adam_step,
+                   static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
 int cadre_ppo_update(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
                      float* params, float* grads, float* losses, void* stream) {
   CADRE_API_BEGIN
-  CADRE_REQUIRE(handle && storages_host && indices_host && params && grads && losses, "ppo_update pointers");
-  cadre::ppo_update(static_cast<PpoPlan*>(handle), storages_host, indices_host, params, grads, losses,
-                    static_cast<cudaStream_t>(stream));
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && params && grads && losses, "ppo_update pointers");
+  CADRE_REQUIRE((storages_host != nullptr) == (indices_host != nullptr), "storages and indices go together");
+  CADRE_REQUIRE(indices_host != nullptr || P->staged_steps > 0, "ppo_update without indices needs cadre_ppo_stage first");
+  cadre::ppo_update(P, storages_host, indices_host, params, grads, losses, static_cast<cudaStream_t>(stream));
   CADRE_API_END
 }
 
@@ -1029,9 +1090,11 @@ int cadre_ppo_adam_step(void* handle, float* params, const float* grads, float* 
                         float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
                         void* stream) {
   CADRE_API_BEGIN
-  CADRE_REQUIRE(handle && params && grads && exp_avg && exp_avg_sq && step >= 1, "adam_step arguments");
-  cadre::launch_clip_adam(static_cast<PpoPlan*>(handle)->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm,
-                          lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream));
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && params && grads && exp_avg && exp_avg_sq && step >= 0, "adam_step arguments");
+  if (step >= 1) P->host_step = step + 1;   // the one-step update path restarts the device counter from here
+  cadre::launch_clip_adam(P->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm, lr, beta1, beta2, eps, step,
+                          static_cast<cudaStream_t>(stream), 0, 16, P->ctrs + 1);
   CADRE_API_END
 }
 
@@ -1078,9 +1141,10 @@ int cadre_ppo_adam_step_modules(void* handle, float* params, const float* grads,
                                 float max_grad_norm, float lr, float beta1, float beta2, float eps, int step,
                                 int mod_begin, int mod_end, void* stream) {
   CADRE_API_BEGIN
-  CADRE_REQUIRE(handle && params && grads && exp_avg && exp_avg_sq && step >= 1, "adam_step arguments");
-  cadre::launch_clip_adam(static_cast<PpoPlan*>(handle)->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm,
-                          lr, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream), mod_begin, mod_end);
+  PpoPlan* P = static_cast<PpoPlan*>(handle);
+  CADRE_REQUIRE(P && params && grads && exp_avg && exp_avg_sq && step >= 0, "adam_step arguments");
+  cadre::launch_clip_adam(P->opt, params, grads, exp_avg, exp_avg_sq, max_grad_norm, lr, beta1, beta2, eps, step,
+                          static_cast<cudaStream_t>(stream), mod_begin, mod_end, P->ctrs + 1);
   CADRE_API_END
 }
 

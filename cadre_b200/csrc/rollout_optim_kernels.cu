@@ -220,11 +220,21 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __rest
 
 __global__ void sqnorm_final_kernel(const float* __restrict__ partial, const int* __restrict__ mod_first,
                                     float max_norm, float* __restrict__ clip_coef, float* __restrict__ norms,
-                                    int mod_begin) {
+                                    int mod_begin, int step, const int* __restrict__ dev_step, float lr, float beta1,
+                                    float beta2, float* __restrict__ scalars) {
   pdl_trigger();
   pdl_wait();
   // one warp per module; chunks of a module are contiguous in the chunk table
   const int m = mod_begin + blockIdx.x, lane = threadIdx.x;
+  if (blockIdx.x == 0 && lane == 0) {
+    // torch.optim.Adam: step_size = lr / (1 - beta1^step); denom = sqrt(v) / sqrt(1 - beta2^step) + eps. The step
+    // comes from the host (step >= 1) or from the device counter the update kernels advance (step = 0: CUDA graphs)
+    const int st = step >= 1 ? step : *dev_step;
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(st));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(st));
+    scalars[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    scalars[1] = static_cast<float>(sqrt(bc2));
+  }
   double s = 0.0;
   for (int i = mod_first[m] + lane; i < mod_first[m + 1]; i += 32) s += static_cast<double>(partial[i]);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -241,10 +251,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const int* __restrict__ chunk_len,
                                                    const int* __restrict__ chunk_mod,
                                                    const float* __restrict__ clip_coef, float beta1,
-                                                   float beta2, float eps, float step_size,
-                                                   float bc2_sqrt) {
+                                                   float beta2, float eps, const float* __restrict__ scalars) {
   pdl_trigger();
   pdl_wait();
+  const float step_size = scalars[0], bc2_sqrt = scalars[1];
   const long long off = chunk_off[blockIdx.x];
   const int len = chunk_len[blockIdx.x];
   const float coef = clip_coef[chunk_mod[blockIdx.x]];
@@ -272,20 +282,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 void launch_clip_adam(const OptTables& t, float* params, const float* grads, float* m, float* v, float max_norm,
                       float lr, float beta1, float beta2, float eps, int step, cudaStream_t s, int mod_begin,
-                      int mod_end) {
+                      int mod_end, const int* dev_step) {
   CADRE_REQUIRE(mod_begin >= 0 && mod_begin < mod_end && mod_end <= 16, "module range");
+  CADRE_REQUIRE(step >= 1 || dev_step != nullptr, "Adam step");
   // chunks of modules [mod_begin, mod_end) are contiguous in the chunk table (it is sorted by module)
   const int c0 = t.mod_first_h[mod_begin], nc = t.mod_first_h[mod_end] - c0;
   if (nc <= 0) return;
   launch_k(sqnorm_partial_kernel, dim3(nc), dim3(256), 0, s, grads, t.chunk_off + c0, t.chunk_len + c0, t.partial + c0);
   launch_k(sqnorm_final_kernel, dim3(mod_end - mod_begin), dim3(32), 0, s, t.partial, t.mod_first, max_norm, t.clip_coef,
-           t.norms, mod_begin);
-  // torch.optim.Adam: step_size = lr / (1 - beta1^step); denom = sqrt(v) / sqrt(1 - beta2^step) + eps
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+           t.norms, mod_begin, step, dev_step, lr, beta1, beta2, t.scalars);
   launch_k(adam_kernel, dim3(nc), dim3(256), 0, s, params, grads, m, v, t.chunk_off + c0, t.chunk_len + c0, t.chunk_mod + c0,
-                                           t.clip_coef, beta1, beta2, eps, static_cast<float>(lr / bc1),
-                                           static_cast<float>(sqrt(bc2)));
+           t.clip_coef, beta1, beta2, eps, t.scalars);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

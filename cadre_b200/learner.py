@@ -81,6 +81,8 @@ class Learner:
         self.pg = process_group
         self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
         self._comm_stream = None
+        self._use_graph = os.environ.get("CADRE_NO_GRAPH", "0") != "1"
+        self._graph, self._graph_key, self._warm_key = None, None, None
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -128,7 +130,7 @@ class Learner:
     # ---------------------------------------------------------------- one synchronous update step
     def _setup_pipeline(self):
         """Streams, events and flat-buffer ranges of the data-parallel gradient pipeline (built on first use)."""
-        groups = int(os.environ.get("CADRE_GRAD_GROUPS", "4")) if self.overlap_allreduce else 1
+        groups = int(os.environ.get("CADRE_GRAD_GROUPS", "2")) if self.overlap_allreduce else 1
         self.engine.set_grad_groups(groups)
         self._comm_stream = torch.cuda.Stream(device=self.device)
         self._ranges = [self.engine.grad_range(g) for g in range(groups)] + [self.engine.grad_range(-1)]
@@ -136,9 +138,9 @@ class Learner:
         self._reduced = [torch.cuda.Event() for _ in self._ranges]
         assert sum(r[1] for r in self._ranges) == self.grads.numel()
 
-    def update_step(self, storages, indices, async_losses=True):
-        """update_policy for all local workers -> all-reduce(sum) -> per-module clip + Adam.
-        storages[w] = (steer, throttle) RolloutStorage with `.advantages`; indices int32 [W,2,mb].
+    def _exchange_and_step(self, step):
+        """all-reduce(sum) + per-module clip + Adam on the gradient the last engine.update left in self.grads.
+        `step`: 1-based Adam step, or 0 to use the device-side counter (staged / graph-captured sequences).
 
         With more than one rank the gradient exchange is pipelined against the end of the backward pass: the LSTM
         weight gradients (72 of the 78 MB) are produced per group of experts, each group one contiguous range of the
@@ -146,11 +148,6 @@ class Learner:
         first: it is final before BPTT ends) while the GEMMs of group k+1 still run, and the main stream applies
         clip + Adam to the modules of range k - a per-module operation, chief.py:16-21 - while range k+1 is on the
         wire. Sums, clip coefficients and Adam arithmetic are those of the single all-reduce + single step."""
-        advs = [(s.advantages, t.advantages) for s, t in storages]
-        if self.world > 1 and self._comm_stream is None:
-            self._setup_pipeline()
-        self.engine.update(storages, advs, indices, self.params, self.grads, self.losses)
-        self.step_count += 1
         if self.world > 1:
             main = torch.cuda.current_stream(self.device)
             order = [len(self._ranges) - 1] + list(range(len(self._ranges) - 1))     # actor-critic range first
@@ -164,14 +161,23 @@ class Learner:
             for k in order:
                 _, _, m0, m1 = self._ranges[k]
                 main.wait_event(self._reduced[k])
-                self.engine.adam_step_modules(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
-                                              m0, m1, self.max_grad_norm, self.lr)
-            self._comm_stream.wait_stream(main)      # the next update overwrites `grads`: order it after these reads
+                self.engine.adam_step_modules(self.params, self.grads, self.exp_avg, self.exp_avg_sq, step, m0, m1,
+                                              self.max_grad_norm, self.lr)
         else:
-            self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count,
-                                  self.max_grad_norm, self.lr)
+            self.engine.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, step, self.max_grad_norm,
+                                  self.lr)
         self.loss_sum += self.losses
         self.loss_steps += 1
+
+    def update_step(self, storages, indices, async_losses=True):
+        """update_policy for all local workers -> all-reduce(sum) -> per-module clip + Adam (one step, eagerly).
+        storages[w] = (steer, throttle) RolloutStorage with `.advantages`; indices int32 [W,2,mb]."""
+        advs = [(s.advantages, t.advantages) for s, t in storages]
+        if self.world > 1 and self._comm_stream is None:
+            self._setup_pipeline()
+        self.engine.update(storages, advs, indices, self.params, self.grads, self.losses)
+        self.step_count += 1
+        self._exchange_and_step(self.step_count)
         return self.losses if async_losses else self.scaled_losses()
 
     def scaled_losses(self, mean=False):
@@ -181,17 +187,58 @@ class Learner:
         L = (self.loss_sum / max(1, self.loss_steps) if mean else self.losses).sum(1).cpu()
         return L * torch.tensor([self.value_coeff, self.clip_coeff, self.ent_coeff])
 
+    # ---------------------------------------------------------------- a whole learn() phase
+    def _staged_step(self):
+        """One update step on the next staged index slice; nothing in here touches host data, so the sequence of
+        launches (kernels of the update, NCCL all-reduces, clip + Adam) is the same every time: a CUDA graph."""
+        self.engine.update_staged(self.params, self.grads, self.losses)
+        self._exchange_and_step(0)
+
     def learn(self, pool_or_storages, ppo_epoch=4):
-        """ppo_epoch x minibatches of update_step over already computed returns/advantages (train.py:93-110)."""
+        """ppo_epoch x minibatches of update steps over already computed returns / advantages (train.py:93-110).
+        All minibatch indices of the phase are drawn first (same per-worker RNG streams and order as one generator
+        pair per epoch, train.py:94) and uploaded once; the update steps then run from a CUDA graph captured on the
+        first call for these storages (CADRE_NO_GRAPH=1: eager launches)."""
         storages = pool_or_storages.storages if hasattr(pool_or_storages, "storages") else pool_or_storages
         self.loss_sum.zero_()
         self.loss_steps = 0
+        if self.world > 1 and self._comm_stream is None:
+            self._setup_pipeline()
+        idx_all = np.concatenate([self.sample_epoch_indices(storages) for _ in range(ppo_epoch)], 0)
+        advs = [(s.advantages, t.advantages) for s, t in storages]
         n = 0
-        for _ in range(ppo_epoch):
-            for idx in self.sample_epoch_indices(storages):
-                self.update_step(storages, idx)
-                n += 1
-        return n
+        while n < idx_all.shape[0]:                       # (the staging table holds 64 steps)
+            m = min(64, idx_all.shape[0] - n)
+            self.engine.stage(storages, advs, idx_all[n:n + m], self.step_count + 1)
+            key = tuple(getattr(st, name).data_ptr() for pair in storages for st in pair
+                        for name in ("obs", "action", "advantages", "command"))
+            if self._graph is not None and self._graph_key != key:
+                self._graph = None                         # other storages: the captured pointers are stale
+            if self._use_graph and self._graph is None and self._warm_key == key:
+                self._capture(key)                         # an eager learn() on these storages has warmed everything
+            for _ in range(m):
+                if self._graph is not None:
+                    self._graph.replay()
+                else:
+                    self._staged_step()
+                self.step_count += 1
+            self._warm_key = key
+            n += m
+        self.loss_steps = idx_all.shape[0]
+        return idx_all.shape[0]
+
+    def _capture(self, key):
+        """Capture one staged update step (update kernels, all-reduces, clip + Adam, loss accumulation) in a CUDA
+        graph. Capturing does not execute: no staged slice and no Adam step is consumed."""
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._staged_step()
+            self._graph, self._graph_key = g, key
+        except Exception as e:                             # keep working without the graph
+            self._use_graph, self._graph = False, None
+            import warnings
+            warnings.warn(f"cadre_b200: CUDA graph capture of the update step failed ({e}); using eager launches")
 
     def state(self):
         return ppo_params.unpack_state(self.params)

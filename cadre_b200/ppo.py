@@ -93,6 +93,29 @@ class PpoEngine:
                                                   _lib.stream_ptr(self.device)))
         return losses
 
+    def stage(self, storages, advantages, indices_all, first_adam_step):
+        """Upload the storage references and the indices of a SEQUENCE of update steps, int [n_steps, W, 2, mb]; each
+        following `update_staged` consumes the next slice and advances the device-side Adam step (the first one is
+        `first_adam_step`, 1-based), which `adam_step*` use when called with step=0."""
+        assert len(storages) == self.workers and len(advantages) == self.workers
+        for w in range(self.workers):
+            for h in range(2):
+                self._refs[w * 2 + h] = storage_ref(storages[w][h], advantages[w][h])
+        idx = np.ascontiguousarray(np.asarray(indices_all, dtype=np.int32))
+        assert idx.ndim == 4 and idx.shape[1:] == (self.workers, 2, self.mini_batch), idx.shape
+        self._keep = (storages, advantages, idx)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_stage(self._h, self._refs, idx.ctypes.data_as(ctypes.c_void_p), idx.shape[0],
+                                                 int(first_adam_step), _lib.stream_ptr(self.device)))
+        return idx.shape[0]
+
+    def update_staged(self, params, grads, losses):
+        """`update` on the next staged index slice: no host data, capturable in a CUDA graph."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.cadre_ppo_update(self._h, None, None, _lib.ptr(params), _lib.ptr(grads),
+                                                  _lib.ptr(losses), _lib.stream_ptr(self.device)))
+        return losses
+
     def evaluate(self, storages, advantages, indices, params):
         """Forward only: returns [2, W*mb, 36] = value, log-prob(action), entropy, 33 normalised logits."""
         idx = self._marshal(storages, advantages, indices)

@@ -175,7 +175,14 @@ int cadre_ppo_create(void** handle, const cadre_ppo_config* cfg);
 int cadre_ppo_destroy(void* handle);
 /* storages_host: [workers][2] (steer, throttle); indices_host: int32 [workers][2][mini_batch] minibatch row
  * indices (host-generated, bit-exact torch.randperm chunks); losses: device fp32 [workers][2][3] =
- * per-worker, per-head UN-scaled (value, action, entropy) losses. grads is overwritten. */
+ * per-worker, per-head UN-scaled (value, action, entropy) losses. grads is overwritten.
+ * Staged form for a sequence of update steps on the same storages (train.py:93-110: ppo_epoch x minibatches):
+ * cadre_ppo_stage uploads the storage references and the indices of n_steps <= 64 steps ([n_steps][workers][2][mb])
+ * once; each following cadre_ppo_update(handle, NULL, NULL, ...) consumes the next slice (a device-side counter) and
+ * advances the device-side Adam step (starting at first_adam_step), which cadre_ppo_adam_step* use when called with
+ * step = 0. Such an update + adam sequence issues no host-to-device copy and can be captured in a CUDA graph. */
+int cadre_ppo_stage(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host, int n_steps,
+                    int first_adam_step, void* stream);
 int cadre_ppo_update(void* handle, const cadre_storage_ref* storages_host, const int32_t* indices_host,
                      float* params, float* grads, float* losses, void* stream);
 /* Forward only (CadreAgent.act / get_value, Model.evaluate_actions; agent.py:114-164, models.py:184-212):

@@ -81,8 +81,6 @@ class Learner:
         self.pg = process_group
         self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
         self._comm_stream = None
-        self._use_graph = os.environ.get("CADRE_NO_GRAPH", "0") != "1"
-        self._graph, self._graph_key, self._warm_key = None, None, None
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -140,7 +138,7 @@ class Learner:
 
     def _exchange_and_step(self, step):
         """all-reduce(sum) + per-module clip + Adam on the gradient the last engine.update left in self.grads.
-        `step`: 1-based Adam step, or 0 to use the device-side counter (staged / graph-captured sequences).
+        `step`: 1-based Adam step, or 0 to use the device-side counter (staged sequences of update steps).
 
         With more than one rank the gradient exchange is pipelined against the end of the backward pass: the LSTM
         weight gradients (72 of the 78 MB) are produced per group of experts, each group one contiguous range of the
@@ -188,17 +186,12 @@ class Learner:
         return L * torch.tensor([self.value_coeff, self.clip_coeff, self.ent_coeff])
 
     # ---------------------------------------------------------------- a whole learn() phase
-    def _staged_step(self):
-        """One update step on the next staged index slice; nothing in here touches host data, so the sequence of
-        launches (kernels of the update, NCCL all-reduces, clip + Adam) is the same every time: a CUDA graph."""
-        self.engine.update_staged(self.params, self.grads, self.losses)
-        self._exchange_and_step(0)
-
     def learn(self, pool_or_storages, ppo_epoch=4):
         """ppo_epoch x minibatches of update steps over already computed returns / advantages (train.py:93-110).
         All minibatch indices of the phase are drawn first (same per-worker RNG streams and order as one generator
-        pair per epoch, train.py:94) and uploaded once; the update steps then run from a CUDA graph captured on the
-        first call for these storages (CADRE_NO_GRAPH=1: eager launches)."""
+        pair per epoch, train.py:94) and uploaded once together with the storage references; every update step then
+        consumes the next slice of that device-side table (and the device-side Adam step), so no host data moves
+        between the steps of a phase."""
         storages = pool_or_storages.storages if hasattr(pool_or_storages, "storages") else pool_or_storages
         self.loss_sum.zero_()
         self.loss_steps = 0
@@ -210,35 +203,13 @@ class Learner:
         while n < idx_all.shape[0]:                       # (the staging table holds 64 steps)
             m = min(64, idx_all.shape[0] - n)
             self.engine.stage(storages, advs, idx_all[n:n + m], self.step_count + 1)
-            key = tuple(getattr(st, name).data_ptr() for pair in storages for st in pair
-                        for name in ("obs", "action", "advantages", "command"))
-            if self._graph is not None and self._graph_key != key:
-                self._graph = None                         # other storages: the captured pointers are stale
-            if self._use_graph and self._graph is None and self._warm_key == key:
-                self._capture(key)                         # an eager learn() on these storages has warmed everything
             for _ in range(m):
-                if self._graph is not None:
-                    self._graph.replay()
-                else:
-                    self._staged_step()
+                self.engine.update_staged(self.params, self.grads, self.losses)
+                self._exchange_and_step(0)
                 self.step_count += 1
-            self._warm_key = key
             n += m
         self.loss_steps = idx_all.shape[0]
         return idx_all.shape[0]
-
-    def _capture(self, key):
-        """Capture one staged update step (update kernels, all-reduces, clip + Adam, loss accumulation) in a CUDA
-        graph. Capturing does not execute: no staged slice and no Adam step is consumed."""
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._staged_step()
-            self._graph, self._graph_key = g, key
-        except Exception as e:                             # keep working without the graph
-            self._use_graph, self._graph = False, None
-            import warnings
-            warnings.warn(f"cadre_b200: CUDA graph capture of the update step failed ({e}); using eager launches")
 
     def state(self):
         return ppo_params.unpack_state(self.params)

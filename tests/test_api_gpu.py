@@ -288,3 +288,37 @@ def test_batched_actor_sampler_follows_the_policy_distribution(agent):
             # log-prob returned with the action is the policy's
             a = int(actions[0, h])
             assert abs(logp[0, h].item() - torch.log(p[a]).item()) < 2e-2
+
+
+def test_learn_staged_steps_equal_step_by_step_updates():
+    """Learner.learn uploads the indices of all its update steps once and runs them from the device-side table (and
+    the device-side Adam step counter); the parameters after three learn() phases (12 update steps, Adam's
+    bias-corrected step sizes included) are bit-identical to driving update_step with the same indices one by one."""
+    from cadre_b200.learner import Learner, RolloutPool
+    ppo = R.ppo_fixture_state(0)
+    cfg = dict(num_steps=64, mini_batch_num=2, feature_dims=530, seq_length=8, use_gae=True, gamma=0.99, tau=0.95)
+    results = []
+    for staged in (True, False):
+        learner = Learner(2, 32, ppo, "cuda:0", seeds=[7, 8])
+        pool = RolloutPool(2, cfg, "cuda:0")
+        g = torch.Generator(device="cuda").manual_seed(3)
+        b = pool.batched
+        b["obs"].copy_(torch.randn(b["obs"].shape, device="cuda", generator=g))
+        b["rewards"].copy_(torch.rand(b["rewards"].shape, device="cuda", generator=g))
+        b["masks"].copy_((torch.rand(b["masks"].shape, device="cuda", generator=g) > 0.05).float())
+        b["command"].copy_(torch.randint(0, 4, b["command"].shape, device="cuda", generator=g, dtype=torch.int32))
+        b["action_log_probs"].copy_(-0.5 - 2.5 * torch.rand(b["action_log_probs"].shape, device="cuda", generator=g))
+        b["value_preds"].copy_(torch.randn(b["value_preds"].shape, device="cuda", generator=g))
+        b["action"].copy_(torch.randint(0, 3, b["action"].shape, device="cuda", generator=g))
+        pool.compute_returns(torch.zeros(2, 2))
+        for _ in range(3):
+            if staged:
+                assert learner.learn(pool, 2) == 4
+            else:
+                for _ in range(2):
+                    for idx in learner.sample_epoch_indices(pool.storages):
+                        learner.update_step(pool.storages, idx)
+        learner.engine.check()
+        assert learner.step_count == 12
+        results.append((learner.params.clone(), learner.exp_avg_sq.clone()))
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])

@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 W_LOCAL, MB, T, WORLD = 2, 100, 200, 2
+_LEARN_RESULTS = {}
 
 
 def _fill_worker(gid):
@@ -56,8 +57,15 @@ def _rank(rank, world, port, out_dir, backend, overlap):
     learner.update_step(pool.storages, idx[0])
     learner.update_step(pool.storages, idx[1])           # a second step: Adam moments + step count in play
     torch.cuda.synchronize()
-    torch.save({"params": learner.params.cpu(), "idx": idx, "losses": learner.scaled_losses(),
-                "grads": learner.grads.cpu()}, os.path.join(out_dir, f"rank{rank}.pt"))
+    out = {"params": learner.params.cpu(), "idx": idx, "losses": learner.scaled_losses(), "grads": learner.grads.cpu()}
+    # three learn() phases of one epoch (2 staged update steps each)
+    for _ in range(3):
+        learner.learn(pool, 1)
+    torch.cuda.synchronize()
+    learner.engine.check()
+    out["params_learn"] = learner.params.cpu()
+    out["steps"] = learner.step_count
+    torch.save(out, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,6 +81,13 @@ def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap):
     # replicas are bit-identical (same reduced gradient, same deterministic clip + Adam)
     assert torch.equal(res[0]["params"], res[1]["params"])
     assert torch.equal(res[0]["grads"], res[1]["grads"])
+    assert torch.equal(res[0]["params_learn"], res[1]["params_learn"]) and res[0]["steps"] == 8
+    assert torch.isfinite(res[0]["params_learn"]).all() and not torch.equal(res[0]["params_learn"], res[0]["params"])
+    # pipelined ranges (overlap=True) and one LSTM range (overlap=False) are the same arithmetic: bit-identical
+    # parameters after 8 steps
+    _LEARN_RESULTS[overlap] = res[0]["params_learn"]
+    if len(_LEARN_RESULTS) == 2:
+        assert torch.equal(_LEARN_RESULTS[True], _LEARN_RESULTS[False])
 
     # oracle: four reference workers + the chief, two update steps
     torch.set_num_threads(min(16, os.cpu_count() or 1))

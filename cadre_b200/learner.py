@@ -127,12 +127,18 @@ class Learner:
 
     # ---------------------------------------------------------------- one synchronous update step
     def _setup_pipeline(self):
-        """Streams, events and flat-buffer ranges of the data-parallel gradient pipeline (built on first use)."""
+        """Streams, events and flat-buffer ranges of the data-parallel gradient pipeline (built on first use).
+        Range k < groups - 1 = LSTM tensors of expert group k; the last range = LSTM tensors of the last group PLUS the
+        actor-critic tensors of all experts, which follow them directly in the flat buffer (one collective less, and
+        no collective is in flight next to the persistent BPTT kernel, which needs every SM it was launched on)."""
         groups = int(os.environ.get("CADRE_GRAD_GROUPS", "2")) if self.overlap_allreduce else 1
         self.engine.set_grad_groups(groups)
         self._comm_stream = torch.cuda.Stream(device=self.device)
-        self._ranges = [self.engine.grad_range(g) for g in range(groups)] + [self.engine.grad_range(-1)]
-        self._group_ids = list(range(groups)) + [-1]
+        lstm = [self.engine.grad_range(g) for g in range(groups)]
+        mlp = self.engine.grad_range(-1)
+        assert lstm[-1][0] + lstm[-1][1] == mlp[0] and lstm[-1][3] == mlp[2]      # contiguous ranges and module ids
+        self._ranges = lstm[:-1] + [(lstm[-1][0], lstm[-1][1] + mlp[1], lstm[-1][2], mlp[3])]
+        self._waits = [[g] for g in range(groups - 1)] + [[groups - 1, -1]]
         self._reduced = [torch.cuda.Event() for _ in self._ranges]
         assert sum(r[1] for r in self._ranges) == self.grads.numel()
 
@@ -142,22 +148,20 @@ class Learner:
 
         With more than one rank the gradient exchange is pipelined against the end of the backward pass: the LSTM
         weight gradients (72 of the 78 MB) are produced per group of experts, each group one contiguous range of the
-        flat buffer; a communication stream all-reduces range k as soon as its event fires (the actor-critic range
-        first: it is final before BPTT ends) while the GEMMs of group k+1 still run, and the main stream applies
-        clip + Adam to the modules of range k - a per-module operation, chief.py:16-21 - while range k+1 is on the
-        wire. Sums, clip coefficients and Adam arithmetic are those of the single all-reduce + single step."""
+        flat buffer; a communication stream all-reduces range k as soon as its event fires while the GEMMs of group
+        k+1 still run, and the main stream applies clip + Adam to the modules of range k - a per-module operation,
+        chief.py:16-21 - while range k+1 is on the wire. Sums, clip coefficients and Adam arithmetic are those of the
+        single all-reduce + single step."""
         if self.world > 1:
             main = torch.cuda.current_stream(self.device)
-            order = [len(self._ranges) - 1] + list(range(len(self._ranges) - 1))     # actor-critic range first
             with torch.cuda.stream(self._comm_stream):
-                for k in order:
-                    off, cnt, _, _ = self._ranges[k]
-                    self.engine.wait_grads(self._group_ids[k], self._comm_stream)
+                for k, (off, cnt, _, _) in enumerate(self._ranges):
+                    for g in self._waits[k]:
+                        self.engine.wait_grads(g, self._comm_stream)
                     torch.distributed.all_reduce(self.grads[off:off + cnt], op=torch.distributed.ReduceOp.SUM,
                                                  group=self.pg)
                     self._reduced[k].record(self._comm_stream)
-            for k in order:
-                _, _, m0, m1 = self._ranges[k]
+            for k, (_, _, m0, m1) in enumerate(self._ranges):
                 main.wait_event(self._reduced[k])
                 self.engine.adam_step_modules(self.params, self.grads, self.exp_avg, self.exp_avg_sq, step, m0, m1,
                                               self.max_grad_norm, self.lr)

@@ -116,7 +116,7 @@ def sample_clocks_stop(p, path):
     except Exception:
         pass
     if sm:
-        busy = sorted(sm)[len(sm) // 4:]          # drop idle samples at the edges
+        busy = sorted(sm)[len(sm) // 2:]          # the sampler also sees start-up and warm-up: keep the loaded half
         out["sm_mhz"] = float(np.median(busy))
         out["sm_max_mhz"] = float(max(mx))
         out["reasons"] = sorted(reasons)
@@ -277,6 +277,9 @@ def run_cadre(args):
     numa, full_affinity = bind_to_gpu_numa_node(local)
     dist = torch.distributed
     if world > 1:
+        # measured on 8 x B200 (tools/gpu_probe_allreduce.py): the 78 MB / 36 MB gradient all-reduces take 0.27 / 0.15 ms
+        # with the ring algorithm against 0.32 / 0.17 ms with NCCL's default choice (NVLS) for these sizes
+        os.environ.setdefault("NCCL_ALGO", "Ring")
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__
     if rank == 0:
@@ -348,15 +351,15 @@ def run_cadre(args):
             losses_h.copy_(learner.losses, non_blocking=True)
 
     def timed(fn, steps, warmup, sample=False):
+        proc = path = None
+        if sample:      # nvidia-smi needs a few hundred ms to start: launch it before the warm-up steps
+            proc, path = sample_clocks_start()
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        proc = path = None
-        if sample:
-            proc, path = sample_clocks_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):

@@ -17,6 +17,7 @@ their own CUDA streams (the tail of one chunk's persistent kernels is filled by 
 chunks are small because the encoder cannot start before its first chunk has landed.
 """
 import ctypes
+import os
 
 import torch
 
@@ -24,10 +25,15 @@ from . import _lib
 from .encoder import Encoder
 
 
-def chunk_schedule(n, max_chunk, ramp=(128, 512)):
+def _default_ramp():
+    v = os.environ.get("CADRE_INGEST_RAMP")
+    return tuple(int(x) for x in v.split(",") if x) if v is not None else (128, 512)
+
+
+def chunk_schedule(n, max_chunk, ramp=None):
     """Chunk sizes covering n frames: a short ramp (PCIe latency hiding), then `max_chunk`, then the remainder."""
     sizes, left = [], n
-    for r in ramp:
+    for r in (_default_ramp() if ramp is None else ramp):
         if left > max_chunk and r < max_chunk:
             sizes.append(r)
             left -= r

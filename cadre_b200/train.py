@@ -71,6 +71,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_ALGO", "Ring")   # faster than NCCL's default for the 36 - 78 MB gradient ranges (8 x B200)
         torch.distributed.init_process_group("nccl")
     cfg.agent_cfg.model_cfg.device_num = cfg.agent_cfg.model_cfg.vae_device = local
     ckpt = os.environ.get("CADRE_ENCODER_CKPT")

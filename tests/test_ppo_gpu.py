@@ -59,6 +59,32 @@ def test_gae_all_kernel_variants_match_oracle(T):
             assert vd[e, T].item() == pytest.approx(nv[e].item())
 
 
+@pytest.mark.parametrize("T", [257, 800, 1000, 1024])
+def test_gae_persistent_pipelined_kernel_matches_oracle(T):
+    """256 < T <= 1024 with at least 8 sequences per SM runs the persistent double-buffered kernel (gae_pipe_kernel):
+    more sequences than warps (every warp loops, both shared-memory buffers get reused), ragged T, ~10 % episode
+    boundaries; a sample of sequences incl. the first, the last and the buffer-parity neighbours vs the oracle."""
+    from cadre_b200 import ppo
+    E = 8 * 148 * 3 + 5
+    g = torch.Generator(device=DEV).manual_seed(T)
+    r = torch.rand(E, T + 1, device=DEV, generator=g)
+    v = torch.randn(E, T + 1, device=DEV, generator=g)
+    m = (torch.rand(E, T + 1, device=DEV, generator=g) > 0.1).float()
+    nv = torch.randn(E, device=DEV, generator=g)
+    for normalize in (True, False):
+        vd = v.clone()
+        ret, adv = torch.zeros(E, T + 1, device=DEV), torch.zeros(E, T, device=DEV)
+        ppo.gae(r, vd, m, nv, ret, adv, normalize=normalize)
+        for e in (0, 1, 7, 8, 1183, 1184, 1185, 2367, 2368, E - 2, E - 1):
+            ref_ret, vp = R.compute_returns(r[e].cpu().view(-1, 1), v[e].cpu().view(-1, 1).clone(),
+                                            m[e].cpu().view(-1, 1), nv[e].cpu().view(1, 1))
+            np.testing.assert_allclose(ret[e, :T].cpu().numpy(), ref_ret[:T, 0].numpy(), rtol=1e-5, atol=1e-5)
+            ref_adv = R.normalized_advantages(ref_ret, vp) if normalize else (ref_ret[:-1] - vp[:-1])
+            assert rel(adv[e], ref_adv[:, 0]) < 2e-5
+            assert vd[e, T].item() == pytest.approx(nv[e].item())
+    assert torch.isfinite(adv).all() and torch.isfinite(ret).all()
+
+
 def test_gae_large_sweep_properties():
     """65 536 sequences x 1 024 steps (1.3 GB): linearity in the rewards and the all-masked closed form."""
     from cadre_b200 import ppo

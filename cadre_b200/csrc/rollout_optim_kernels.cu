@@ -187,125 +187,99 @@ __global__ void __launch_bounds__(256, (ITERS > 16 ? 3 : 1)) gae_kernel(const fl
   }
 }
 
-// Persistent, software-pipelined variant for 256 < T <= 1024 (the roofline regime: 12 KB of input per sequence).
-// One CTA per SM, eight warps, each looping over sequences: while a warp scans sequence n out of one shared-memory
-// buffer, cp.async is already filling its other buffer with sequence n + 1 (r, V, m: 12 KB in flight per warp, 96 KB
-// per SM, so HBM never waits for the scan). With one sequence per warp and CTA (gae_kernel<32>) every CTA alternates
-// between a load phase and a compute phase and the memory pipe idles about a third of the time.
-__global__ void __launch_bounds__(256, 1) gae_pipe_kernel(const float* __restrict__ rewards, float* __restrict__ values,
-                                                          const float* __restrict__ masks,
-                                                          const float* __restrict__ next_value,
-                                                          float* __restrict__ returns, float* __restrict__ adv, int E,
-                                                          int T, float gamma, float tau, int normalize) {
+// Register-resident variant for 256 < T <= 32 * ITERS (the roofline regime: 12 KB of input per 1024-step sequence).
+// One warp per sequence; lane l holds elements l, l + 32, ... (coalesced) of r, V, m in registers - all 3 * ITERS
+// loads of the sequence are in flight before the first use. Time block k (steps 32k .. 32k+31) is suffix-scanned
+// across the lanes with shuffles (the ITERS block scans are independent: instruction-level parallelism instead of the
+// 32-step dependent chains of a per-lane chunk scan), then one FMA + shuffle per block carries the GAE value from
+// block k+1 into block k. No shared memory, ~128 registers: 16 warps per SM keep ~190 KB of loads in flight.
+template <int ITERS>
+__global__ void __launch_bounds__(256, 2) gae_reg_kernel(const float* __restrict__ rewards, float* __restrict__ values,
+                                                         const float* __restrict__ masks,
+                                                         const float* __restrict__ next_value,
+                                                         float* __restrict__ returns, float* __restrict__ adv, int E,
+                                                         int T, float gamma, float tau, int normalize) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float gsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = skew(T) + 1;
-  float* wbuf = gsm + static_cast<long long>(warp) * 6 * L;   // [2 buffers][r | V | m][L]
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int e = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (e >= E) return;
+  const long long base = static_cast<long long>(e) * (T + 1);
+  const float nv = next_value[e];
   const float gt = gamma * tau;
-  const int iters = (T + 31) >> 5;
-  auto issue = [&](int e, int b) {
-    float* R = wbuf + b * 3 * L;
-    const long long base = static_cast<long long>(e) * (T + 1);
-    for (int k = 0; k < iters; ++k) {
-      const int i = lane + 32 * k;
-      if (i < T) {
-        cp_async_4(&R[skew(i)], rewards + base + i);
-        cp_async_4(&R[L + skew(i)], values + base + i);
-        cp_async_4(&R[2 * L + skew(i)], masks + base + i);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int e = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (e < E) issue(e, 0);
-  for (int it = 0; e < E; e += nwarps, ++it) {
-    const int b = it & 1;
-    if (e + nwarps < E) {
-      issue(e + nwarps, b ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncwarp();
-    float* sd = wbuf + b * 3 * L;     // rewards -> delta -> gae -> raw advantage
-    float* sv = sd + L;               // V
-    float* sa_ = sd + 2 * L;          // masks -> a_t = gamma * tau * m_t
-    const long long base = static_cast<long long>(e) * (T + 1);
-    const float nv = next_value[e];
-    for (int k = 0; k < iters; ++k) {
-      const int i = lane + 32 * k;
-      if (i < T) {
-        const float vn = (i + 1 == T) ? nv : sv[skew(i + 1)];
-        const float r = sd[skew(i)], m = sa_[skew(i)];
-        sd[skew(i)] = r + gamma * vn * m - sv[skew(i)];
-        sa_[skew(i)] = gt * m;
-      }
-    }
-    if (lane == 0) values[base + T] = nv;  // storage.py:70 value_preds[-1] = next_value
-    __syncwarp();
-    const int cs = (T + 31) / 32;
-    const int t0 = min(T, lane * cs), t1 = min(T, t0 + cs);
-    {
-      float a = 1.f, bb = 0.f;   // chunk map x -> a*x + b (x = gae entering the chunk from later time steps)
-#pragma unroll 8
-      for (int t = t1 - 1; t >= t0; --t) {
-        const float at = sa_[skew(t)];
-        bb = at * bb + sd[skew(t)];
-        a = at * a;
-      }
-      float sa = a, sb = bb;     // inclusive suffix composition S_l = F_l o F_{l+1} o ... o F_31
+  float d[ITERS], a[ITERS], v[ITERS];
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const float oa = __shfl_down_sync(0xffffffffu, sa, off);
-        const float ob = __shfl_down_sync(0xffffffffu, sb, off);
-        if (lane + off < 32) {
-          sb = sa * ob + sb;
-          sa = sa * oa;
-        }
-      }
-      float gae = __shfl_down_sync(0xffffffffu, sb, 1);  // S_{l+1}(0)
-      if (lane == 31) gae = 0.f;
-#pragma unroll 8
-      for (int t = t1 - 1; t >= t0; --t) {   // replay the chunk
-        gae = sd[skew(t)] + sa_[skew(t)] * gae;
-        sd[skew(t)] = gae;
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = lane + 32 * k;
+    const bool ok = i < T;
+    d[k] = ok ? rewards[base + i] : 0.f;
+    v[k] = ok ? values[base + i] : 0.f;
+    a[k] = ok ? masks[base + i] : 0.f;
+  }
+  if (lane == 0) values[base + T] = nv;  // storage.py:70 value_preds[-1] = next_value
+  // delta_t = r_t + gamma V_{t+1} m_t - V_t, a_t = gamma tau m_t; steps >= T are the identity map (a = 1, delta = 0)
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = lane + 32 * k;
+    const float dn = __shfl_down_sync(0xffffffffu, v[k], 1);
+    const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, v[k + 1 < ITERS ? k + 1 : k], 0) : nv;
+    float vn = lane < 31 ? dn : wrap;
+    if (i + 1 == T) vn = nv;
+    const float m = a[k];
+    d[k] = i < T ? d[k] + gamma * vn * m - v[k] : 0.f;
+    a[k] = i < T ? gt * m : 1.f;
+  }
+  // inclusive suffix composition inside every block: (a, d)[k] := F_l o F_{l+1} o ... o F_31
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const float oa = __shfl_down_sync(0xffffffffu, a[k], off);
+      const float ob = __shfl_down_sync(0xffffffffu, d[k], off);
+      if (lane + off < 32) {
+        d[k] = a[k] * ob + d[k];
+        a[k] = a[k] * oa;
       }
     }
-    __syncwarp();
-    // returns_t = gae_t + V_t (storage.py:75); advantage_t = returns_t - V_t (train.py:82: the rounding of the round
-    // trip through returns is kept)
-    float lsum = 0.f;
-    for (int k = 0; k < iters; ++k) {
-      const int i = lane + 32 * k;
-      if (i < T) {
-        const float v = sv[skew(i)];
-        const float ret = sd[skew(i)] + v;
-        const float ad = ret - v;
-        returns[base + i] = ret;
-        sd[skew(i)] = ad;
-        lsum += ad;
+  }
+  // carry the GAE value across blocks, latest block first; d[k] becomes gae_t
+  float carry = 0.f;
+#pragma unroll
+  for (int k = ITERS - 1; k >= 0; --k) {
+    d[k] = d[k] + a[k] * carry;
+    carry = __shfl_sync(0xffffffffu, d[k], 0);
+  }
+  // returns_t = gae_t + V_t (storage.py:75); advantage_t = returns_t - V_t (train.py:82: the rounding of the round
+  // trip through returns is kept)
+  float lsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = lane + 32 * k;
+    if (i < T) {
+      const float ret = d[k] + v[k];
+      returns[base + i] = ret;
+      d[k] = ret - v[k];
+      lsum += d[k];
+    }
+  }
+  float mean = 0.f, denom = 1.f;
+  if (normalize) {
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    mean = lsum / static_cast<float>(T);
+    float lsq = 0.f;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k)
+      if (lane + 32 * k < T) {
+        const float x = d[k] - mean;
+        lsq += x * x;
       }
-    }
-    float mean = 0.f, denom = 1.f;
-    if (normalize) {
-      for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-      mean = lsum / static_cast<float>(T);
-      float lsq = 0.f;
-      for (int i = lane; i < T; i += 32) {
-        const float d = sd[skew(i)] - mean;
-        lsq += d * d;
-      }
-      for (int o = 16; o > 0; o >>= 1) lsq += __shfl_xor_sync(0xffffffffu, lsq, o);
-      denom = sqrtf(lsq / static_cast<float>(T - 1)) + 1e-8f;  // torch.std is unbiased; train.py:86
-    }
-    for (int i = lane; i < T; i += 32) {
-      const float ad = sd[skew(i)];
-      adv[static_cast<long long>(e) * T + i] = normalize ? (ad - mean) / denom : ad;
-    }
-    __syncwarp();   // buffer b is refilled by the next iteration's prefetch
+    for (int o = 16; o > 0; o >>= 1) lsq += __shfl_xor_sync(0xffffffffu, lsq, o);
+    denom = sqrtf(lsq / static_cast<float>(T - 1)) + 1e-8f;  // torch.std is unbiased; train.py:86
+  }
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = lane + 32 * k;
+    if (i < T) adv[static_cast<long long>(e) * T + i] = normalize ? (d[k] - mean) / denom : d[k];
   }
 }
 
@@ -481,22 +455,15 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   int warps = 8;
   while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
-  if (T > 256 && T <= 1024) {
-    int dev = cadre::current_device(), sms = 0;
-    CADRE_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (E >= 8 * sms) {   // enough sequences to keep persistent warps busy; small calls stay on the one-shot kernel
-      const size_t psm = static_cast<size_t>(8) * 6 * L * sizeof(float);
-      static size_t pcfg[cadre::CADRE_MAX_DEVICES] = {};
-      cadre::ensure_dynamic_smem(cadre::gae_pipe_kernel, psm, pcfg);
-      cadre::launch_k(cadre::gae_pipe_kernel, dim3(sms), dim3(256), psm, static_cast<cudaStream_t>(stream), rewards, values,
-                      masks, next_value, returns, adv, E, T, gamma, tau, normalize);
-      CADRE_CUDA_CHECK(cudaGetLastError());
-      return 0;
-    }
+  if (T > 256 && T <= 1024) {   // register-resident block-scan kernel, no shared memory
+    cadre::launch_k(cadre::gae_reg_kernel<32>, dim3((E + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), rewards,
+                    values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
+    CADRE_CUDA_CHECK(cudaGetLastError());
+    return 0;
   }
-  auto kern = T <= 256 ? cadre::gae_kernel<8> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>);
-  static size_t configured[3][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
-  const int which = T <= 256 ? 0 : (T <= 1024 ? 1 : 2);
+  auto kern = T <= 256 ? cadre::gae_kernel<8> : cadre::gae_kernel<0>;
+  static size_t configured[2][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
+  const int which = T <= 256 ? 0 : 1;
   if (smem > 48 * 1024) cadre::ensure_dynamic_smem(kern, smem, configured[which]);
   cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
                   rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);

@@ -60,10 +60,9 @@ def test_gae_all_kernel_variants_match_oracle(T):
 
 
 @pytest.mark.parametrize("T", [257, 800, 1000, 1024])
-def test_gae_persistent_pipelined_kernel_matches_oracle(T):
-    """256 < T <= 1024 with at least 8 sequences per SM runs the persistent double-buffered kernel (gae_pipe_kernel):
-    more sequences than warps (every warp loops, both shared-memory buffers get reused), ragged T, ~10 % episode
-    boundaries; a sample of sequences incl. the first, the last and the buffer-parity neighbours vs the oracle."""
+def test_gae_register_block_scan_kernel_many_sequences(T):
+    """256 < T <= 1024 runs the register-resident block-scan kernel (gae_reg_kernel): several waves of sequences, ragged
+    T (partially filled last time block), ~10 % episode boundaries; a sample of sequences vs the oracle."""
     from cadre_b200 import ppo
     E = 8 * 148 * 3 + 5
     g = torch.Generator(device=DEV).manual_seed(T)

@@ -187,102 +187,6 @@ __global__ void __launch_bounds__(256, (ITERS > 16 ? 3 : 1)) gae_kernel(const fl
   }
 }
 
-// Register-resident variant for 256 < T <= 32 * ITERS (the roofline regime: 12 KB of input per 1024-step sequence).
-// One warp per sequence; lane l holds elements l, l + 32, ... (coalesced) of r, V, m in registers - all 3 * ITERS
-// loads of the sequence are in flight before the first use. Time block k (steps 32k .. 32k+31) is suffix-scanned
-// across the lanes with shuffles (the ITERS block scans are independent: instruction-level parallelism instead of the
-// 32-step dependent chains of a per-lane chunk scan), then one FMA + shuffle per block carries the GAE value from
-// block k+1 into block k. No shared memory, ~128 registers: 16 warps per SM keep ~190 KB of loads in flight.
-template <int ITERS>
-__global__ void __launch_bounds__(256, 2) gae_reg_kernel(const float* __restrict__ rewards, float* __restrict__ values,
-                                                         const float* __restrict__ masks,
-                                                         const float* __restrict__ next_value,
-                                                         float* __restrict__ returns, float* __restrict__ adv, int E,
-                                                         int T, float gamma, float tau, int normalize) {
-  pdl_trigger();
-  pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (e >= E) return;
-  const long long base = static_cast<long long>(e) * (T + 1);
-  const float nv = next_value[e];
-  const float gt = gamma * tau;
-  float d[ITERS], a[ITERS], v[ITERS];
-#pragma unroll
-  for (int k = 0; k < ITERS; ++k) {
-    const int i = lane + 32 * k;
-    const bool ok = i < T;
-    d[k] = ok ? rewards[base + i] : 0.f;
-    v[k] = ok ? values[base + i] : 0.f;
-    a[k] = ok ? masks[base + i] : 0.f;
-  }
-  if (lane == 0) values[base + T] = nv;  // storage.py:70 value_preds[-1] = next_value
-  // delta_t = r_t + gamma V_{t+1} m_t - V_t, a_t = gamma tau m_t; steps >= T are the identity map (a = 1, delta = 0)
-#pragma unroll
-  for (int k = 0; k < ITERS; ++k) {
-    const int i = lane + 32 * k;
-    const float dn = __shfl_down_sync(0xffffffffu, v[k], 1);
-    const float wrap = (k + 1 < ITERS) ? __shfl_sync(0xffffffffu, v[k + 1 < ITERS ? k + 1 : k], 0) : nv;
-    float vn = lane < 31 ? dn : wrap;
-    if (i + 1 == T) vn = nv;
-    const float m = a[k];
-    d[k] = i < T ? d[k] + gamma * vn * m - v[k] : 0.f;
-    a[k] = i < T ? gt * m : 1.f;
-  }
-  // inclusive suffix composition inside every block: (a, d)[k] := F_l o F_{l+1} o ... o F_31
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-      const float oa = __shfl_down_sync(0xffffffffu, a[k], off);
-      const float ob = __shfl_down_sync(0xffffffffu, d[k], off);
-      if (lane + off < 32) {
-        d[k] = a[k] * ob + d[k];
-        a[k] = a[k] * oa;
-      }
-    }
-  }
-  // carry the GAE value across blocks, latest block first; d[k] becomes gae_t
-  float carry = 0.f;
-#pragma unroll
-  for (int k = ITERS - 1; k >= 0; --k) {
-    d[k] = d[k] + a[k] * carry;
-    carry = __shfl_sync(0xffffffffu, d[k], 0);
-  }
-  // returns_t = gae_t + V_t (storage.py:75); advantage_t = returns_t - V_t (train.py:82: the rounding of the round
-  // trip through returns is kept)
-  float lsum = 0.f;
-#pragma unroll
-  for (int k = 0; k < ITERS; ++k) {
-    const int i = lane + 32 * k;
-    if (i < T) {
-      const float ret = d[k] + v[k];
-      returns[base + i] = ret;
-      d[k] = ret - v[k];
-      lsum += d[k];
-    }
-  }
-  float mean = 0.f, denom = 1.f;
-  if (normalize) {
-    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    mean = lsum / static_cast<float>(T);
-    float lsq = 0.f;
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k)
-      if (lane + 32 * k < T) {
-        const float x = d[k] - mean;
-        lsq += x * x;
-      }
-    for (int o = 16; o > 0; o >>= 1) lsq += __shfl_xor_sync(0xffffffffu, lsq, o);
-    denom = sqrtf(lsq / static_cast<float>(T - 1)) + 1e-8f;  // torch.std is unbiased; train.py:86
-  }
-#pragma unroll
-  for (int k = 0; k < ITERS; ++k) {
-    const int i = lane + 32 * k;
-    if (i < T) adv[static_cast<long long>(e) * T + i] = normalize ? (d[k] - mean) / denom : d[k];
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // chief.py:13-21: per-module clip_grad_norm_(max_norm) on the summed gradient, then one Adam step
 // (torch.optim.Adam defaults, main.py:55). The flat buffers are cut into fixed chunks; every chunk belongs to
@@ -454,16 +358,16 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   const size_t per_warp = 2 * static_cast<size_t>(L) * sizeof(float);
   int warps = 8;
   while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
+  // Warps are independent (no block-level barrier) and a block's shared memory is only released when its LAST warp is
+  // done, so long sequences run in blocks of two warps: the ~26 warps an SM holds then retire and get replaced one
+  // pair at a time and their load / scan / store phases stay staggered (65 536 x 1 024 sweep on B200: 4.18 TB/s with
+  // 8-warp blocks, 4.56 TB/s = 71 % of the measured copy peak with 2-warp blocks).
+  if (T > 256) warps = warps > 2 ? 2 : warps;
   const size_t smem = warps * per_warp;
-  if (T > 256 && T <= 1024) {   // register-resident block-scan kernel, no shared memory
-    cadre::launch_k(cadre::gae_reg_kernel<32>, dim3((E + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), rewards,
-                    values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);
-    CADRE_CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
-  auto kern = T <= 256 ? cadre::gae_kernel<8> : cadre::gae_kernel<0>;
-  static size_t configured[2][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
-  const int which = T <= 256 ? 0 : 1;
+  auto kern = T <= 256 ? cadre::gae_kernel<8>
+                       : (T <= 512 ? cadre::gae_kernel<16> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>));
+  static size_t configured[4][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
+  const int which = T <= 256 ? 0 : (T <= 512 ? 1 : (T <= 1024 ? 2 : 3));
   if (smem > 48 * 1024) cadre::ensure_dynamic_smem(kern, smem, configured[which]);
   cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
                   rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);

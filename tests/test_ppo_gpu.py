@@ -59,10 +59,10 @@ def test_gae_all_kernel_variants_match_oracle(T):
             assert vd[e, T].item() == pytest.approx(nv[e].item())
 
 
-@pytest.mark.parametrize("T", [257, 800, 1000, 1024])
-def test_gae_register_block_scan_kernel_many_sequences(T):
-    """256 < T <= 1024 runs the register-resident block-scan kernel (gae_reg_kernel): several waves of sequences, ragged
-    T (partially filled last time block), ~10 % episode boundaries; a sample of sequences vs the oracle."""
+@pytest.mark.parametrize("T", [257, 500, 512, 513, 800, 1000, 1024])
+def test_gae_many_sequences_long_T(T):
+    """256 < T <= 1024 (two-warp blocks; register batches of 16 loads per lane up to T = 512, 32 above): several waves
+    of sequences, ragged T, ~10 % episode boundaries; a sample of sequences vs the oracle."""
     from cadre_b200 import ppo
     E = 8 * 148 * 3 + 5
     g = torch.Generator(device=DEV).manual_seed(T)

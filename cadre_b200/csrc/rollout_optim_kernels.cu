@@ -364,10 +364,10 @@ int cadre_gae(const float* rewards, float* values, const float* masks, const flo
   // 8-warp blocks, 4.56 TB/s = 71 % of the measured copy peak with 2-warp blocks).
   if (T > 256) warps = warps > 2 ? 2 : warps;
   const size_t smem = warps * per_warp;
-  auto kern = T <= 256 ? cadre::gae_kernel<8>
-                       : (T <= 512 ? cadre::gae_kernel<16> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>));
-  static size_t configured[4][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
-  const int which = T <= 256 ? 0 : (T <= 512 ? 1 : (T <= 1024 ? 2 : 3));
+  // (a 16-loads-per-lane instance for T <= 512 measured slower than the cp.async path: 3.07 against 4.00 TB/s)
+  auto kern = T <= 256 ? cadre::gae_kernel<8> : (T <= 1024 ? cadre::gae_kernel<32> : cadre::gae_kernel<0>);
+  static size_t configured[3][cadre::CADRE_MAX_DEVICES] = {};   // per kernel variant and device
+  const int which = T <= 256 ? 0 : (T <= 1024 ? 1 : 2);
   if (smem > 48 * 1024) cadre::ensure_dynamic_smem(kern, smem, configured[which]);
   cadre::launch_k(kern, dim3((E + warps - 1) / warps), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream),
                   rewards, values, masks, next_value, returns, adv, E, T, gamma, tau, normalize);

@@ -61,7 +61,7 @@ def test_gae_all_kernel_variants_match_oracle(T):
 
 @pytest.mark.parametrize("T", [257, 500, 512, 513, 800, 1000, 1024])
 def test_gae_many_sequences_long_T(T):
-    """256 < T <= 1024 (two-warp blocks; register batches of 16 loads per lane up to T = 512, 32 above): several waves
+    """256 < T <= 1024 (two-warp blocks, cp.async staging): several waves
     of sequences, ragged T, ~10 % episode boundaries; a sample of sequences vs the oracle."""
     from cadre_b200 import ppo
     E = 8 * 148 * 3 + 5

@@ -417,13 +417,19 @@ def run_cadre(args):
     allreduce = None
     if world > 1:
         dist.barrier()
+        if learner._switch is not None:      # the library's in-switch reduction on the symmetric gradient buffer
+            def exchange():
+                learner._switch.sum_()
+        else:
+            def exchange():
+                dist.all_reduce(learner.grads, op=dist.ReduceOp.SUM)
         for _ in range(3):
-            dist.all_reduce(learner.grads, op=dist.ReduceOp.SUM)
+            exchange()
         torch.cuda.synchronize()
         ar0, ar1 = torch.cuda.Event(True), torch.cuda.Event(True)
         ar0.record()
         for _ in range(10):
-            dist.all_reduce(learner.grads, op=dist.ReduceOp.SUM)
+            exchange()
         ar1.record()
         torch.cuda.synchronize()
         ar = torch.tensor([ar0.elapsed_time(ar1) / 10], device=dev)
@@ -432,9 +438,14 @@ def run_cadre(args):
         ar_ms = float(ar.item())
         allreduce = {"bytes": nbytes, "ms": round(ar_ms, 4), "algbw_GBps": round(nbytes / (ar_ms * 1e-3) / 1e9, 1),
                      "busbw_GBps": round(2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9, 1),
-                     "per_step": n_upd}
+                     "per_step": n_upd,
+                     "impl": ("cadre allreduce_kernel (multimem.ld_reduce / multimem.st)"
+                              if learner._switch is not None and learner._switch.multicast else
+                              "cadre allreduce_kernel (peer loads / stores)" if learner._switch is not None else
+                              "ncclAllReduce, NCCL_ALGO=" + os.environ.get("NCCL_ALGO", "default"))}
         phase["allreduce"] = allreduce
         learner.grads.zero_()
+        learner.check()
 
     # ---- per-kernel view (rank 0)
     if rank == 0:

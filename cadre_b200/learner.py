@@ -71,7 +71,21 @@ class Learner:
         self.lr, self.max_grad_norm = lr, max_grad_norm
         self.engine = _ppo.PpoEngine(workers, mini_batch, clip, value_coeff, clip_coeff, ent_coeff, self.device)
         self.params = ppo_params.pack_state(ppo_state, self.device)
-        self.grads = torch.zeros_like(self.params)
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        # Gradient exchange: "switch" = the library's in-switch reduction on a symmetric gradient buffer
+        # (collective.SwitchAllReduce, csrc/allreduce.cu), "nccl" = torch.distributed.all_reduce
+        self.exchange = os.environ.get("CADRE_ALLREDUCE", "nccl") if self.world > 1 else "none"
+        self._switch = None
+        if self.exchange == "switch":
+            from .collective import SwitchAllReduce
+            self._switch = SwitchAllReduce(self.params.numel(), self.device, process_group)
+            self.grads = self._switch.buffer
+        elif self.exchange in ("nccl", "none"):
+            self.grads = torch.zeros_like(self.params)
+        else:
+            raise CadreError(f"CADRE_ALLREDUCE={self.exchange!r}: expected 'switch' or 'nccl'")
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.losses = torch.zeros(workers, 2, 3, device=self.device)       # last update step
@@ -81,9 +95,6 @@ class Learner:
         self.pg = process_group
         self.overlap_allreduce = os.environ.get("CADRE_NO_ALLREDUCE_OVERLAP", "0") != "1"
         self._comm_stream = None
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
         # one CPU RNG stream per logical worker (each reference worker is its own process with its own global RNG)
         self._rng_states = []
         if seeds is not None:
@@ -141,6 +152,7 @@ class Learner:
         self._waits = [[g] for g in range(groups - 1)] + [[groups - 1, -1]]
         self._reduced = [torch.cuda.Event() for _ in self._ranges]
         assert sum(r[1] for r in self._ranges) == self.grads.numel()
+        assert all(r[0] % 4 == 0 and r[1] % 4 == 0 for r in self._ranges)        # 16-byte vectors in the exchange
 
     def _exchange_and_step(self, step):
         """all-reduce(sum) + per-module clip + Adam on the gradient the last engine.update left in self.grads.
@@ -158,8 +170,11 @@ class Learner:
                 for k, (off, cnt, _, _) in enumerate(self._ranges):
                     for g in self._waits[k]:
                         self.engine.wait_grads(g, self._comm_stream)
-                    torch.distributed.all_reduce(self.grads[off:off + cnt], op=torch.distributed.ReduceOp.SUM,
-                                                 group=self.pg)
+                    if self._switch is not None:
+                        self._switch.sum_(off, cnt, stream=self._comm_stream)
+                    else:
+                        torch.distributed.all_reduce(self.grads[off:off + cnt], op=torch.distributed.ReduceOp.SUM,
+                                                     group=self.pg)
                     self._reduced[k].record(self._comm_stream)
             for k, (_, _, m0, m1) in enumerate(self._ranges):
                 main.wait_event(self._reduced[k])
@@ -214,6 +229,13 @@ class Learner:
             n += m
         self.loss_steps = idx_all.shape[0]
         return idx_all.shape[0]
+
+    def check(self):
+        """Synchronise and raise CadreError if a bounded wait inside a kernel (LSTM hand-off, all-reduce barrier) ever
+        timed out."""
+        self.engine.check()
+        if self._switch is not None:
+            self._switch.check()
 
     def state(self):
         return ppo_params.unpack_state(self.params)

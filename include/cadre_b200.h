@@ -217,6 +217,26 @@ int cadre_ppo_adam_step_modules(void* handle, float* params, const float* grads,
 int cadre_ppo_check(void* handle);
 int cadre_ppo_launches(void* handle);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Gradient exchange across the ranks of one NVSwitch domain, in place: grads <- sum over ranks, every rank receives
+ * the same bits. Replaces Shared_grad_buffers.add_gradient + the chief installing the summed gradient
+ * (ppo_agent/models.py:231-239, ppo_agent/chief.py:13-16). The buffer must be symmetric memory: buffer_ptrs_host[r] =
+ * rank r's copy as mapped into THIS process (r == rank: the local buffer), `multicast` = the multicast mapping of all
+ * copies (NULL when the fabric has none), flag_ptrs_host[r] = rank r's zero-initialised flag area of
+ * cadre_allreduce_flag_bytes() bytes, also symmetric memory (cadre_b200/collective.py obtains all of them from
+ * torch.distributed._symmetric_memory). cadre_allreduce_sum reduces [offset, offset + count) (floats, multiples of 4);
+ * all ranks must issue the same sequence of calls. use_multicast = 1: in-switch reduction (multimem.ld_reduce /
+ * multimem.st); 0: peer loads summed in rank order + peer stores. cadre_allreduce_check synchronises and fails if a
+ * barrier ever timed out (polling is bounded; a lost peer cannot hang the GPU). */
+int cadre_allreduce_flag_bytes(void);
+int cadre_allreduce_create(void** handle, int rank, int world, float* const* buffer_ptrs_host, float* multicast,
+                           uint32_t* const* flag_ptrs_host, int64_t count);
+/* thread blocks per launch (default 32, at most 128): every rank must use the same value for the same call */
+int cadre_allreduce_set_blocks(void* handle, int blocks);
+int cadre_allreduce_destroy(void* handle);
+int cadre_allreduce_sum(void* handle, int64_t offset, int64_t count, int use_multicast, void* stream);
+int cadre_allreduce_check(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

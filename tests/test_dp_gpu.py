@@ -5,7 +5,9 @@ models.py:231-239, chief.py:12-24).
 With >= 2 GPUs the two ranks use one GPU each over NCCL; on a one-GPU box both ranks share cuda:0 and exchange the
 gradient with gloo (NCCL refuses two ranks on one device) - the learner code path is the same: the gradient is
 all-reduced per contiguous range (actor-critic tensors, then one range per group of LSTM experts as their weight-gradient
-GEMMs finish) on a communication stream, and clip + Adam run per range behind it (`overlap=False`: one LSTM range)."""
+GEMMs finish) on a communication stream, and clip + Adam run per range behind it (`overlap=False`: one LSTM range).
+`exchange="switch"` (two GPUs only) swaps NCCL for the library's own in-switch reduction (csrc/allreduce.cu) on a
+symmetric gradient buffer."""
 import os
 import sys
 
@@ -30,19 +32,20 @@ def _fill_worker(gid):
     return pair, nv
 
 
-def _rank(rank, world, port, out_dir, backend, overlap):
+def _rank(rank, world, port, out_dir, backend, overlap, exchange="nccl"):
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CADRE_ALLREDUCE=exchange)
     os.environ["CADRE_NO_ALLREDUCE_OVERLAP"] = "0" if overlap else "1"
     import torch.distributed as dist
     dev_index = rank if backend == "nccl" else 0
     torch.cuda.set_device(dev_index)
-    dist.init_process_group(backend, rank=rank, world_size=world)
+    dist.init_process_group(backend, rank=rank, world_size=world,
+                            **({"device_id": torch.device("cuda", dev_index)} if backend == "nccl" else {}))
     from cadre_b200.learner import Learner, RolloutPool
     from oracle import restate as R
     dev = f"cuda:{dev_index}"
     learner = Learner(W_LOCAL, MB, R.ppo_fixture_state(0), dev, seeds=[500 + rank * W_LOCAL + w for w in range(W_LOCAL)])
-    assert learner.world == world
+    assert learner.world == world and learner.exchange == exchange
     pool = RolloutPool(W_LOCAL, dict(num_steps=T, mini_batch_num=T // MB, feature_dims=530, seq_length=8, use_gae=True,
                                      gamma=0.99, tau=0.95), dev)
     nvs = torch.zeros(W_LOCAL, 2)
@@ -62,7 +65,7 @@ def _rank(rank, world, port, out_dir, backend, overlap):
     for _ in range(3):
         learner.learn(pool, 1)
     torch.cuda.synchronize()
-    learner.engine.check()
+    learner.check()
     out["params_learn"] = learner.params.cpu()
     out["steps"] = learner.step_count
     torch.save(out, os.path.join(out_dir, f"rank{rank}.pt"))
@@ -70,13 +73,15 @@ def _rank(rank, world, port, out_dir, backend, overlap):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False])
-def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap):
+@pytest.mark.parametrize("overlap,exchange", [(True, "nccl"), (False, "nccl"), (True, "switch")])
+def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap, exchange):
     from cadre_b200 import ppo_params as P
     from oracle import restate as R
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
-    port = 29700 + (os.getpid() % 1000) + (1 if overlap else 0)
-    mp.spawn(_rank, args=(WORLD, port, str(tmp_path), backend, overlap), nprocs=WORLD, join=True)
+    if exchange == "switch" and backend != "nccl":
+        pytest.skip("the in-switch all-reduce needs two GPUs (symmetric memory between two devices)")
+    port = 29700 + (os.getpid() % 1000) + (1 if overlap else 0) + (2 if exchange == "switch" else 0)
+    mp.spawn(_rank, args=(WORLD, port, str(tmp_path), backend, overlap, exchange), nprocs=WORLD, join=True)
     res = [torch.load(str(tmp_path / f"rank{r}.pt"), weights_only=False) for r in range(WORLD)]
     # replicas are bit-identical (same reduced gradient, same deterministic clip + Adam)
     assert torch.equal(res[0]["params"], res[1]["params"])
@@ -85,9 +90,10 @@ def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap):
     assert torch.isfinite(res[0]["params_learn"]).all() and not torch.equal(res[0]["params_learn"], res[0]["params"])
     # pipelined ranges (overlap=True) and one LSTM range (overlap=False) are the same arithmetic: bit-identical
     # parameters after 8 steps
-    _LEARN_RESULTS[overlap] = res[0]["params_learn"]
-    if len(_LEARN_RESULTS) == 2:
-        assert torch.equal(_LEARN_RESULTS[True], _LEARN_RESULTS[False])
+    if exchange == "nccl":
+        _LEARN_RESULTS[overlap] = res[0]["params_learn"]
+        if len(_LEARN_RESULTS) == 2:
+            assert torch.equal(_LEARN_RESULTS[True], _LEARN_RESULTS[False])
 
     # oracle: four reference workers + the chief, two update steps
     torch.set_num_threads(min(16, os.cpu_count() or 1))

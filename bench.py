@@ -377,6 +377,16 @@ def run_cadre(args):
 
     if world > 1:
         learner.world = world   # all-reduce inside update_step
+    if args.profile_step:
+        # for `ncu --profile-from-start off`: exactly ONE resident step between cudaProfilerStart / Stop, then exit
+        for _ in range(max(1, args.warmup)):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     ms_step, clocks = timed(step_resident, args.steps, args.warmup, sample=True)
     ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup - 1))
     h2d_unique = ingest.h2d_bytes_last
@@ -587,6 +597,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-full-windows", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE resident step inside cudaProfilerStart/Stop and exit (ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

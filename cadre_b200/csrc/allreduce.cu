@@ -26,9 +26,9 @@
 namespace cadre {
 namespace {
 
-constexpr int AR_THREADS = 512;
+constexpr int AR_THREADS = 256;
 constexpr int AR_UNROLL = 8;
-constexpr int AR_MAX_BLOCKS = 128;
+constexpr int AR_MAX_BLOCKS = 256;
 constexpr int AR_MAX_WORLD = 16;
 constexpr long long AR_POLL_BUDGET = 4000000000ll;   // ~2 s of SM clock
 
@@ -107,36 +107,35 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArParams p)
   const long long per = (nv + p.world - 1) / p.world;
   const long long v0 = per * p.rank, v1 = (v0 + per < nv) ? v0 + per : nv;
   const long long stride = static_cast<long long>(nb) * AR_THREADS;
-  for (long long i = v0 + static_cast<long long>(b) * AR_THREADS + threadIdx.x; i < v1; i += stride * AR_UNROLL) {
+  auto reduce_one = [&](long long f) -> float4 {
+    if (MC) return multimem_ld_reduce_add(p.multicast + f);
+    float4 acc = ld_peer(p.peers[0] + f);
+    for (int r = 1; r < p.world; ++r) {
+      const float4 x = ld_peer(p.peers[r] + f);
+      acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
+    }
+    return acc;
+  };
+  auto publish_one = [&](long long f, const float4& v) {
+    if (MC) {
+      multimem_st(p.multicast + f, v);
+    } else {
+      for (int r = 0; r < p.world; ++r) st_peer(p.peers[r] + f, v);
+    }
+  };
+  long long i = v0 + static_cast<long long>(b) * AR_THREADS + threadIdx.x;
+  // full batches: AR_UNROLL independent 16-byte reductions in flight per thread before the first store
+  for (; i + (AR_UNROLL - 1) * stride < v1; i += stride * AR_UNROLL) {
+    const long long f = p.offset + (i << 2);
     float4 acc[AR_UNROLL];
 #pragma unroll
-    for (int u = 0; u < AR_UNROLL; ++u) {
-      const long long j = i + u * stride;
-      if (j < v1) {
-        const long long f = p.offset + (j << 2);
-        if (MC) {
-          acc[u] = multimem_ld_reduce_add(p.multicast + f);
-        } else {
-          acc[u] = ld_peer(p.peers[0] + f);
-          for (int r = 1; r < p.world; ++r) {
-            const float4 x = ld_peer(p.peers[r] + f);
-            acc[u].x += x.x, acc[u].y += x.y, acc[u].z += x.z, acc[u].w += x.w;
-          }
-        }
-      }
-    }
+    for (int u = 0; u < AR_UNROLL; ++u) acc[u] = reduce_one(f + ((u * stride) << 2));
 #pragma unroll
-    for (int u = 0; u < AR_UNROLL; ++u) {
-      const long long j = i + u * stride;
-      if (j < v1) {
-        const long long f = p.offset + (j << 2);
-        if (MC) {
-          multimem_st(p.multicast + f, acc[u]);
-        } else {
-          for (int r = 0; r < p.world; ++r) st_peer(p.peers[r] + f, acc[u]);
-        }
-      }
-    }
+    for (int u = 0; u < AR_UNROLL; ++u) publish_one(f + ((u * stride) << 2), acc[u]);
+  }
+  for (; i < v1; i += stride) {
+    const long long f = p.offset + (i << 2);
+    publish_one(f, reduce_one(f));
   }
   __threadfence_system();
   __syncthreads();
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArParams p)
 
 struct ArHandle {
   ArParams p;
-  int blocks = 32;
+  int blocks = 64;
   int device = 0;
   long long total = 0;
 };

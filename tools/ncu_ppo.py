@@ -1,4 +1,4 @@
-"""Short PPO run for ncu: W=4 workers x mb=100, 2 update steps (first = warm-up)."""
+"""Short PPO run for ncu (--profile-from-start off): W=4 workers x mb=100, one warm-up update step, one profiled."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,6 +21,9 @@ for w in range(W):
     b["action"][2 * w + 1].copy_(torch.randint(0, 3, (201, 1), device=dev, generator=g))
 pool.compute_returns(torch.zeros(W, 2, device=dev))
 idx = learner.sample_epoch_indices(pool.storages)
-for k in range(2):
-    learner.update_step(pool.storages, idx[k % len(idx)])
+learner.update_step(pool.storages, idx[0])          # warm-up (also builds the TMA descriptors)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()                         # ncu --profile-from-start off: exactly one update step
+learner.update_step(pool.storages, idx[1 % len(idx)])
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()

@@ -85,6 +85,7 @@ __device__ __forceinline__ void pair_barrier(const ArParams& p, int b, uint32_t 
     const uint32_t* mine = p.flags[p.rank] + b * AR_MAX_WORLD + t;
     const long long t0 = clock64();
     while (static_cast<int>(ld_acquire_sys(mine) - value) < 0) {
+      __nanosleep(20);
       if (clock64() - t0 > AR_POLL_BUDGET) {
         atomicExch(p.error, 1 + t);
         break;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_kernel(const ArParams p)
 
 struct ArHandle {
   ArParams p;
-  int blocks = 64;
+  int blocks = 32;
   int device = 0;
   long long total = 0;
 };

@@ -231,7 +231,7 @@ int cadre_ppo_launches(void* handle);
 int cadre_allreduce_flag_bytes(void);
 int cadre_allreduce_create(void** handle, int rank, int world, float* const* buffer_ptrs_host, float* multicast,
                            uint32_t* const* flag_ptrs_host, int64_t count);
-/* thread blocks of 256 threads per launch (default 64, at most 256): every rank must use the same value for the same call */
+/* thread blocks of 256 threads per launch (default 32, at most 256): every rank must use the same value for the same call */
 int cadre_allreduce_set_blocks(void* handle, int blocks);
 int cadre_allreduce_destroy(void* handle);
 int cadre_allreduce_sum(void* handle, int64_t offset, int64_t count, int use_multicast, void* stream);

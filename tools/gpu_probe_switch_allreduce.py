@@ -45,7 +45,7 @@ for mc in ([True, False] if os.environ.get("PROBE_P2P", "1") == "1" else [True])
         res[f"range_{off}_{cnt}"] = {"max_err_rel": err, "untouched_outside": untouched, "replicas_identical": same}
     out[tag + "_check"] = res
     sizes = {"full_77.9MB": (0, N), "range_36MB": (0, 9005760), "small_1.4MB": (N - 345600, 345600)}
-    for blocks in (32, 64, 128, 192):
+    for blocks in [int(b) for b in os.environ.get("PROBE_BLOCKS", "32,64,128,192").split(",")]:
         ar.set_blocks(blocks)
         for name, (off, cnt) in sizes.items():
             for _ in range(5):

@@ -7,7 +7,8 @@ One STEP = one learner iteration on every rank (weak scaling: per-GPU work is fi
   cfg3 (default; BASELINE config 3, and config 4 for N > 1): 4 logical workers x T=200 env ticks x 8 stacked frames ->
        encoder forward over 6400 camera frames (uint8 rgb + route map + measurements), features written into the 8
        RolloutStorages, GAE + advantage normalisation, then ppo_epoch=4 x 2 minibatches of (routed LSTM / actor-critic
-       forward + backward over 400 rows x 2 heads, gradient all-reduce over NCCL for N > 1, per-module clip + Adam).
+       forward + backward over 400 rows x 2 heads, gradient all-reduce for N > 1 - the library's in-switch kernel from 4
+       ranks on, NCCL between 2 -, per-module clip + Adam).
   cfg5 (BASELINE config 5 when run with --gpus 8): 8 envs per GPU, T=800, minibatches of 400 rows per env
        (51 200 window frames and 8 x 3200-row update steps per GPU and step).
 value = window frames/s with inputs resident in HBM; EVERY window frame is encoded (device-timed, max over ranks).
@@ -334,8 +335,12 @@ def run_cadre(args):
     losses_h = torch.empty(WORKERS, 2, 3, pin_memory=True)
     d2h_bytes = losses_h.numel() * 4
 
+    prefetch = os.environ.get("CADRE_NO_PREFETCH", "0") != "1"
+
     def step_e2e():
         ingest.encode(rgb_uh, route_uh, meas_uh, b["obs"], unique=True)   # distinct frames: H2D + encode once each
+        if prefetch:     # the NEXT rollout's frames cross PCIe under this rollout's update phase (one copy per step)
+            ingest.prefetch(rgb_uh, route_uh, meas_uh)
         pool.compute_returns(next_values)
         learner.learn(pool, PPO_EPOCH)
         losses_h.copy_(learner.losses, non_blocking=True)
@@ -394,7 +399,10 @@ def run_cadre(args):
     value = total_frames / (ms_step * 1e-3)
     e2e = {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d_unique, "d2h_bytes_per_step": d2h_bytes,
-           "api": "cadre_b200.ingest.RolloutIngest.encode(unique=True) + RolloutPool.compute_returns + Learner.learn",
+           "api": "cadre_b200.ingest.RolloutIngest.encode(unique=True) [+ .prefetch of the next rollout] + "
+                  "RolloutPool.compute_returns + Learner.learn",
+           "h2d_overlap": ("the next rollout's frames are copied under the current update phase (RolloutIngest.prefetch): "
+                           "one full-rollout H2D copy per step inside the timed region") if prefetch else "in-step staging only",
            "frames_shipped_and_encoded_per_step": WORKERS * K,
            "unique_frames_per_s": WORKERS * K * world / (ms_e2e * 1e-3),
            "note": "value counts window frames (workers x T x 8) like `value`; each distinct frame crosses PCIe and "
@@ -539,10 +547,22 @@ def run_cadre(args):
                           "note": f"the configured call ({2 * WORKERS} sequences x {T}) is in the launch-latency regime"})
         del r_, v_, mk, nv_, ret_, adv_
         if allreduce is not None:
-            rooflines.append({"kernel": "gradient all-reduce (NCCL over NVLink 5 / NVSwitch)", "bound": "nvlink",
-                              "achieved": allreduce["busbw_GBps"], "peak": 900.0, "unit": "GB/s",
-                              "frac": round(allreduce["busbw_GBps"] / 900.0, 4), "ms": allreduce["ms"],
-                              "peak_source": "nominal NVLink 5 per direction per GPU"})
+            if learner._switch is not None and learner._switch.multicast:
+                # in-switch reduction: every GPU sends its copy of all W slices (S) plus its reduced slice (S / W) and
+                # receives its reduced slice plus all W broadcast slices: S (1 + 1/W) bytes per direction
+                wire = allreduce["bytes"] * (1.0 + 1.0 / world) / (allreduce["ms"] * 1e-3) / 1e9
+                rooflines.append({"kernel": "gradient all-reduce: cadre allreduce_kernel (multimem.ld_reduce / multimem.st "
+                                            "through NVSwitch)", "bound": "nvlink", "achieved": round(wire, 1),
+                                  "peak": 770.0, "unit": "GB/s", "frac": round(wire / 770.0, 4), "ms": allreduce["ms"],
+                                  "algbw_GBps": allreduce["algbw_GBps"],
+                                  "algorithmic_bytes": "S (1 + 1/W) per direction per GPU, S = 77.9 MB",
+                                  "peak_source": "measured peer-copy bandwidth per direction (B200_PROFILING.md); "
+                                                 "nominal NVLink 5: 900"})
+            else:
+                rooflines.append({"kernel": "gradient all-reduce (NCCL over NVLink 5 / NVSwitch)", "bound": "nvlink",
+                                  "achieved": allreduce["busbw_GBps"], "peak": 900.0, "unit": "GB/s",
+                                  "frac": round(allreduce["busbw_GBps"] / 900.0, 4), "ms": allreduce["ms"],
+                                  "peak_source": "nominal NVLink 5 per direction per GPU"})
 
         eager = None
         if world == 1 and not args.no_eager_baseline:

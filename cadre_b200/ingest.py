@@ -14,7 +14,8 @@ independent). `unique=False` ships and encodes every window frame like the refer
 like-for-like measurements against round 1). In both modes the host-to-device copies run on a copy stream into
 double-buffered staging tensors and overlap the encoder, whose chunks alternate between `streams` encoder instances on
 their own CUDA streams (the tail of one chunk's persistent kernels is filled by the other chunk's CTAs); the first
-chunks are small because the encoder cannot start before its first chunk has landed.
+chunks are small because the encoder cannot start before its first chunk has landed. `prefetch()` software-pipelines
+across rollouts: the next rollout's distinct frames cross PCIe while the current rollout's update phase runs.
 """
 import ctypes
 import os
@@ -70,6 +71,11 @@ class RolloutIngest:
             self.fork_ev = torch.cuda.Event()
             self.join_ev = [torch.cuda.Event() for _ in range(self.NS)]
             self._feats = {}
+            self._landing = None                          # device copies of a prefetched rollout's distinct frames
+            self._landing_key = None
+            self._landed_ev = torch.cuda.Event()
+            self._landing_free_ev = torch.cuda.Event()
+            self._landing_free_ev.record(torch.cuda.current_stream(self.device))
         self.h2d_bytes_last = 0
         self.frames_encoded_last = 0
 
@@ -130,6 +136,35 @@ class RolloutIngest:
                                                       _lib.stream_ptr(self.device)))
 
     # ------------------------------------------------------------------ public
+    @staticmethod
+    def _key(rgb, route_fig, measurements):
+        return (rgb.data_ptr(), route_fig.data_ptr(), measurements.data_ptr(), tuple(rgb.shape))
+
+    def prefetch(self, rgb, route_fig, measurements):
+        """Start copying the NEXT rollout's distinct frames (pinned host tensors, `unique=True` shapes) to the device on
+        the copy stream and return immediately. The copy runs under whatever the caller enqueues next (the update phase
+        of the current rollout); the following `encode()` of the same tensors consumes the device copies instead of
+        staging chunk by chunk. One rollout can be in flight; the copy waits for the previous consumer of the landing
+        buffers."""
+        if rgb.is_cuda or not (rgb.is_pinned() and route_fig.is_pinned() and measurements.is_pinned()):
+            raise _lib.CadreError("prefetch takes frames in pinned host memory")
+        if tuple(rgb.shape[:2]) != (self.W, self.K):
+            raise _lib.CadreError(f"frames have leading shape {tuple(rgb.shape[:2])}, expected {(self.W, self.K)}")
+        n = self.W * self.K
+        with torch.cuda.device(self.device):
+            if self._landing is None:
+                u8 = dict(dtype=torch.uint8, device=self.device)
+                self._landing = (torch.empty(n, 144, 256, 3, **u8), torch.empty(n, 256, 144, **u8),
+                                 torch.empty(n, 3, dtype=torch.float64, device=self.device))
+            self.copy_stream.wait_event(self._landing_free_ev)
+            with torch.cuda.stream(self.copy_stream):
+                self._landing[0].copy_(rgb.view(n, 144, 256, 3), non_blocking=True)
+                self._landing[1].copy_(route_fig.view(n, 256, 144), non_blocking=True)
+                self._landing[2].copy_(measurements.view(n, 3), non_blocking=True)
+                self._landed_ev.record(self.copy_stream)
+        self._landing_key = self._key(rgb, route_fig, measurements)
+        self._prefetched_bytes = int(rgb.numel() + route_fig.numel() + measurements.numel() * 8)
+
     def encode(self, rgb, route_fig, measurements, obs, unique=True):
         """Fill obs[2w + head][t] (t < T) for all workers of this rank from raw frames.
 
@@ -147,6 +182,16 @@ class RolloutIngest:
         for d in lead:
             n *= d
         feats = self._feat_buffer(n)
+        if host and unique and self._landing_key is not None and self._landing_key == self._key(rgb, route_fig, measurements):
+            # this rollout was prefetched: its frames are (or will be, once the copy stream's event fires) on the device
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(self._landed_ev)
+            self._encode_stream(self._landing[0], self._landing[1], self._landing[2], feats, False)
+            self._landing_free_ev.record(main)
+            self._landing_key = None
+            self._scatter(feats, obs, self.S, self.T)
+            self.h2d_bytes_last = self._prefetched_bytes
+            return obs
         self._encode_stream(rgb.view(n, 144, 256, 3), route_fig.view(n, 256, 144), measurements.view(n, 3), feats, host)
         if unique:
             self._scatter(feats, obs, self.S, self.T)

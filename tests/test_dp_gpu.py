@@ -73,7 +73,7 @@ def _rank(rank, world, port, out_dir, backend, overlap, exchange="nccl"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap,exchange", [(True, "nccl"), (False, "nccl"), (True, "switch")])
+@pytest.mark.parametrize("overlap,exchange", [(True, "nccl"), (False, "nccl"), (True, "switch"), (False, "switch")])
 def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap, exchange):
     from cadre_b200 import ppo_params as P
     from oracle import restate as R
@@ -81,6 +81,10 @@ def test_two_rank_update_step_matches_oracle_chief(tmp_path, overlap, exchange):
     if exchange == "switch" and backend != "nccl":
         pytest.skip("the in-switch all-reduce needs two GPUs (symmetric memory between two devices)")
     port = 29700 + (os.getpid() % 1000) + (1 if overlap else 0) + (2 if exchange == "switch" else 0)
+    if exchange == "switch" and overlap:
+        os.environ["CADRE_GRAD_GROUPS"] = "2"           # the switch exchange defaults to one range: force the pipeline
+    else:
+        os.environ.pop("CADRE_GRAD_GROUPS", None)
     mp.spawn(_rank, args=(WORLD, port, str(tmp_path), backend, overlap, exchange), nprocs=WORLD, join=True)
     res = [torch.load(str(tmp_path / f"rank{r}.pt"), weights_only=False) for r in range(WORLD)]
     # replicas are bit-identical (same reduced gradient, same deterministic clip + Adam)

@@ -68,6 +68,43 @@ def test_unique_frame_ingest_equals_per_tick_window_encoding(max_chunk, streams)
         assert err < 1e-2, (w, t, err)
 
 
+def test_prefetched_rollout_equals_in_step_staging():
+    """RolloutIngest.prefetch (the next rollout's frames cross PCIe under the current update phase) feeds encode() the
+    same bytes as the chunked in-step staging: identical observations, for two consecutive rollouts, and a rollout that
+    was NOT the prefetched one falls back to staging."""
+    from cadre_b200.ingest import RolloutIngest
+    from cadre_b200.learner import RolloutPool
+    W, T, S = 2, 13, 8
+    K = T + S - 1
+    ing = RolloutIngest(R.danet_fixture_state(0), "cuda:0", W, T, S, 530, max_chunk=32, streams=2)
+    cfg = dict(num_steps=T, mini_batch_num=1, feature_dims=530, seq_length=S, use_gae=True, gamma=0.99, tau=0.95)
+    pa, pb = RolloutPool(W, cfg, "cuda:0"), RolloutPool(W, cfg, "cuda:0")
+    rollouts = [tuple(_pin(t) for t in _rollout_frames(W, K, seed=s)) for s in (11, 12)]
+    nbytes = W * K * (144 * 256 * 3 + 256 * 144 + 24)
+    for i, host in enumerate(rollouts):
+        ing.encode(*host, pa.batched["obs"], unique=True)                   # in-step staging
+        assert ing.h2d_bytes_last == nbytes
+        ing.prefetch(*host)
+        torch.cuda._sleep(2_000_000)                                        # something else runs meanwhile
+        ing.encode(*host, pb.batched["obs"], unique=True)                   # consumes the prefetched copy
+        assert ing.h2d_bytes_last == nbytes and ing._landing_key is None
+        torch.cuda.synchronize()
+        assert torch.equal(pa.batched["obs"], pb.batched["obs"]), i
+    # prefetched rollout 1, but rollout 0 is encoded: staging path, and the prefetched copy stays valid for later
+    ing.prefetch(*rollouts[1])
+    ing.encode(*rollouts[0], pa.batched["obs"], unique=True)
+    assert ing._landing_key is not None
+    ing.encode(*rollouts[1], pb.batched["obs"], unique=True)
+    assert ing._landing_key is None
+    torch.cuda.synchronize()
+    assert not torch.equal(pa.batched["obs"], pb.batched["obs"])
+    ing.encode(*rollouts[1], pa.batched["obs"], unique=True)
+    torch.cuda.synchronize()
+    assert torch.equal(pa.batched["obs"], pb.batched["obs"])
+    with pytest.raises(Exception, match="pinned"):
+        ing.prefetch(*[t.clone() for t in _rollout_frames(W, K, seed=1)])
+
+
 def test_ingest_rejects_pageable_host_memory_and_wrong_shapes():
     from cadre_b200._lib import CadreError
     from cadre_b200.ingest import RolloutIngest

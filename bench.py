@@ -335,7 +335,10 @@ def run_cadre(args):
     losses_h = torch.empty(WORKERS, 2, 3, pin_memory=True)
     d2h_bytes = losses_h.numel() * 4
 
-    prefetch = os.environ.get("CADRE_NO_PREFETCH", "0") != "1"
+    # RolloutIngest.prefetch (the next rollout's frames cross PCIe under the update phase) is OFF here: measured, the
+    # in-step staging already hides the copy behind the encoder and the DMA under the update phase costs ~0.8 ms per step
+    # (1 x B200: 9.4 ms without / 10.2 ms with; 4 x B200: 11.2 / 12.1 ms). CADRE_PREFETCH=1 switches it on.
+    prefetch = os.environ.get("CADRE_PREFETCH", "0") == "1"
 
     def step_e2e():
         ingest.encode(rgb_uh, route_uh, meas_uh, b["obs"], unique=True)   # distinct frames: H2D + encode once each

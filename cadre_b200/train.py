@@ -72,7 +72,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("NCCL_ALGO", "Ring")   # faster than NCCL's default for the 36 - 78 MB gradient ranges (8 x B200)
-        torch.distributed.init_process_group("nccl")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg.agent_cfg.model_cfg.device_num = cfg.agent_cfg.model_cfg.vae_device = local
     ckpt = os.environ.get("CADRE_ENCODER_CKPT")
     if not ckpt:

@@ -21,7 +21,7 @@
 #include "internal.h"
 
 #include <cstdlib>
-#include <vector>
+#include <memory>
 
 namespace cadre {
 namespace {
@@ -180,7 +180,7 @@ int cadre_allreduce_create(void** handle, int rank, int world, float* const* buf
   CADRE_REQUIRE(handle != nullptr && buffer_ptrs_host != nullptr && flag_ptrs_host != nullptr, "null argument");
   CADRE_REQUIRE(world >= 2 && world <= AR_MAX_WORLD && rank >= 0 && rank < world, "rank / world");
   CADRE_REQUIRE(count > 0 && count % 4 == 0, "count must be a positive multiple of 4 floats");
-  auto* h = new ArHandle();
+  auto h = std::make_unique<ArHandle>();
   h->device = current_device();
   h->total = count;
   ArParams& p = h->p;
@@ -200,7 +200,7 @@ int cadre_allreduce_create(void** handle, int rank, int world, float* const* buf
   CADRE_CUDA_CHECK(cudaDeviceSynchronize());
   if (const char* e = getenv("CADRE_AR_BLOCKS")) h->blocks = atoi(e);
   CADRE_REQUIRE(h->blocks >= 1 && h->blocks <= AR_MAX_BLOCKS, "CADRE_AR_BLOCKS out of range");
-  *handle = h;
+  *handle = h.release();
   CADRE_API_END
 }
 

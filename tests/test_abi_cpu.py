@@ -59,6 +59,27 @@ def test_no_cpu_fallback():
         create_model({"device_num": -1, "vae_params": "CoPM", "measurement_dim": 18}, load_vae=False)
 
 
+def test_allreduce_entry_points_validate_their_arguments():
+    """cadre_allreduce_*: argument errors and a missing CUDA device come back as error codes + messages (no crash, no
+    silent success); the collective wrapper refuses to work without an initialised process group."""
+    from cadre_b200 import CadreError, _lib
+    from cadre_b200.collective import SwitchAllReduce
+    lib = _lib.lib()
+    assert lib.cadre_allreduce_flag_bytes() >= 16 * 16 * 4
+    h = ctypes.c_void_p()
+    two = (ctypes.c_void_p * 2)(None, None)
+    # world of 1, rank out of range, count not a multiple of 4 floats, null peer mappings
+    for rank, world, count in ((0, 1, 1024), (2, 2, 1024), (0, 2, 1023), (0, 2, 1024)):
+        rc = lib.cadre_allreduce_create(ctypes.byref(h), rank, world, two, None, two, ctypes.c_int64(count))
+        assert rc != 0 and lib.cadre_last_error()
+    assert lib.cadre_allreduce_sum(None, ctypes.c_int64(0), ctypes.c_int64(4), 1, None) != 0
+    assert b"handle" in lib.cadre_last_error()
+    assert lib.cadre_allreduce_check(None) != 0
+    assert lib.cadre_allreduce_set_blocks(None, 32) != 0
+    with pytest.raises(CadreError, match="process group"):
+        SwitchAllReduce(1024, "cuda:0")
+
+
 def test_product_package_does_not_import_oracle():
     pkg = os.path.join(ROOT, "cadre_b200")
     for dirpath, _, files in os.walk(pkg):

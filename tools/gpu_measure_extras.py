@@ -79,4 +79,4 @@ for (W, Tn, mbn) in ((4, 200, 2), (8, 800, 2)):
                                       "tflops_routed_217.8MF_per_row": fl / (ms * 1e-3) / 1e12}
     print(f"ppo update W={W} mb={mb}", out[f"ppo_update_W{W}_mb{mb}"], flush=True)
     del learner, pool
-json.dump(out, open("gpurun_out/r1_extras4.json", "w"), indent=1)
+json.dump(out, open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r2_extras.json", "w"), indent=1)

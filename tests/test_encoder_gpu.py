@@ -190,10 +190,10 @@ def test_bench_batch_sizes_match_oracle(bench_encoders, B):
 
 
 def test_bench_two_stream_ramp_schedule(bench_encoders):
-    """bench.py's e2e schedule: chunks of 128, 512, 640, 640 frames alternating between two encoder instances on two
-    streams, each writing its rows of one [N,530] feature matrix through ld_out. Bit-identical to one encoder on one
+    """The ingest's e2e schedule (cadre_b200.ingest.chunk_schedule: a geometric start-up ramp 32, 96, 288, then chunks of
+    640; round 1's 128 / 512 steps ride along) alternating between two encoder instances on two streams, each writing its rows of one [N,530] feature matrix through ld_out. Bit-identical to one encoder on one
     stream, and equal to the oracle on a sample of frames from every chunk."""
-    sizes = [128, 512, 640, 640]
+    sizes = [32, 96, 288, 640, 128, 512, 224]
     n = sum(sizes)
     rgb, route, meas = _u8_frames(n, seed=77)
     d = [t.cuda() for t in (rgb, route, meas)]
@@ -208,7 +208,7 @@ def test_bench_two_stream_ramp_schedule(bench_encoders):
         s0 += m
     torch.cuda.synchronize()
     assert torch.equal(out, one)
-    rows = [0, 5, 127, 128, 300, 639, 640, 1000, 1279, 1280, 1500, 1919, 64, 777, 1281, 1800]
+    rows = [0, 5, 31, 32, 127, 128, 300, 415, 416, 1000, 1055, 1056, 1183, 1184, 1500, 1695, 1696, 1919]   # every chunk + edges
     torch.set_num_threads(min(16, os.cpu_count() or 1))
     ref = _oracle_features(rgb, route, meas, R.danet_fixture_state(0), rows)
     assert rel_l2(out[rows, :512].cpu(), ref[:, :512]) < REL_FEATURE

@@ -63,8 +63,9 @@ def test_prepare_weights_matches_oracle_math():
 
 def test_ingest_chunk_schedule():
     from cadre_b200.ingest import chunk_schedule
-    assert chunk_schedule(6400, 640) == [128, 512] + [640] * 9           # bench.py's e2e ramp (round 1: 128, 512, 9 x 640)
-    assert chunk_schedule(828, 640) == [128, 512, 188]                   # cfg 3, distinct frames only: 4 x 207
+    assert chunk_schedule(6400, 640, ramp=(128, 512)) == [128, 512] + [640] * 9     # round 1's e2e ramp
+    assert chunk_schedule(6400, 640) == [32, 96, 288] + [640] * 9 + [224]           # default: geometric start-up
+    assert chunk_schedule(828, 640) == [32, 96, 288, 412]                # cfg 3, distinct frames only: 4 x 207
     assert chunk_schedule(300, 640) == [300] and chunk_schedule(640, 640) == [640]
     assert chunk_schedule(6400, 640, ramp=()) == [640] * 10
     for n in (1, 127, 641, 5000):

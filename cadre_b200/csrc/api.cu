@@ -92,4 +92,30 @@ int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, con
   CADRE_API_END
 }
 
+int cadre_conv3x3_flat128(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
+                          int act, void* out, void* stream) {
+  CADRE_API_BEGIN
+  cadre::FlatArgs a;
+  a.in = static_cast<const cadre::enc_t*>(in), a.B = B, a.H = H, a.W = W;
+  a.w = static_cast<const cadre::enc_t*>(w), a.bias = bias, a.res = static_cast<const cadre::enc_t*>(res);
+  a.act = act, a.out = static_cast<cadre::enc_t*>(out);
+  cadre::launch_halo128(a, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
+int cadre_conv2d_nhwc_bordered_out(const void* in, int B, int Hin, int Win, int Cin, const void* w, int Cout, int KH,
+                                   int KW, int stride, int pad, const float* bias, int act, void* out, int in_pad,
+                                   void* stream) {
+  CADRE_API_BEGIN
+  cadre::ConvArgs a;
+  a.in_pad = in_pad, a.out_pad = 1;
+  a.in = static_cast<const cadre::enc_t*>(in);
+  a.B = B, a.Hin = Hin, a.Win = Win, a.Cin = Cin;
+  a.w = static_cast<const cadre::enc_t*>(w);
+  a.Cout = Cout, a.KH = KH, a.KW = KW, a.stride = stride, a.pad = pad;
+  a.bias = bias, a.act = act, a.out = static_cast<cadre::enc_t*>(out);
+  cadre::launch_conv(a, static_cast<cudaStream_t>(stream));
+  CADRE_API_END
+}
+
 }  // extern "C"

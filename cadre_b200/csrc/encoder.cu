@@ -34,6 +34,10 @@ struct Encoder {
   enc_t* padded = nullptr;   // [Bmax][75][262][8]
   enc_t* act[4] = {nullptr, nullptr, nullptr, nullptr};  // ping-pong, each [Bmax][36*64*64]
   enc_t* padact[3] = {nullptr, nullptr, nullptr};        // zero-bordered layer1 activations [Bmax][38][66][64]
+  // layer2 on zero-bordered activations [Bmax][20][34][128]: its two plain 3x3 convs (layer2.1) run on the halo-reuse
+  // kernel (tc_halo128.cuh), layer2.0's launches write bordered outputs for them
+  bool halo2 = false;
+  enc_t* pad2[3] = {nullptr, nullptr, nullptr};
   // fused shortcuts (layer2.0 / 3.0 / 4.0): conv2 weights with the 1x1 downsample appended along K, summed bias
   bool fuse_ds = true;
   enc_t* fused_w[3] = {nullptr, nullptr, nullptr};
@@ -84,6 +88,9 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
   e->fuse_ds = getenv("CADRE_NO_SHORTCUT_FUSION") == nullptr;   // A/B switch kept for the fused-shortcut parity test
+  e->halo2 = e->fuse_ds && getenv("CADRE_LAYER2_HALO") != nullptr && atoi(getenv("CADRE_LAYER2_HALO")) != 0;
+  if (e->halo2)
+    for (int i = 0; i < 3; ++i) e->pad2[i] = dev_alloc<enc_t>(B * 20 * 34 * 128, true);  // borders stay zero
   if (e->fuse_ds) {
     // conv indices follow execution order: layer1 = 0..3, then per stage (conv1, conv2, downsample, conv1, conv2)
     const int planes[4] = {64, 128, 256, 512};
@@ -131,6 +138,7 @@ static void encoder_destroy(Encoder* e) {
   cudaFree(e->padded);
   for (int i = 0; i < 4; ++i) cudaFree(e->act[i]);
   for (int i = 0; i < 3; ++i) cudaFree(e->padact[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(e->pad2[i]);
   cudaFree(e->head5), cudaFree(e->sa), cudaFree(e->sc), cudaFree(e->sa_conv), cudaFree(e->feat_sum);
   cudaFree(e->fc1), cudaFree(e->qkv), cudaFree(e->route_max), cudaFree(e->lut255);
   for (int i = 0; i < 3; ++i) cudaFree(e->fused_w[i]), cudaFree(e->fused_b[i]);
@@ -139,9 +147,10 @@ static void encoder_destroy(Encoder* e) {
 
 static void conv(Encoder* e, int idx, const enc_t* in, int B, int H, int W, int Cin, int Cout, int k,
                  int stride, int pad, const enc_t* res, int act, enc_t* out,
-                 cudaStream_t s, bool in_pad = false) {
+                 cudaStream_t s, bool in_pad = false, bool out_pad = false) {
   ConvArgs a;
   a.in_pad = in_pad ? 1 : 0;
+  a.out_pad = out_pad ? 1 : 0;
   a.in = in, a.B = B, a.Hin = H, a.Win = W, a.Cin = Cin;
   a.w = static_cast<const enc_t*>(e->w.conv_w[idx]);
   a.bias = e->w.conv_b[idx];
@@ -186,11 +195,42 @@ static void encoder_trunk(Encoder* e, int B, const double* meas, float* out, int
     padded_in = x;
   }
   for (int li = 1; li < 4; ++li) {
+    if (li == 1 && e->halo2) {
+      // layer2 on zero-bordered buffers: 2.0.conv1 (3x3/s2) and 2.0.conv2 + shortcut on the implicit-GEMM kernel with
+      // bordered outputs, 2.1.conv1 / 2.1.conv2 (plain 3x3/s1, 128 -> 128) on the halo-reuse kernel
+      enc_t* t0 = e->pad2[0];
+      enc_t* y0 = e->pad2[1];
+      enc_t* t1 = e->pad2[2];
+      conv(e, ci++, padded_in, B, 36, 64, 64, 128, 3, 2, 1, nullptr, 1, t0, s, true, true);
+      step(e, s, n, "layer2.0.conv1");
+      {
+        ++ci, ++ci;   // conv2 and the downsample conv are folded into fused_w[0]
+        ConvArgs a;
+        a.in = t0, a.in_pad = 1, a.B = B, a.Hin = 18, a.Win = 32, a.Cin = 128;
+        a.w = e->fused_w[0], a.bias = e->fused_b[0];
+        a.Cout = 128, a.KH = 3, a.KW = 3, a.stride = 1, a.pad = 1;
+        a.act = 1, a.out = y0, a.out_pad = 1;
+        a.in2 = padded_in, a.Cin2 = 64, a.in2_pad = 1, a.Hin2 = 36, a.Win2 = 64;
+        launch_conv(a, s);
+        step(e, s, n, "layer2.0.conv2+shortcut");
+      }
+      FlatArgs f;
+      f.B = B, f.H = 18, f.W = 32, f.act = 1;
+      f.in = y0, f.w = static_cast<const enc_t*>(e->w.conv_w[ci]), f.bias = e->w.conv_b[ci], f.out = t1;
+      launch_halo128(f, s), ++ci;
+      step(e, s, n, "layer2.1.conv1");
+      f.in = t1, f.w = static_cast<const enc_t*>(e->w.conv_w[ci]), f.bias = e->w.conv_b[ci], f.out = t0, f.res = y0;
+      launch_halo128(f, s), ++ci;
+      step(e, s, n, "layer2.1.conv2");
+      padded_in = t0;
+      H = 18, W = 32, C = 128;
+      continue;
+    }
     for (int bi = 0; bi < 2; ++bi) {
       const int stride = (li > 0 && bi == 0) ? 2 : 1;
       const int Cout = planes[li];
       const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-      const bool from_pad = (padded_in != nullptr && li == 1 && bi == 0);
+      const bool from_pad = (padded_in != nullptr && bi == 0 && (li == 1 || (li == 2 && e->halo2)));
       const enc_t* x = from_pad ? padded_in : e->act[cur];
       enc_t* t = e->act[(cur + 1) & 3];
       enc_t* ds = e->act[(cur + 2) & 3];

@@ -136,6 +136,7 @@ struct ConvArgs {
   int act = 0;
   enc_t* out = nullptr;  // [B][Hout][Wout][Cout]
   int in_pad = 0;        // input tensor is [B][Hin+2][Win+2][Cin] with a zero border (Hin/Win stay logical)
+  int out_pad = 0;       // output (and residual) tensors are [B][Hout+2][Wout+2][Cout]; the border is never written
   // Optional fused shortcut (ResNet downsample, resnet.py:152-158): out += conv1x1/stride-2 of a SECOND input,
   // executed as Cin2/64 extra k-blocks of the same implicit GEMM. `w` is then [Cout][KH*KW*Cin + Cin2] (the
   // shortcut weights appended along K) and `bias` the sum of both biases; in2 is [B][Hin2 (+2)][Win2 (+2)][Cin2]
@@ -156,6 +157,8 @@ struct FlatArgs {
   enc_t* out = nullptr;
 };
 void launch_flat3x3(const FlatArgs& a, cudaStream_t stream);
+// the same for 128 -> 128 channels (ResNet layer2): [B][H+2][W+2][128], weights [128][3][3][128] (tc_halo128.cuh)
+void launch_halo128(const FlatArgs& a, cudaStream_t stream);
 
 // 7x7/s2/p3 stem over the padded 4-channel bf16 image [B][150][262][4]; weights [64][256] (K = 4 row pairs x
 // 2 rows x 8 pixels x 4 ch, zero where kh==7 or kw==7); output [B][72][128][64].

@@ -2,6 +2,7 @@
 #include "internal.h"
 #include "tc_gemm.cuh"
 #include "tc_flat3x3.cuh"
+#include "tc_halo128.cuh"
 #include "tc_persist.cuh"
 #include "tc_stem_pool.cuh"
 
@@ -328,10 +329,13 @@ void launch_conv(const ConvArgs& a, cudaStream_t stream) {
     for (int i = 0; i < 4; ++i) q.tmA[i] = p.tmA[i];
     q.tmB = p.tmB;
     {
-      const uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)a.B};
-      const uint64_t str[3] = {(uint64_t)a.Cout * es, (uint64_t)Wout * a.Cout * es,
-                               (uint64_t)Hout * Wout * a.Cout * es};
+      // out_pad: the output tensor is [B][Hout+2][Wout+2][Cout] with a zero border the stores never touch
+      const int Ho2 = Hout + 2 * a.out_pad, Wo2 = Wout + 2 * a.out_pad;
+      const uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)Wo2, (uint64_t)Ho2, (uint64_t)a.B};
+      const uint64_t str[3] = {(uint64_t)a.Cout * es, (uint64_t)Wo2 * a.Cout * es,
+                               (uint64_t)Ho2 * Wo2 * a.Cout * es};
       make_map(&q.tmOut, 2, 4, a.out, dims, str, box);
+      q.out_pad = a.out_pad;
     }
     q.num_kb = p.num_kb, q.kb_main = kb_main, q.ntaps = p.ntaps, q.cin_chunks = p.cin_chunks;
     q.Hout = Hout, q.Wout = Wout, q.TH = TH, q.TN = TN, q.Bimg = a.B;
@@ -388,6 +392,35 @@ void launch_flat3x3(const FlatArgs& a, cudaStream_t stream) {
   ensure_dynamic_smem(tc_flat3x3_kernel, FLAT_SMEM, configured);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   launch_k(tc_flat3x3_kernel, dim3(grid), dim3(320), FLAT_SMEM, stream, p);
+  CADRE_CUDA_CHECK(cudaGetLastError());
+}
+
+// Halo-reuse 3x3/s1/p1 128 -> 128 convolution on zero-bordered activations [B][H+2][W+2][128] (tc_halo128.cuh)
+void launch_halo128(const FlatArgs& a, cudaStream_t stream) {
+  CADRE_REQUIRE(2 * (a.W + 2) + 2 + 256 <= HALO_WIN_ROWS, "halo128 window is sized for W <= 33");
+  Halo128Params p;
+  memset(&p, 0, sizeof(p));
+  const int PW = a.W + 2;
+  const long long P = static_cast<long long>(a.B) * (a.H + 2) * PW;
+  CADRE_REQUIRE(P < (1LL << 31) - 1024, "halo128: too many pixels");
+  const uint64_t dims[2] = {128, (uint64_t)P};
+  const uint64_t str[1] = {256};
+  const uint32_t box_a[2] = {64, (uint32_t)HALO_WIN_A}, box_b[2] = {64, 128};
+  make_map(&p.tmXa, 2, 2, a.in, dims, str, box_a);
+  make_map(&p.tmXb, 2, 2, a.in, dims, str, box_b);
+  make_map(&p.tmY, 2, 2, a.out, dims, str, box_b);
+  const uint64_t wdims[2] = {1152, 128};
+  const uint64_t wstr[1] = {1152 * 2};
+  const uint32_t wbox[2] = {64, 128};
+  make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox);
+  p.P = static_cast<int>(P), p.H = a.H, p.W = a.W, p.PW = PW;
+  p.num_tiles = static_cast<int>((P + 127) / 128);
+  p.num_groups = (p.num_tiles + 1) / 2;
+  p.bias = a.bias, p.res = a.res, p.act = a.act;
+  static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
+  ensure_dynamic_smem(tc_halo128_kernel, HALO_SMEM, configured);
+  const int grid = p.num_groups < num_sms() ? p.num_groups : num_sms();
+  launch_k(tc_halo128_kernel, dim3(grid), dim3(320), HALO_SMEM, stream, p);
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

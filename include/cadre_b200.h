@@ -79,6 +79,15 @@ int cadre_debug_clk(long long* dev_counters);
 
 int cadre_conv3x3_flat64(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
                          int act, void* out, void* stream);
+/* The same for 128 -> 128 channels (ResNet layer2, W <= 33): in / res / out are [B][H+2][W+2][128] enc16 with zero
+ * borders, w is [128][3][3][128]; res (optional) is added before the activation (resnet.py:52-53). */
+int cadre_conv3x3_flat128(const void* in, int B, int H, int W, const void* w, const float* bias, const void* res,
+                          int act, void* out, void* stream);
+/* cadre_conv2d_nhwc writing into a zero-bordered output tensor [B][Hout+2][Wout+2][Cout] (the border is left
+ * untouched: the caller zeroes it once). Feeds the halo-reuse kernels above. */
+int cadre_conv2d_nhwc_bordered_out(const void* in, int B, int Hin, int Win, int Cin, const void* w, int Cout, int KH,
+                                   int KW, int stride, int pad, const float* bias, int act, void* out, int in_pad,
+                                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Perception encoder forward = DANet.get_latent_feature(x, "concate")

@@ -270,3 +270,106 @@ def test_intertask_stage_matches_oracle(encoders):
     got = enc.debug_buffer(5, B).view(B, 3072).float().cpu()
     assert rel_l2(got, hid) < 5e-3, rel_l2(got, hid)
     assert rel_l2(lat, ref) < REL_FEATURE
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# layer2 on zero-bordered activations: halo-reuse 128 -> 128 kernel (csrc/tc_halo128.cuh) and bordered conv outputs
+def _conv_ops():
+    from cadre_b200 import _lib
+    return _lib, _lib.lib(), _lib.enc_dtype()
+
+
+@pytest.mark.parametrize("B,res", [(1, False), (3, True), (37, True), (640, False)])
+def test_halo128_conv_matches_fp32_conv_and_implicit_gemm_kernel(B, res):
+    """cadre_conv3x3_flat128 (BasicBlock conv of ResNet layer2, resnet.py:39-55: conv3x3 + folded BN bias (+ residual) +
+    ReLU on [B][20][34][128] bordered activations) against torch's fp32 convolution of the same fp16 operands and against
+    the implicit-GEMM kernel (cadre_conv2d_nhwc) it replaces; the zero border must come back exactly zero. B = 37 gives
+    an odd number of 128-pixel tiles (the last group's second tile is empty), B = 640 is the benchmarked chunk."""
+    import torch.nn.functional as F
+    _lib, L, dt = _conv_ops()
+    H, W, C = 18, 32, 128
+    g = torch.Generator(device="cuda").manual_seed(100 + B)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g).to(dt)
+    w = (torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5).to(dt)
+    bias = torch.randn(C, device="cuda", generator=g)
+    xp = torch.zeros(B, H + 2, W + 2, C, device="cuda", dtype=dt)
+    xp[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    w_k = w.permute(0, 2, 3, 1).contiguous().view(C, -1)
+    r = rp = None
+    if res:
+        r = torch.randn(B, H, W, C, device="cuda", generator=g).to(dt)
+        rp = torch.zeros_like(xp)
+        rp[:, 1:-1, 1:-1] = r
+    out = torch.full((B, H + 2, W + 2, C), 7.0, device="cuda", dtype=dt)
+    _lib.check(L.cadre_conv3x3_flat128(_lib.ptr(xp), B, H, W, _lib.ptr(w_k), _lib.ptr(bias), _lib.ptr(rp), 1,
+                                       _lib.ptr(out), _lib.stream_ptr()))
+    old = torch.full((B, H, W, C), 7.0, device="cuda", dtype=dt)
+    _lib.check(L.cadre_conv2d_nhwc(_lib.ptr(xp), B, H, W, C, _lib.ptr(w_k), C, 3, 3, 1, 1, _lib.ptr(bias), _lib.ptr(r), 0, 1,
+                                   _lib.ptr(old), 1, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w.float(), bias, stride=1, padding=1)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    ref = ref.relu().permute(0, 2, 3, 1)
+    got = out[:, 1:-1, 1:-1].float()
+    border = out.float().clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert float(border.abs().max()) == 0.0
+    assert rel_l2(got, ref) < 1e-3                       # fp16 output rounding only (2^-11 relative per element)
+    assert rel_l2(got, old.float()) < 1e-3
+    assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+
+
+def test_conv_with_bordered_output_equals_plain_output():
+    """cadre_conv2d_nhwc_bordered_out (layer2.0.conv1: 3x3 / stride 2, 64 -> 128, bordered input) writes exactly the
+    values of cadre_conv2d_nhwc into the interior of a [B][20][34][128] tensor and never touches the border."""
+    _lib, L, dt = _conv_ops()
+    B, H, W, Cin, Cout = 5, 36, 64, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xp = torch.zeros(B, H + 2, W + 2, Cin, device="cuda", dtype=dt)
+    xp[:, 1:-1, 1:-1] = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(dt)
+    w_k = (torch.randn(Cout, 9 * Cin, device="cuda", generator=g) / 24.0).to(dt)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    plain = torch.zeros(B, 18, 32, Cout, device="cuda", dtype=dt)
+    _lib.check(L.cadre_conv2d_nhwc(_lib.ptr(xp), B, H, W, Cin, _lib.ptr(w_k), Cout, 3, 3, 2, 1, _lib.ptr(bias), None, 0, 1,
+                                   _lib.ptr(plain), 1, _lib.stream_ptr()))
+    bord = torch.full((B, 20, 34, Cout), -3.0, device="cuda", dtype=dt)
+    _lib.check(L.cadre_conv2d_nhwc_bordered_out(_lib.ptr(xp), B, H, W, Cin, _lib.ptr(w_k), Cout, 3, 3, 2, 1, _lib.ptr(bias),
+                                                1, _lib.ptr(bord), 1, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(bord[:, 1:-1, 1:-1], plain) and float(plain.float().abs().max()) > 0
+    edge = bord.clone()
+    edge[:, 1:-1, 1:-1] = -3.0
+    assert bool((edge == -3.0).all())
+
+
+def test_layer2_halo_path_matches_default_path_and_oracle():
+    """The encoder with layer2 on zero-bordered activations (CADRE_LAYER2_HALO, read when the encoder is created) against
+    the implicit-GEMM layer2 and the oracle, at a ragged batch and at the benchmarked chunk size."""
+    from cadre_b200.encoder import Encoder
+    sd = R.danet_fixture_state(0)
+    keep = os.environ.get("CADRE_LAYER2_HALO")
+    try:
+        os.environ["CADRE_LAYER2_HALO"] = "1"
+        halo = Encoder(sd, "cuda:0", max_batch=640)
+        os.environ["CADRE_LAYER2_HALO"] = "0"
+        plain = Encoder(sd, "cuda:0", max_batch=640)
+    finally:
+        if keep is None:
+            os.environ.pop("CADRE_LAYER2_HALO", None)
+        else:
+            os.environ["CADRE_LAYER2_HALO"] = keep
+    x = torch.from_numpy(np.random.RandomState(11).rand(7, 4, 144, 256).astype(np.float32)).cuda()
+    a, b = halo.forward_f32(x).cpu(), plain.forward_f32(x).cpu()
+    assert halo.launches_per_forward == plain.launches_per_forward
+    with torch.no_grad():
+        ref = R.encoder_latent(x.cpu(), sd)
+    assert rel_l2(a, b) < 2e-3 and rel_l2(a, ref) < REL_FEATURE
+    rgb, route, meas = _u8_frames(640, seed=91)
+    d = [t.cuda() for t in (rgb, route, meas)]
+    fa, fb = halo.forward_u8(*d).clone(), plain.forward_u8(*d).clone()
+    torch.cuda.synchronize()
+    assert rel_l2(fa[:, :512], fb[:, :512]) < 2e-3 and torch.equal(fa[:, 512:], fb[:, 512:])
+    fa2 = halo.forward_u8(*d)                   # the bordered buffers keep their zero border across forwards
+    torch.cuda.synchronize()
+    assert torch.equal(fa, fa2)

@@ -88,7 +88,8 @@ static Encoder* encoder_create(const cadre_encoder_weights* w, int max_batch) {
   for (int i = 0; i < 4; ++i) e->act[i] = dev_alloc<enc_t>(B * 36 * 64 * 64, false);
   for (int i = 0; i < 3; ++i) e->padact[i] = dev_alloc<enc_t>(B * 38 * 66 * 64, true);  // borders stay zero
   e->fuse_ds = getenv("CADRE_NO_SHORTCUT_FUSION") == nullptr;   // A/B switch kept for the fused-shortcut parity test
-  e->halo2 = e->fuse_ds && getenv("CADRE_LAYER2_HALO") != nullptr && atoi(getenv("CADRE_LAYER2_HALO")) != 0;
+  // default on; CADRE_LAYER2_HALO=0 keeps layer2 on the implicit-GEMM kernel (A/B switch, read when the encoder is created)
+  e->halo2 = e->fuse_ds && !(getenv("CADRE_LAYER2_HALO") != nullptr && atoi(getenv("CADRE_LAYER2_HALO")) == 0);
   if (e->halo2)
     for (int i = 0; i < 3; ++i) e->pad2[i] = dev_alloc<enc_t>(B * 20 * 34 * 128, true);  // borders stay zero
   if (e->fuse_ds) {

@@ -409,18 +409,30 @@ void launch_halo128(const FlatArgs& a, cudaStream_t stream) {
   make_map(&p.tmXa, 2, 2, a.in, dims, str, box_a);
   make_map(&p.tmXb, 2, 2, a.in, dims, str, box_b);
   make_map(&p.tmY, 2, 2, a.out, dims, str, box_b);
+  if (a.res) make_map(&p.tmR, 2, 2, a.res, dims, str, box_b);
   const uint64_t wdims[2] = {1152, 128};
   const uint64_t wstr[1] = {1152 * 2};
-  const uint32_t wbox[2] = {64, 128};
+  const uint32_t wbox[2] = {64, 64};
   make_map(&p.tmW, 2, 2, a.w, wdims, wstr, wbox);
   p.P = static_cast<int>(P), p.H = a.H, p.W = a.W, p.PW = PW;
   p.num_tiles = static_cast<int>((P + 127) / 128);
   p.num_groups = (p.num_tiles + 1) / 2;
+  p.num_pairs = (p.num_groups + 1) / 2;
   p.bias = a.bias, p.res = a.res, p.act = a.act;
   static size_t configured[CADRE_MAX_DEVICES] = {};   // per instantiation and device
   ensure_dynamic_smem(tc_halo128_kernel, HALO_SMEM, configured);
-  const int grid = p.num_groups < num_sms() ? p.num_groups : num_sms();
-  launch_k(tc_halo128_kernel, dim3(grid), dim3(320), HALO_SMEM, stream, p);
+  int clusters = num_sms() / 2;
+  if (p.num_pairs < clusters) clusters = p.num_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = HALO_SMEM, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  CADRE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_halo128_kernel, p));
   CADRE_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -8,6 +8,12 @@
 //   * the weights (nine taps x two Cin halves x [128 cout][64 cin] = 288 KB) cannot stay resident: they stream through a
 //     ring of 16 KB tiles, and every weight tile is used by BOTH tiles of the group before it is released, which halves
 //     the weight traffic per output pixel: 2 x 41 KB + 18 x 16 KB = 370 KB per 256 pixels = 185 KB per 128 (was 432 KB);
+//   * CTAs run as PAIRS (tcgen05.mma.cta_group::2, M = 256): the pair's two CTAs hold one tile each in the upper / lower
+//     128 accumulator rows and each CTA keeps only HALF of every weight tile (64 cout rows, 8 KB) in its ring. A
+//     128x128x16 MMA reads 4 KB of A + 4 KB of B per 64 cycles = 128 B/clk, the whole shared-memory bandwidth of an SM -
+//     measured without pairs: tensor pipe 64 % with the TMA writes and the epilogue staging competing for the same
+//     banks; the pair form reads 4 + 2 KB per CTA and MMA (96 B/clk), halves the weight bytes each CTA pulls from L2 and
+//     doubles the ring depth (12 tiles in flight in the same 96 KB);
 //   * four TMEM accumulators (2 tiles x 2 groups in flight, all 512 columns), eight epilogue warps: the residual of the
 //     BasicBlock is prefetched from global memory while the MMAs run (the main loop is 4x longer per tile than layer1's,
 //     the epilogue has the slack), bias / ReLU / saturating fp16 pack, border pixels forced back to zero, 128B-swizzled
@@ -20,10 +26,11 @@ namespace cadre {
 struct Halo128Params {
   CUtensorMap tmXa;   // [P][128] box {64, HALO_WIN_A}
   CUtensorMap tmXb;   // [P][128] box {64, 128}
-  CUtensorMap tmW;    // [128][1152] box {64, 128}
+  CUtensorMap tmW;    // [128][1152] box {64, 64}: one CTA's half (64 cout rows) of a (tap, Cin half) weight tile
   CUtensorMap tmY;    // [P][128] box {64, 128}
+  CUtensorMap tmR;    // residual [P][128] box {64, 128} (valid when res != nullptr)
   int P, H, W, PW;    // PW = W + 2
-  int num_tiles, num_groups;
+  int num_tiles, num_groups, num_pairs;   // a cluster of two CTAs takes the group pair (2m, 2m + 1)
   const float* bias;
   const enc_t* res;   // padded flat, 128 channels, or nullptr
   int act;
@@ -32,11 +39,13 @@ struct Halo128Params {
 constexpr int HALO_WIN_A = 200;                               // rows of the first TMA box (25 KB: keeps the second 1 KB aligned)
 constexpr int HALO_WIN_ROWS = HALO_WIN_A + 128;               // 328 >= 256 + 2*35 + 2
 constexpr int HALO_WIN_BYTES = HALO_WIN_ROWS * 128;           // one Cin half of a group's window
-constexpr int HALO_W_BYTES = 128 * 128;                       // one (tap, Cin half) weight tile
-constexpr int HALO_NW = 6;                                    // weight tiles in flight
+constexpr int HALO_W_BYTES = 64 * 128;                        // this CTA's half (64 cout rows) of a (tap, Cin half) weight tile
+constexpr int HALO_NW = 9;                                    // weight tiles in flight (what fits next to the residual tile)
 constexpr int HALO_OUT_BYTES = 2 * 128 * 128;                 // one output tile: two 64-channel groups
-constexpr int HALO_NBAR = 2 + 2 + 2 * HALO_NW + 4 + 4;
-constexpr int HALO_SMEM = 2 * HALO_WIN_BYTES + HALO_NW * HALO_W_BYTES + HALO_OUT_BYTES + HALO_NBAR * 8 + 16 + 1024;
+constexpr int HALO_RES_BYTES = HALO_OUT_BYTES;                // the next tile's residual, same layout as the staging tile
+constexpr int HALO_NBAR = 2 + 2 + 2 * HALO_NW + 4 + 4 + 1;
+constexpr int HALO_SMEM =
+    2 * HALO_WIN_BYTES + HALO_NW * HALO_W_BYTES + HALO_OUT_BYTES + HALO_RES_BYTES + HALO_NBAR * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constant__ Halo128Params p) {
   pdl_trigger();
@@ -45,13 +54,15 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
   uint8_t* win_s = smem;                                   // 2 x 41 KB (slot = Cin half)
   uint8_t* w_s = win_s + 2 * HALO_WIN_BYTES;               // HALO_NW x 16 KB
   uint8_t* out_s = w_s + HALO_NW * HALO_W_BYTES;           // 32 KB
-  uint64_t* win_full = reinterpret_cast<uint64_t*>(out_s + HALO_OUT_BYTES);   // [2]
+  uint8_t* res_s = out_s + HALO_OUT_BYTES;                 // 32 KB
+  uint64_t* win_full = reinterpret_cast<uint64_t*>(res_s + HALO_RES_BYTES);   // [2]
   uint64_t* win_empty = win_full + 2;                      // [2]
   uint64_t* w_full = win_empty + 2;                        // [HALO_NW]
   uint64_t* w_empty = w_full + HALO_NW;                    // [HALO_NW]
   uint64_t* tfull = w_empty + HALO_NW;                     // [4] accumulator = (group parity) * 2 + tile of the group
   uint64_t* tempty = tfull + 4;                            // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+  uint64_t* res_full = tempty + 4;                         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
   __shared__ __align__(16) float s_bias[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -61,28 +72,32 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmXb);
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmY);
+    if (p.res != nullptr) tma_prefetch_desc(&p.tmR);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&win_full[i], 1);
       mbar_init(&win_empty[i], 1);
     }
     for (int i = 0; i < HALO_NW; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_full[i], 1);    // used in the leader CTA only: both CTAs' halves complete bytes on it
+      mbar_init(&w_empty[i], 1);   // the leader's commit arrives on both CTAs' barriers
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);   // one arrival per epilogue warp
+      mbar_init(&tempty[i], 16);  // leader CTA: one arrival per epilogue warp of both CTAs
     }
+    mbar_init(res_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before either signals the other
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (converged warp, elected lane):
@@ -90,15 +105,17 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
     pdl_wait();   // the activations are written by the stream predecessor
     int lg = 0;
     unsigned wq = 0;   // weight tiles issued
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++lg) {
+    for (int m = cluster_id; m < p.num_pairs; m += num_clusters, ++lg) {
+      const int g = 2 * m + crank;           // g >= num_groups (odd group count): a dummy group of zero-filled windows
       const int row0 = g * 256 - p.PW - 1;   // may be negative / run past P: TMA zero-fills out-of-range rows
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         mbar_wait(&win_empty[h], (lg & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&win_full[h], HALO_WIN_BYTES);
-          tma_load_2d(win_s + h * HALO_WIN_BYTES, &p.tmXa, &win_full[h], h * 64, row0);
-          tma_load_2d(win_s + h * HALO_WIN_BYTES + HALO_WIN_A * 128, &p.tmXb, &win_full[h], h * 64, row0 + HALO_WIN_A);
+          // both CTAs load into their own shared memory; all bytes are accounted on the LEADER's barrier
+          if (crank == 0) mbar_expect_tx(&win_full[h], 2 * HALO_WIN_BYTES);
+          tma_load_2d_2sm(win_s + h * HALO_WIN_BYTES, &p.tmXa, &win_full[h], h * 64, row0);
+          tma_load_2d_2sm(win_s + h * HALO_WIN_BYTES + HALO_WIN_A * 128, &p.tmXb, &win_full[h], h * 64, row0 + HALO_WIN_A);
         }
         __syncwarp();
 #pragma unroll 1
@@ -106,20 +123,23 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
           const int slot = wq % HALO_NW;
           mbar_wait(&w_empty[slot], ((wq / HALO_NW) & 1) ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&w_full[slot], HALO_W_BYTES);
-            tma_load_2d(w_s + slot * HALO_W_BYTES, &p.tmW, &w_full[slot], t * 128 + h * 64, 0);
+            if (crank == 0) mbar_expect_tx(&w_full[slot], 2 * HALO_W_BYTES);
+            tma_load_2d_2sm(w_s + slot * HALO_W_BYTES, &p.tmW, &w_full[slot], t * 128 + h * 64, crank * 64);
           }
           __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
-    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 128, 128);
+    if (crank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of the pair; converged warp,
+    // elected lane). The descriptors address the same offsets in both CTAs: rows 0..127 of every M = 256 MMA are the
+    // leader's tile, rows 128..255 the peer's, each against its own window; B rows 0..63 / 64..127 likewise.
+    constexpr uint32_t idesc = umma_idesc(CADRE_ENC_FP16 ? 0u : 1u, 0, 0, 256, 128);
     const uint32_t win_addr0 = smem_u32(win_s), w_addr0 = smem_u32(w_s);
     int lg = 0;
     unsigned wq = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++lg) {
+    for (int m = cluster_id; m < p.num_pairs; m += num_clusters, ++lg) {
       const int buf = lg & 1;
       const uint32_t aph = (lg >> 1) & 1;
       mbar_wait(&tempty[buf * 2 + 0], aph ^ 1);
@@ -144,19 +164,20 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
               for (int k = 0; k < 4; ++k) {
                 const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, 2);
                 const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, 2);
-                tc_mma_f16(tacc, da, db, idesc, (h | t | k) != 0);
+                tc_mma_f16_2sm(tacc, da, db, idesc, (h | t | k) != 0);
               }
             }
-            tc_commit(&w_empty[slot]);
-            if (t == 8) tc_commit(&win_empty[h]);
+            tc_commit_2sm(&w_empty[slot]);
+            if (t == 8) tc_commit_2sm(&win_empty[h]);
             if (t == 8 && h == 1) {
-              tc_commit(&tfull[buf * 2 + 0]);
-              tc_commit(&tfull[buf * 2 + 1]);
+              tc_commit_2sm(&tfull[buf * 2 + 0]);
+              tc_commit_2sm(&tfull[buf * 2 + 1]);
             }
           }
           __syncwarp();
         }
       }
+    }
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue: 8 warps, 2 per TMEM lane quarter
@@ -167,29 +188,33 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
     const bool leader = (warp == 2 && lane == 0);
     const int img_pix = (p.H + 2) * p.PW;
     const bool has_res = p.res != nullptr;
-    int lg = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x, ++lg) {
+    // The BasicBlock residual (resnet.py:52) arrives by TMA, one tile ahead, in the layout of the staging tile: a thread
+    // finds its row's 16-byte chunks where it will write them. (Row-per-thread global loads - 32 cache lines per warp
+    // instruction - cost +26 us per conv, measured.)
+    auto request_residual = [&](int tile) {
+      mbar_expect_tx(res_full, HALO_RES_BYTES);
+      tma_load_2d(res_s, &p.tmR, res_full, 0, tile * 128);
+      tma_load_2d(res_s + 128 * 128, &p.tmR, res_full, 64, tile * 128);
+    };
+    if (has_res && leader && cluster_id < p.num_pairs) request_residual((2 * cluster_id + crank) * 2);
+    int lg = 0, lt = 0;
+    for (int m = cluster_id; m < p.num_pairs; m += num_clusters, ++lg) {
+      const int g = 2 * m + crank;
       const int buf = lg & 1;
       const uint32_t aph = (lg >> 1) & 1;
 #pragma unroll 1
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < 2; ++s, ++lt) {
         const int tile = g * 2 + s;
         const long long pix = static_cast<long long>(tile) * 128 + row;
         const int rem = static_cast<int>(pix % img_pix);
         const int y = rem / p.PW, x = rem - y * p.PW;
         const bool interior = pix < p.P && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
-        // this thread's residual half-row (64 channels = 128 bytes), requested before the accumulator is ready
-        uint4 rres[8];
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * 128 + half * 64);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rres[j] = interior ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
-        }
         if (leader) tma_store_wait_read();   // the previous tile's store has read the staging buffer
         epi_bar_sync256();
         const int acc = buf * 2 + s;
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
+        if (has_res) mbar_wait(res_full, lt & 1);
         const uint32_t taddr = tmem_base + acc * 128 + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -199,7 +224,7 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
           if (c == 1) {   // this warp's part of the accumulator is in registers
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -210,8 +235,11 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + bb[i];
+            const int chunk = c * 4 + j;                // 16-byte chunk inside this thread's 64-channel group
+            const int soff = half * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
             if (has_res) {
-              const enc_t* h8 = reinterpret_cast<const enc_t*>(&rres[c * 4 + j]);
+              const uint4 rr = *reinterpret_cast<const uint4*>(res_s + soff);
+              const enc_t* h8 = reinterpret_cast<const enc_t*>(&rr);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
             }
@@ -224,8 +252,7 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
               u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
             }
             if (!interior) u = make_uint4(0, 0, 0, 0);  // keep the zero border intact
-            const int chunk = c * 4 + j;                // 16-byte chunk inside this thread's 64-channel group
-            *reinterpret_cast<uint4*>(out_s + half * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = u;
+            *reinterpret_cast<uint4*>(out_s + soff) = u;
           }
         }
         fence_proxy_async_smem();
@@ -235,14 +262,18 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
           tma_store_2d(&p.tmY, out_s + 128 * 128, 64, tile * 128);
           tma_store_commit();
         }
+        if (has_res && leader) {              // every epilogue thread has read res_s (barrier above): fetch the next tile's
+          const int next = s == 0 ? tile + 1 : (m + num_clusters < p.num_pairs ? (2 * (m + num_clusters) + crank) * 2 : -1);
+          if (next >= 0) request_residual(next);
+        }
       }
     }
     if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();   // the peer may still arrive on this CTA's barriers / the leader's MMAs read the peer's smem
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 }  // namespace cadre

@@ -42,8 +42,8 @@ constexpr int HALO_WIN_BYTES = HALO_WIN_ROWS * 128;           // one Cin half of
 constexpr int HALO_W_BYTES = 64 * 128;                        // this CTA's half (64 cout rows) of a (tap, Cin half) weight tile
 constexpr int HALO_NW = 9;                                    // weight tiles in flight (what fits next to the residual tile)
 constexpr int HALO_OUT_BYTES = 2 * 128 * 128;                 // one output tile: two 64-channel groups
-constexpr int HALO_RES_BYTES = HALO_OUT_BYTES;                // the next tile's residual, same layout as the staging tile
-constexpr int HALO_NBAR = 2 + 2 + 2 * HALO_NW + 4 + 4 + 1;
+constexpr int HALO_RES_BYTES = HALO_OUT_BYTES;                // second staging tile (tiles alternate between the two)
+constexpr int HALO_NBAR = 2 + 2 + 2 * HALO_NW + 4 + 4 + 2;
 constexpr int HALO_SMEM =
     2 * HALO_WIN_BYTES + HALO_NW * HALO_W_BYTES + HALO_OUT_BYTES + HALO_RES_BYTES + HALO_NBAR * 8 + 16 + 1024;
 
@@ -54,15 +54,15 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
   uint8_t* win_s = smem;                                   // 2 x 41 KB (slot = Cin half)
   uint8_t* w_s = win_s + 2 * HALO_WIN_BYTES;               // HALO_NW x 16 KB
   uint8_t* out_s = w_s + HALO_NW * HALO_W_BYTES;           // 32 KB
-  uint8_t* res_s = out_s + HALO_OUT_BYTES;                 // 32 KB
+  uint8_t* res_s = out_s + HALO_OUT_BYTES;                 // 32 KB: staging tile of the odd tiles
   uint64_t* win_full = reinterpret_cast<uint64_t*>(res_s + HALO_RES_BYTES);   // [2]
   uint64_t* win_empty = win_full + 2;                      // [2]
   uint64_t* w_full = win_empty + 2;                        // [HALO_NW]
   uint64_t* w_empty = w_full + HALO_NW;                    // [HALO_NW]
   uint64_t* tfull = w_empty + HALO_NW;                     // [4] accumulator = (group parity) * 2 + tile of the group
   uint64_t* tempty = tfull + 4;                            // [4]
-  uint64_t* res_full = tempty + 4;                         // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+  uint64_t* res_full = tempty + 4;                         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
   __shared__ __align__(16) float s_bias[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 16);  // leader CTA: one arrival per epilogue warp of both CTAs
     }
-    mbar_init(res_full, 1);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -188,15 +189,17 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
     const bool leader = (warp == 2 && lane == 0);
     const int img_pix = (p.H + 2) * p.PW;
     const bool has_res = p.res != nullptr;
-    // The BasicBlock residual (resnet.py:52) arrives by TMA, one tile ahead, in the layout of the staging tile: a thread
-    // finds its row's 16-byte chunks where it will write them. (Row-per-thread global loads - 32 cache lines per warp
-    // instruction - cost +26 us per conv, measured.)
-    auto request_residual = [&](int tile) {
-      mbar_expect_tx(res_full, HALO_RES_BYTES);
-      tma_load_2d(res_s, &p.tmR, res_full, 0, tile * 128);
-      tma_load_2d(res_s + 128 * 128, &p.tmR, res_full, 64, tile * 128);
+    // Two staging tiles, used alternately. The BasicBlock residual (resnet.py:52) of a tile arrives by TMA IN its staging
+    // tile, one tile ahead: a thread finds its row's 16-byte chunks exactly where it will write the result, adds and
+    // overwrites them in place. (Row-per-thread global loads - 32 cache lines per warp instruction - cost +26 us per conv,
+    // one residual buffer requested after the previous tile's epilogue left ~1.5 us exposed on every second tile.)
+    auto request_residual = [&](int tile, int b) {
+      uint8_t* dst = b ? res_s : out_s;
+      mbar_expect_tx(&res_full[b], HALO_RES_BYTES);
+      tma_load_2d(dst, &p.tmR, &res_full[b], 0, tile * 128);
+      tma_load_2d(dst + 128 * 128, &p.tmR, &res_full[b], 64, tile * 128);
     };
-    if (has_res && leader && cluster_id < p.num_pairs) request_residual((2 * cluster_id + crank) * 2);
+    if (has_res && leader && cluster_id < p.num_pairs) request_residual((2 * cluster_id + crank) * 2, 0);
     int lg = 0, lt = 0;
     for (int m = cluster_id; m < p.num_pairs; m += num_clusters, ++lg) {
       const int g = 2 * m + crank;
@@ -209,12 +212,21 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
         const int rem = static_cast<int>(pix % img_pix);
         const int y = rem / p.PW, x = rem - y * p.PW;
         const bool interior = pix < p.P && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
-        if (leader) tma_store_wait_read();   // the previous tile's store has read the staging buffer
+        uint8_t* stage = (lt & 1) ? res_s : out_s;
+        if (leader) {
+          // this tile's staging buffer was last read by the store of tile lt-2; with a residual the OTHER buffer (store
+          // of tile lt-1) must be free as well: the next tile's residual lands there during this tile's epilogue
+          if (has_res) tma_store_wait_read(); else tma_store_wait_read1();
+          if (has_res) {
+            const int next = s == 0 ? tile + 1 : (m + num_clusters < p.num_pairs ? (2 * (m + num_clusters) + crank) * 2 : -1);
+            if (next >= 0) request_residual(next, (lt + 1) & 1);
+          }
+        }
         epi_bar_sync256();
         const int acc = buf * 2 + s;
         mbar_wait(&tfull[acc], aph);
         tc_fence_after();
-        if (has_res) mbar_wait(res_full, lt & 1);
+        if (has_res) mbar_wait(&res_full[lt & 1], (lt >> 1) & 1);
         const uint32_t taddr = tmem_base + acc * 128 + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
             const int chunk = c * 4 + j;                // 16-byte chunk inside this thread's 64-channel group
             const int soff = half * (128 * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
             if (has_res) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(res_s + soff);
+              const uint4 rr = *reinterpret_cast<const uint4*>(stage + soff);
               const enc_t* h8 = reinterpret_cast<const enc_t*>(&rr);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += enc_to_float(h8[i]);
@@ -252,19 +264,15 @@ __global__ void __launch_bounds__(320, 1) tc_halo128_kernel(const __grid_constan
               u.z = enc_pack2(v[4], v[5]), u.w = enc_pack2(v[6], v[7]);
             }
             if (!interior) u = make_uint4(0, 0, 0, 0);  // keep the zero border intact
-            *reinterpret_cast<uint4*>(out_s + soff) = u;
+            *reinterpret_cast<uint4*>(stage + soff) = u;
           }
         }
         fence_proxy_async_smem();
         epi_bar_sync256();
         if (leader && tile < p.num_tiles) {   // an odd tile count leaves the last group's second tile empty
-          tma_store_2d(&p.tmY, out_s, 0, tile * 128);
-          tma_store_2d(&p.tmY, out_s + 128 * 128, 64, tile * 128);
+          tma_store_2d(&p.tmY, stage, 0, tile * 128);
+          tma_store_2d(&p.tmY, stage + 128 * 128, 64, tile * 128);
           tma_store_commit();
-        }
-        if (has_res && leader) {              // every epilogue thread has read res_s (barrier above): fetch the next tile's
-          const int next = s == 0 ? tile + 1 : (m + num_clusters < p.num_pairs ? (2 * (m + num_clusters) + crank) * 2 : -1);
-          if (next >= 0) request_residual(next);
         }
       }
     }

@@ -6,18 +6,19 @@
 //   * one GROUP = two consecutive tiles of 128 flat pixels. Per group and 64-channel half of Cin ONE window of
 //     256 + 2*(W+2) + 2 input rows (41 KB) serves all nine taps of both tiles through row-shifted UMMA descriptors;
 //   * the weights (nine taps x two Cin halves x [128 cout][64 cin] = 288 KB) cannot stay resident: they stream through a
-//     ring of 16 KB tiles, and every weight tile is used by BOTH tiles of the group before it is released, which halves
-//     the weight traffic per output pixel: 2 x 41 KB + 18 x 16 KB = 370 KB per 256 pixels = 185 KB per 128 (was 432 KB);
+//     ring of (tap, Cin half) tiles, and every weight tile is used by BOTH tiles of the group before it is released, which
+//     halves the weight traffic per output pixel: 2 x 41 KB + 18 x 16 KB = 370 KB per 256 pixels = 185 KB per 128 (was
+//     432 KB), of which each CTA of a pair pulls half of the weight part;
 //   * CTAs run as PAIRS (tcgen05.mma.cta_group::2, M = 256): the pair's two CTAs hold one tile each in the upper / lower
 //     128 accumulator rows and each CTA keeps only HALF of every weight tile (64 cout rows, 8 KB) in its ring. A
 //     128x128x16 MMA reads 4 KB of A + 4 KB of B per 64 cycles = 128 B/clk, the whole shared-memory bandwidth of an SM -
 //     measured without pairs: tensor pipe 64 % with the TMA writes and the epilogue staging competing for the same
 //     banks; the pair form reads 4 + 2 KB per CTA and MMA (96 B/clk), halves the weight bytes each CTA pulls from L2 and
-//     doubles the ring depth (12 tiles in flight in the same 96 KB);
-//   * four TMEM accumulators (2 tiles x 2 groups in flight, all 512 columns), eight epilogue warps: the residual of the
-//     BasicBlock is prefetched from global memory while the MMAs run (the main loop is 4x longer per tile than layer1's,
-//     the epilogue has the slack), bias / ReLU / saturating fp16 pack, border pixels forced back to zero, 128B-swizzled
-//     staging tile, TMA store.
+//     deepens the ring (9 half tiles of 8 KB in flight: ~4.6 k MMA cycles of look-ahead). Measured: tensor pipe 87 %;
+//   * four TMEM accumulators (2 tiles x 2 groups in flight, all 512 columns), eight epilogue warps, two alternating
+//     128B-swizzled staging tiles: the residual of the BasicBlock (resnet.py:52) lands IN the staging tile by TMA one tile
+//     ahead and is overwritten in place by bias + residual -> ReLU -> saturating fp16 pack; border pixels are forced back
+//     to zero; TMA store.
 #pragma once
 #include "tc_flat3x3.cuh"
 
